@@ -1,0 +1,1002 @@
+// engine.cu -- host side of the statistics engine behind include/bamqc_b200.h: device memory, the
+// pinned double-buffered staging ring, record framing + the sequential coverage anchor scan
+// (src/OverallNumbers.hpp:79-110), kernel launches, the end-of-run merge helpers and result access.
+//
+// There is deliberately no CPU implementation of the statistics here: if CUDA is unavailable
+// bqc_create() fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <random>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/bamqc_b200.h"
+#include "kernels.cuh"
+
+using namespace bqc;
+
+static thread_local std::string g_last_error;
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t err__ = (call);                                                                \
+        if (err__ != cudaSuccess) {                                                                \
+            set_error(e, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+            return BQC_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+struct CovState {  // OverallNumbers::{first,id,shift} (src/OverallNumbers.hpp:37-41) + virtual window index
+    bool first = true;
+    int32_t id = 0;
+    uint32_t shift = 0;
+    uint64_t v1 = 0;         // absolute virtual index of the window held in v1
+    uint64_t flushed = 0;    // absolute virtual position up to which windows have been flushed
+};
+
+struct Segment {  // a run of records of one submission that fits the coverage ring
+    uint64_t r0, r1;
+    std::vector<uint64_t> base_window;  // per lane: window index that code 0 refers to
+    std::vector<uint64_t> flush_to;     // per lane: absolute virtual position to flush up to afterwards
+};
+
+struct DeviceBatch {
+    uint8_t* bytes = nullptr;
+    uint32_t* offsets = nullptr;
+    uint32_t* cov = nullptr;
+    uint8_t* rec_lane = nullptr;
+    uint64_t n_records = 0, n_bytes = 0;
+    uint32_t max_lseq = 0;
+    std::vector<Segment> segs;
+    uint64_t first_record = 0;
+    bool owns = false;
+    std::vector<CovState> cov_after;  // anchor state after this batch (resident path replays)
+    uint64_t records_after = 0;
+};
+struct bqc_batch {
+    DeviceBatch d;
+};
+
+struct Slot {  // one half of the staging double buffer
+    uint8_t* pinned = nullptr;
+    uint32_t* h_offsets = nullptr;
+    uint32_t* h_cov = nullptr;
+    uint8_t* h_lane = nullptr;
+    DeviceBatch dev;
+    cudaEvent_t done = nullptr;
+    bool in_flight = false;
+};
+
+struct bqc_engine {
+    bqc_config cfg;
+    std::vector<std::string> lane_ids;
+    std::unordered_map<std::string, uint32_t> lane_map;
+    std::vector<uint8_t> main_chrom;
+    std::vector<int32_t> klist;
+    std::vector<uint64_t> qlist;
+    Layout L;
+    int n_sm = 0;
+    uint32_t n_lanes = 1, n_qk = 1;
+    uint64_t sketch_words_per_qk = 0;  // uint32 words
+    uint64_t staging_bytes = 0, max_records_per_slot = 0;
+    uint32_t ring_log2 = 26;
+
+    // device state
+    uint64_t* d_counters = nullptr;
+    uint32_t* d_sketch = nullptr;
+    uint32_t* d_ring = nullptr;
+    uint32_t* d_cov_carry = nullptr;
+    uint32_t* d_cov_sums = nullptr;
+    uint64_t cov_sums_cap = 0;
+    unsigned long long* d_error = nullptr;
+    const uint32_t** d_ref = nullptr;
+    uint64_t* d_ref_len = nullptr;
+    uint8_t* d_main_chrom = nullptr;
+    HashTables* d_hash = nullptr;  // one per k
+    std::vector<uint32_t*> ref_bufs;
+    std::vector<uint64_t> ref_len;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    Slot slots[2];
+    int next_slot = 0;
+    cudaEvent_t copied = nullptr;
+
+    // host state
+    std::vector<CovState> cov;
+    uint64_t records_seen = 0, launches = 0;
+    bool finished = false;
+    std::string last_error;
+    bqc_error_info host_error = {0, 0, {0}};
+    int stats_blocks_per_sm = 0;
+
+    // results (after finish)
+    bool have_results = false;
+    std::vector<uint64_t> h_counters;
+    std::vector<uint32_t> h_sketch;
+};
+
+static void set_error(bqc_engine* e, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (e) e->last_error = buf;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RepHash tables (src/kmerstream/RepHash.cpp:4-17, RepHash.hpp:8-13,57-61)
+// ------------------------------------------------------------------------------------------------
+static const unsigned char kTwin[32] = {0,  20, 2,  7,  4,  5,  6,  3,  8,  9,  10, 11, 12, 13, 14, 15,
+                                        16, 17, 18, 19, 1,  21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31};
+static void build_hash_tables(int seed, int k, HashTables& T) {
+    uint64_t hv[32][2];  // [i][0]=hi [1]=lo
+    std::mt19937 mt((uint32_t)seed);  // == MTRand(seed).randInt() (mersennetwister.h); golden-tested
+    for (int i = 0; i < 32; ++i) {
+        uint64_t a = mt(), b = mt(), c = mt(), d = mt();
+        hv[i][0] = (a << 32) | b;
+        hv[i][1] = (c << 32) | d;
+    }
+    auto rotlk = [&](const uint64_t* x, uint64_t* o) {  // fastleftshiftk: 128-bit rotate left by k (1..63)
+        o[0] = (x[0] << k) | (x[1] >> (64 - k));
+        o[1] = (x[1] << k) | (x[0] >> (64 - k));
+    };
+    static const char nt16[] = "=ACMGRSVTWYHKDBN";
+    auto bitrev4 = [](int n) { return ((n & 1) << 3) | ((n & 2) << 1) | ((n & 4) >> 1) | ((n & 8) >> 3); };
+    memset(&T, 0, sizeof(T));
+    for (int s = 0; s < 2; ++s)
+        for (int n = 0; n < 16; ++n) {
+            int ch = nt16[s ? bitrev4(n) : n] & 31;  // reverse reads: IUPAC complement = nibble bit reversal (R7)
+            const uint64_t* fwd = hv[ch];
+            const uint64_t* twn = hv[kTwin[ch]];
+            const uint64_t* hsrc = s ? twn : fwd;  // table feeding the forward state h
+            const uint64_t* tsrc = s ? fwd : twn;  // table feeding the twin state ht
+            T.t[s][0][n][0] = hsrc[0];
+            T.t[s][0][n][1] = hsrc[1];
+            rotlk(hsrc, T.t[s][1][n]);
+            rotlk(tsrc, T.t[s][2][n]);
+            T.t[s][3][n][0] = tsrc[0];
+            T.t[s][3][n][1] = tsrc[1];
+        }
+}
+
+static size_t round_up_pow2(size_t size) {  // StreamCounter.hpp:11-21
+    size--;
+    size |= size >> 1; size |= size >> 2; size |= size >> 4; size |= size >> 8; size |= size >> 16; size |= size >> 32;
+    size++;
+    return size;
+}
+
+// ------------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------------
+static void free_device_batch(DeviceBatch& d) {
+    if (!d.owns) return;
+    cudaFree(d.bytes);
+    cudaFree(d.offsets);
+    cudaFree(d.cov);
+    cudaFree(d.rec_lane);
+    d = DeviceBatch();
+}
+
+extern "C" void bqc_destroy(bqc_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->compute) cudaStreamSynchronize(e->compute);
+    if (e->copy) cudaStreamSynchronize(e->copy);
+    for (auto& s : e->slots) {
+        if (s.pinned) cudaFreeHost(s.pinned);
+        if (s.h_offsets) cudaFreeHost(s.h_offsets);
+        if (s.h_cov) cudaFreeHost(s.h_cov);
+        if (s.h_lane) cudaFreeHost(s.h_lane);
+        free_device_batch(s.dev);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    for (auto p : e->ref_bufs) cudaFree(p);
+    cudaFree(e->d_counters);
+    cudaFree(e->d_sketch);
+    cudaFree(e->d_ring);
+    cudaFree(e->d_cov_carry);
+    cudaFree(e->d_cov_sums);
+    cudaFree(e->d_error);
+    cudaFree((void*)e->d_ref);
+    cudaFree(e->d_ref_len);
+    cudaFree(e->d_main_chrom);
+    cudaFree(e->d_hash);
+    if (e->copied) cudaEventDestroy(e->copied);
+    if (e->compute) cudaStreamDestroy(e->compute);
+    if (e->copy) cudaStreamDestroy(e->copy);
+    delete e;
+}
+
+extern "C" const char* bqc_last_error(bqc_engine* e) { return e ? e->last_error.c_str() : g_last_error.c_str(); }
+
+static int alloc_device_batch(bqc_engine* e, DeviceBatch& d, uint64_t bytes_cap, uint64_t rec_cap) {
+    d.owns = true;
+    CU(cudaMalloc(&d.bytes, bytes_cap + 256));
+    CU(cudaMemset(d.bytes, 0, bytes_cap + 256));
+    CU(cudaMalloc(&d.offsets, (rec_cap + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&d.cov, (rec_cap + 1) * sizeof(uint32_t)));
+    if (e->n_lanes > 1) CU(cudaMalloc(&d.rec_lane, rec_cap + 1));
+    return 0;
+}
+
+extern "C" int bqc_reset(bqc_engine* e) {
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->compute));
+    CU(cudaStreamSynchronize(e->copy));
+    CU(cudaMemsetAsync(e->d_counters, 0, e->n_lanes * e->L.lane_stride * 8, e->compute));
+    CU(cudaMemsetAsync(e->d_sketch, 0, e->n_lanes * e->n_qk * e->sketch_words_per_qk * 4, e->compute));
+    CU(cudaMemsetAsync(e->d_ring, 0, (uint64_t)e->n_lanes * (1ull << e->ring_log2) * 4, e->compute));
+    CU(cudaMemsetAsync(e->d_cov_carry, 0, e->n_lanes * 4, e->compute));
+    CU(cudaMemsetAsync(e->d_error, 0xFF, 8, e->compute));
+    e->cov.assign(e->n_lanes, CovState());
+    e->records_seen = 0;
+    e->finished = false;
+    e->have_results = false;
+    e->host_error.code = 0;
+    for (auto& s : e->slots) s.in_flight = false;
+    return 0;
+}
+
+extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
+    bqc_engine* e = nullptr;
+    if (!cfg || !out) { set_error(nullptr, "bqc_create: null argument"); return BQC_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        set_error(nullptr, "bqc_create: no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(ce));
+        return BQC_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { set_error(nullptr, "bqc_create: bad device %d", cfg->device); return BQC_ERR_ARG; }
+    if (cfg->n_lanes < 1 || cfg->n_k < 0 || cfg->n_q < 0 || cfg->isize < 0) { set_error(nullptr, "bqc_create: bad configuration"); return BQC_ERR_ARG; }
+    if (cfg->seed == 0) { set_error(nullptr, "bqc_create: seed 0 (time-based hash seed, src/kmerstream/RepHash.cpp:5-7) is not reproducible and is rejected"); return BQC_ERR_ARG; }
+    for (int i = 0; i < cfg->n_k; ++i)
+        if (cfg->klist[i] < 1 || cfg->klist[i] > 63) { set_error(nullptr, "bqc_create: k must be in 1..63 (src/kmerstream/RepHash.hpp:34-35)"); return BQC_ERR_ARG; }
+    e = new bqc_engine();
+    e->cfg = *cfg;
+    e->n_lanes = (uint32_t)cfg->n_lanes;
+    for (int i = 0; i < cfg->n_lanes; ++i) {
+        e->lane_ids.push_back(cfg->lane_ids ? cfg->lane_ids[i] : "");
+        e->lane_map[e->lane_ids.back()] = (uint32_t)i;  // later duplicates overwrite, like laneNames[id] = size
+    }
+    e->main_chrom.assign(cfg->main_chrom, cfg->main_chrom + cfg->n_ref);
+    e->klist.assign(cfg->klist, cfg->klist + cfg->n_k);
+    e->qlist.assign(cfg->q_cutoff, cfg->q_cutoff + cfg->n_q);
+    e->n_qk = (uint32_t)(cfg->n_k * cfg->n_q);
+    // StreamCounter geometry (src/kmerstream/StreamCounter.hpp:25-38)
+    double er = cfg->e;
+    size_t numcounts = (size_t)(48.0 / (er * er) + 1);
+    size_t f2size = round_up_pow2((size_t)(2.0 / (er * er) + 1));
+    if (numcounts < 8192) numcounts = 8192;
+    size_t sksize = round_up_pow2((numcounts + 15) / 16);
+    if (f2size > (1u << 26) || sksize > (1u << 24)) { set_error(e, "bqc_create: -e %g needs tables beyond the supported size", er); delete e; return BQC_ERR_ARG; }
+    uint32_t cyc = cfg->max_read_len > 0 ? (uint32_t)cfg->max_read_len : 512u;
+    cyc = pad8(cyc);
+    e->L = make_layout(cyc, (uint32_t)cfg->isize, e->n_qk, (uint32_t)f2size, (uint32_t)sksize);
+    e->sketch_words_per_qk = 32ull * sksize * 2ull;
+    e->staging_bytes = cfg->staging_bytes ? cfg->staging_bytes : (256ull << 20);
+    if (e->staging_bytes > 0xF0000000ull) e->staging_bytes = 0xF0000000ull;
+    e->max_records_per_slot = e->staging_bytes / 40 + 16;  // a record is at least 36 bytes
+    e->ring_log2 = cfg->cov_ring_log2 ? cfg->cov_ring_log2 : 26;
+    if (e->ring_log2 < 13 || e->ring_log2 > 30) { set_error(e, "bqc_create: cov_ring_log2 out of range"); delete e; return BQC_ERR_ARG; }
+
+    int rc = [&]() -> int {
+        CU(cudaSetDevice(cfg->device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, cfg->device));
+        e->n_sm = prop.multiProcessorCount;
+        CU(cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&e->copied, cudaEventDisableTiming));
+        CU(cudaMalloc(&e->d_counters, e->n_lanes * e->L.lane_stride * 8));
+        CU(cudaMalloc(&e->d_sketch, std::max<uint64_t>(4, e->n_lanes * e->n_qk * e->sketch_words_per_qk * 4)));
+        CU(cudaMalloc(&e->d_ring, (uint64_t)e->n_lanes * (1ull << e->ring_log2) * 4));
+        CU(cudaMalloc(&e->d_cov_carry, e->n_lanes * 4));
+        e->cov_sums_cap = ((1ull << e->ring_log2) + kCovChunk - 1) / kCovChunk + 1;
+        CU(cudaMalloc(&e->d_cov_sums, e->cov_sums_cap * 4));
+        CU(cudaMalloc(&e->d_error, 8));
+        int nref = std::max(1, cfg->n_ref);
+        CU(cudaMalloc((void**)&e->d_ref, nref * sizeof(uint32_t*)));
+        CU(cudaMemset((void*)e->d_ref, 0, nref * sizeof(uint32_t*)));
+        CU(cudaMalloc(&e->d_ref_len, nref * 8));
+        CU(cudaMemset(e->d_ref_len, 0, nref * 8));
+        CU(cudaMalloc(&e->d_main_chrom, nref));
+        CU(cudaMemset(e->d_main_chrom, 0, nref));
+        if (cfg->n_ref) CU(cudaMemcpy(e->d_main_chrom, e->main_chrom.data(), cfg->n_ref, cudaMemcpyHostToDevice));
+        e->ref_bufs.assign(nref, nullptr);
+        e->ref_len.assign(nref, 0);
+        if (cfg->n_k) {
+            std::vector<HashTables> ht(cfg->n_k);
+            for (int i = 0; i < cfg->n_k; ++i) build_hash_tables(cfg->seed, cfg->klist[i], ht[i]);
+            CU(cudaMalloc(&e->d_hash, sizeof(HashTables) * cfg->n_k));
+            CU(cudaMemcpy(e->d_hash, ht.data(), sizeof(HashTables) * cfg->n_k, cudaMemcpyHostToDevice));
+        }
+        for (auto& s : e->slots) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        // opt in to large dynamic shared memory
+        CU(cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(k_eightmer, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        CU(cudaFuncSetAttribute(k_sketch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        return 0;
+    }();
+    if (rc) { g_last_error = e->last_error; bqc_destroy(e); return rc; }
+    rc = bqc_reset(e);
+    if (rc) { g_last_error = e->last_error; bqc_destroy(e); return rc; }
+    *out = e;
+    return 0;
+}
+
+extern "C" int bqc_set_reference(bqc_engine* e, int32_t rid, const uint8_t* packed, uint64_t n_bases) {
+    if (rid < 0 || rid >= e->cfg.n_ref) { set_error(e, "bqc_set_reference: rid %d out of range", rid); return BQC_ERR_ARG; }
+    CU(cudaSetDevice(e->cfg.device));
+    uint64_t words = (n_bases + 15) / 16 + 4;  // +4: the triplet walk may touch one word past the end
+    uint32_t* buf = nullptr;
+    CU(cudaMalloc(&buf, words * 4));
+    CU(cudaMemset(buf, 0, words * 4));
+    CU(cudaMemcpy(buf, packed, (n_bases + 3) / 4, cudaMemcpyHostToDevice));
+    if (e->ref_bufs[rid]) cudaFree(e->ref_bufs[rid]);
+    e->ref_bufs[rid] = buf;
+    e->ref_len[rid] = n_bases;
+    CU(cudaMemcpy((void*)(e->d_ref + rid), &buf, sizeof(buf), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_ref_len + rid, &n_bases, 8, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host framing + coverage anchor scan
+// ------------------------------------------------------------------------------------------------
+static inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+extern "C" uint64_t bqc_frame_records(const uint8_t* data, size_t n, uint64_t* offsets, uint64_t cap) {
+    uint64_t nrec = 0;
+    size_t p = 0;
+    while (p + 4 <= n) {
+        uint32_t bs = rd32(data + p);
+        if (bs < 32 || p + 4 + (size_t)bs > n) break;
+        if (nrec + 1 >= cap) break;
+        offsets[nrec++] = p;
+        p += 4 + (size_t)bs;
+    }
+    if (cap) offsets[nrec] = p;
+    return nrec;
+}
+
+// lane of a record from its RG:Z tag (only needed when the header declares several read groups)
+static uint32_t host_lane(const bqc_engine* e, const uint8_t* r, uint32_t avail) {
+    uint32_t lname = r[12], ncig = r[16] | (r[17] << 8);
+    int32_t lseq = (int32_t)rd32(r + 20);
+    uint64_t pos = 36ull + lname + 4ull * ncig + ((uint64_t)(lseq > 0 ? lseq : 0) + 1) / 2 + (uint64_t)(lseq > 0 ? lseq : 0);
+    while (pos + 3 <= avail) {
+        uint8_t k0 = r[pos], k1 = r[pos + 1], ty = r[pos + 2];
+        pos += 3;
+        uint64_t sz;
+        switch (ty) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'Z': case 'H': { uint64_t q = pos; while (q < avail && r[q]) ++q; sz = q - pos + 1; break; }
+            case 'B': { if (pos + 5 > avail) return 0; uint8_t sub = r[pos]; uint32_t cnt = rd32(r + pos + 1); sz = 5ull + (uint64_t)cnt * ((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4); break; }
+            default: return 0;
+        }
+        if (k0 == 'R' && k1 == 'G') {
+            if (ty != 'Z') return 0;
+            uint64_t end = std::min<uint64_t>(pos + sz, avail);
+            std::string v((const char*)r + pos, (const char*)r + end);
+            while (!v.empty() && v.back() == '\0') v.pop_back();
+            auto it = e->lane_map.find(v);
+            return it == e->lane_map.end() ? 0u : it->second;  // unknown RG aliases lane 0 (laneNames[...] inserts 0)
+        }
+        pos += sz;
+    }
+    return 0;
+}
+
+// Walk the records of a submission once: 32-bit offsets, per-record lane, the coverage anchor scan
+// (the only order-dependent part of the reference, src/OverallNumbers.hpp:84-110) and the segments
+// that keep the coverage ring within capacity.
+static int host_scan(bqc_engine* e, const uint8_t* data, const uint64_t* offs, uint64_t n_records, uint32_t* o32, uint32_t* cov, uint8_t* lane_out, uint32_t& max_lseq, std::vector<Segment>& segs) {
+    const uint64_t ring_size = 1ull << e->ring_log2;
+    auto open_segment = [&](uint64_t r0) {
+        Segment s;
+        s.r0 = r0;
+        s.r1 = r0;
+        s.base_window.resize(e->n_lanes);
+        s.flush_to.resize(e->n_lanes);
+        for (uint32_t l = 0; l < e->n_lanes; ++l) s.base_window[l] = e->cov[l].flushed / 1000;
+        segs.push_back(s);
+    };
+    auto close_segment = [&](uint64_t r1) {
+        Segment& s = segs.back();
+        s.r1 = r1;
+        for (uint32_t l = 0; l < e->n_lanes; ++l) {
+            s.flush_to[l] = e->cov[l].v1 * 1000;
+            e->cov[l].flushed = s.flush_to[l];
+        }
+    };
+    segs.clear();
+    open_segment(0);
+    max_lseq = 0;
+    const uint64_t base_off = offs[0];
+    for (uint64_t r = 0; r < n_records; ++r) {
+        const uint8_t* p = data + offs[r];
+        uint64_t rel = offs[r] - base_off;
+        o32[r] = (uint32_t)rel;
+        uint32_t avail = (uint32_t)(offs[r + 1] - offs[r]);
+        uint32_t code = kNone;
+        uint32_t lane = 0;
+        if (avail >= 36) {
+            int32_t rid = (int32_t)rd32(p + 4);
+            uint32_t b = rd32(p + 8);
+            uint32_t flag = p[18] | (p[19] << 8);
+            int32_t lseq = (int32_t)rd32(p + 20);
+            if (lseq > 0 && (uint32_t)lseq > max_lseq) max_lseq = (uint32_t)lseq;
+            if (e->n_lanes > 1) lane = host_lane(e, p, avail);
+            bool q = !(flag & 0x900u) && (flag & 0xC0u) && !(flag & 0x4u) && !(flag & 0x400u) && rid >= 0 && rid < e->cfg.n_ref && e->main_chrom[rid];
+            if (q) {
+                CovState& st = e->cov[lane];
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    CovState t = st;
+                    if (t.first) { t.first = false; t.id = rid; t.shift = b; }
+                    if (t.id != rid || (uint32_t)(b - t.shift) > 2000u) { t.id = rid; t.v1 += 2; t.shift = b; }
+                    uint32_t pos = b - t.shift;
+                    if (pos > 1000u && pos < 2000u) { t.v1 += 1; t.shift += 1000u; pos = b - t.shift; }
+                    // everything this record can touch must fit the ring behind the unflushed position
+                    if (t.v1 * 1000 + 2001 - t.flushed > ring_size - 8 && attempt == 0 && r > segs.back().r0) {
+                        close_segment(r);
+                        open_segment(r);
+                        continue;
+                    }
+                    st = t;
+                    code = (uint32_t)((t.v1 - segs.back().base_window[lane]) << 11) | pos;
+                    break;
+                }
+            }
+        }
+        cov[r] = code;
+        if (lane_out) lane_out[r] = (uint8_t)lane;
+    }
+    o32[n_records] = (uint32_t)(offs[n_records] - base_off);
+    close_segment(n_records);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel launches for one device-resident batch
+// ------------------------------------------------------------------------------------------------
+static int launch_cov_flush(bqc_engine* e, uint32_t lane, uint64_t from_abs, uint64_t to_abs) {
+    if (to_abs <= from_abs) return 0;
+    uint64_t len = to_abs - from_abs;
+    uint32_t mask = (uint32_t)((1ull << e->ring_log2) - 1);
+    uint32_t* ring = e->d_ring + (uint64_t)lane * (1ull << e->ring_log2);
+    uint32_t start = (uint32_t)(from_abs & mask);
+    uint64_t nchunks = (len + kCovChunk - 1) / kCovChunk;
+    if (nchunks > e->cov_sums_cap) { set_error(e, "coverage flush larger than the ring"); return BQC_ERR_ARG; }
+    int grid = (int)std::min<uint64_t>(nchunks, (uint64_t)e->n_sm * 2);
+    unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
+    k_cov_chunk_sums<<<grid, 1024, 0, e->compute>>>(ring, mask, start, len, e->d_cov_sums);
+    k_cov_scan_sums<<<1, 1024, 0, e->compute>>>(e->d_cov_sums, nchunks, e->d_cov_carry + lane);
+    k_cov_apply<<<grid, 1024, 0, e->compute>>>(ring, mask, start, len, e->d_cov_sums, poscov);
+    e->launches += 3;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static EngineView make_view(bqc_engine* e) {
+    EngineView E;
+    E.L = e->L;
+    E.counters = e->d_counters;
+    E.sketch = e->d_sketch;
+    E.ring = e->d_ring;
+    E.ring_mask = (uint32_t)((1ull << e->ring_log2) - 1);
+    E.ref = e->d_ref;
+    E.ref_len = e->d_ref_len;
+    E.main_chrom = e->d_main_chrom;
+    E.n_ref = e->cfg.n_ref;
+    E.error = e->d_error;
+    E.insert_smem = std::min<uint32_t>(pad8(e->L.isize1), 4096u);
+    return E;
+}
+
+static int run_device_batch(bqc_engine* e, const DeviceBatch& d) {
+    EngineView E = make_view(e);
+    uint32_t cycb = pad8(std::max<uint32_t>(d.max_lseq, 8u));
+    if (cycb > e->L.cyc) cycb = e->L.cyc;  // longer reads are reported as unsupported by the kernel
+    StatsSmem S = stats_smem_layout(cycb, E.insert_smem);
+    size_t stats_smem = (size_t)S.total * 4;
+    int bps = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats, (int)kStatsThreads, stats_smem));
+    if (bps < 1) { set_error(e, "k_stats does not fit: %zu bytes of shared memory", stats_smem); return BQC_ERR_ARG; }
+    e->stats_blocks_per_sm = bps;
+    const uint64_t ring_size = 1ull << e->ring_log2;
+    for (const Segment& sg : d.segs) {
+        uint64_t n = sg.r1 - sg.r0;
+        for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
+            if (n) {
+                BatchView B;
+                B.bytes = d.bytes;
+                B.offsets = d.offsets + sg.r0;
+                B.cov = d.cov + sg.r0;
+                B.rec_lane = d.rec_lane ? d.rec_lane + sg.r0 : nullptr;
+                B.n_records = (uint32_t)n;
+                B.cycb = cycb;
+                B.first_record = d.first_record + sg.r0;
+                B.ring_base = (uint32_t)((sg.base_window[lane] * 1000) & (ring_size - 1));
+                int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * bps);
+                k_stats<<<grid, kStatsThreads, stats_smem, e->compute>>>(E, B, lane);
+                int g8 = (int)std::min<uint64_t>(2 * ((n + kEightThreads - 1) / kEightThreads), (uint64_t)(e->n_sm & ~1));
+                if (g8 < 2) g8 = 2;
+                k_eightmer<<<g8, kEightThreads, 32768 * 4, e->compute>>>(E, B, lane);
+                e->launches += 2;
+                for (uint32_t qi = 0; qi < e->qlist.size(); ++qi)
+                    for (uint32_t ki = 0; ki < e->klist.size(); ++ki) {
+                        SketchParams SP;
+                        SP.k = (uint32_t)e->klist[ki];
+                        SP.q_thresh = (int32_t)(int8_t)(char)(e->cfg.q_base + e->qlist[qi]);
+                        SP.qk = qi * (uint32_t)e->klist.size() + ki;
+                        int gs = (int)std::min<uint64_t>((n + kSketchThreads - 1) / kSketchThreads, (uint64_t)e->n_sm);
+                        if (e->L.f2size <= 32768u)
+                            k_sketch<true><<<gs, kSketchThreads, e->L.f2size * 4, e->compute>>>(E, B, lane, SP, e->d_hash + ki);
+                        else
+                            k_sketch<false><<<gs, kSketchThreads, 0, e->compute>>>(E, B, lane, SP, e->d_hash + ki);
+                        e->launches += 1;
+                    }
+            }
+            // flush the coverage windows this segment completed
+            uint64_t from = sg.base_window[lane] * 1000;
+            int rc = launch_cov_flush(e, lane, from, sg.flush_to[lane]);
+            if (rc) return rc;
+        }
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming path
+// ------------------------------------------------------------------------------------------------
+static int ensure_slot(bqc_engine* e, Slot& s) {
+    if (s.pinned) return 0;
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaHostAlloc((void**)&s.pinned, e->staging_bytes + 256, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&s.h_offsets, (e->max_records_per_slot + 1) * 4, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&s.h_cov, (e->max_records_per_slot + 1) * 4, cudaHostAllocDefault));
+    if (e->n_lanes > 1) CU(cudaHostAlloc((void**)&s.h_lane, e->max_records_per_slot + 1, cudaHostAllocDefault));
+    return alloc_device_batch(e, s.dev, e->staging_bytes, e->max_records_per_slot);
+}
+
+extern "C" int bqc_acquire_staging(bqc_engine* e, void** pinned, size_t* capacity) {
+    Slot& s = e->slots[e->next_slot];
+    int rc = ensure_slot(e, s);
+    if (rc) return rc;
+    if (s.in_flight) {
+        CU(cudaEventSynchronize(s.done));
+        s.in_flight = false;
+    }
+    *pinned = s.pinned;
+    *capacity = e->staging_bytes;
+    return 0;
+}
+
+extern "C" int bqc_submit(bqc_engine* e, const void* data, size_t n_bytes, const uint64_t* record_offsets, uint64_t n_records) {
+    if (e->finished) { set_error(e, "bqc_submit after bqc_finish (call bqc_reset)"); return BQC_ERR_ARG; }
+    if (n_bytes > e->staging_bytes) { set_error(e, "bqc_submit: %zu bytes exceed the staging capacity %llu", n_bytes, (unsigned long long)e->staging_bytes); return BQC_ERR_ARG; }
+    CU(cudaSetDevice(e->cfg.device));
+    Slot& s = e->slots[e->next_slot];
+    int rc = ensure_slot(e, s);
+    if (rc) return rc;
+    if (s.in_flight) {
+        CU(cudaEventSynchronize(s.done));
+        s.in_flight = false;
+    }
+    const uint8_t* src = (const uint8_t*)data;
+    std::vector<uint64_t> own_offsets;
+    if (!record_offsets) {
+        own_offsets.resize(e->max_records_per_slot + 1);
+        n_records = bqc_frame_records(src, n_bytes, own_offsets.data(), own_offsets.size());
+        if (own_offsets[n_records] != n_bytes) {
+            e->host_error.code = BQC_ERR_BAD_RECORD;
+            e->host_error.record = e->records_seen + n_records;
+            set_error(e, "bqc_submit: bytes do not end on a record boundary");
+            return BQC_ERR_BAD_RECORD;
+        }
+        record_offsets = own_offsets.data();
+    }
+    if (n_records > e->max_records_per_slot) { set_error(e, "bqc_submit: too many records for one staging buffer"); return BQC_ERR_ARG; }
+    if (n_records == 0) return 0;
+    DeviceBatch& d = s.dev;
+    rc = host_scan(e, src, record_offsets, n_records, s.h_offsets, s.h_cov, s.h_lane, d.max_lseq, d.segs);
+    if (rc) return rc;
+    const uint8_t* first = src + record_offsets[0];
+    size_t span = (size_t)(record_offsets[n_records] - record_offsets[0]);
+    const uint8_t* h2d_src = first;
+    if (first < s.pinned || first + span > s.pinned + e->staging_bytes + 256) {  // not our pinned buffer: stage it
+        memcpy(s.pinned, first, span);
+        h2d_src = s.pinned;
+    }
+    d.n_records = n_records;
+    d.n_bytes = span;
+    d.first_record = e->records_seen;
+    CU(cudaMemcpyAsync(d.bytes, h2d_src, span, cudaMemcpyHostToDevice, e->copy));
+    CU(cudaMemcpyAsync(d.offsets, s.h_offsets, (n_records + 1) * 4, cudaMemcpyHostToDevice, e->copy));
+    CU(cudaMemcpyAsync(d.cov, s.h_cov, n_records * 4, cudaMemcpyHostToDevice, e->copy));
+    if (e->n_lanes > 1) CU(cudaMemcpyAsync(d.rec_lane, s.h_lane, n_records, cudaMemcpyHostToDevice, e->copy));
+    CU(cudaEventRecord(e->copied, e->copy));
+    CU(cudaStreamWaitEvent(e->compute, e->copied, 0));
+    rc = run_device_batch(e, d);
+    if (rc) return rc;
+    CU(cudaEventRecord(s.done, e->compute));
+    s.in_flight = true;
+    e->records_seen += n_records;
+    e->next_slot ^= 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// resident path
+// ------------------------------------------------------------------------------------------------
+extern "C" int bqc_batch_prepare(bqc_engine* e, const void* data, size_t n_bytes, const uint64_t* record_offsets, uint64_t n_records, bqc_batch** out) {
+    *out = nullptr;
+    if (n_bytes >= 0xFFFFFF00ull) { set_error(e, "bqc_batch_prepare: a batch must be smaller than 4 GiB"); return BQC_ERR_ARG; }
+    CU(cudaSetDevice(e->cfg.device));
+    const uint8_t* src = (const uint8_t*)data;
+    std::vector<uint64_t> own_offsets;
+    if (!record_offsets) {
+        own_offsets.resize(n_bytes / 36 + 2);
+        n_records = bqc_frame_records(src, n_bytes, own_offsets.data(), own_offsets.size());
+        record_offsets = own_offsets.data();
+    }
+    bqc_batch* b = new bqc_batch();
+    DeviceBatch& d = b->d;
+    int rc = alloc_device_batch(e, d, n_bytes, n_records);
+    if (rc) { free_device_batch(d); delete b; return rc; }
+    std::vector<uint32_t> o32(n_records + 1), cov(n_records + 1);
+    std::vector<uint8_t> lanes(e->n_lanes > 1 ? n_records + 1 : 0);
+    host_scan(e, src, record_offsets, n_records, o32.data(), cov.data(), lanes.empty() ? nullptr : lanes.data(), d.max_lseq, d.segs);
+    size_t span = n_records ? (size_t)(record_offsets[n_records] - record_offsets[0]) : 0;
+    d.n_records = n_records;
+    d.n_bytes = span;
+    d.first_record = e->records_seen;
+    e->records_seen += n_records;
+    d.cov_after = e->cov;
+    d.records_after = e->records_seen;
+    if (n_records) {
+        CU(cudaMemcpy(d.bytes, src + record_offsets[0], span, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.offsets, o32.data(), (n_records + 1) * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.cov, cov.data(), n_records * 4, cudaMemcpyHostToDevice));
+        if (e->n_lanes > 1) CU(cudaMemcpy(d.rec_lane, lanes.data(), n_records, cudaMemcpyHostToDevice));
+    }
+    *out = b;
+    return 0;
+}
+extern "C" int bqc_batch_run(bqc_engine* e, bqc_batch* b) {
+    CU(cudaSetDevice(e->cfg.device));
+    if (e->finished) { set_error(e, "bqc_batch_run after bqc_finish (call bqc_reset)"); return BQC_ERR_ARG; }
+    e->cov = b->d.cov_after;  // replaying a prepared batch restores the anchor state that follows it
+    e->records_seen = b->d.records_after;
+    return run_device_batch(e, b->d);
+}
+extern "C" void bqc_batch_free(bqc_engine* e, bqc_batch* b) {
+    if (!b) return;
+    if (e) cudaSetDevice(e->cfg.device);
+    free_device_batch(b->d);
+    delete b;
+}
+extern "C" uint64_t bqc_batch_records(const bqc_batch* b) { return b->d.n_records; }
+extern "C" uint64_t bqc_batch_bytes(const bqc_batch* b) { return b->d.n_bytes; }
+
+// ------------------------------------------------------------------------------------------------
+// completion
+// ------------------------------------------------------------------------------------------------
+static const char* reference_message(int code) {
+    switch (code) {
+        case BQC_ERR_RG_NOT_Z: return "Read does not have Z";
+        case BQC_ERR_NO_MATE_FLAG: return "ERROR: No first or second flag in read";
+        case BQC_ERR_AS_TAG: return "ERROR: Read has no AS tag / could not read AS tag";
+        case BQC_ERR_BAD_RECORD: return "ERROR: Could not read record from BAM File";
+        case BQC_ERR_NO_RG: return "ERROR: record without RG tag";
+        case BQC_ERR_UNSUPPORTED: return "ERROR: value outside the engine's table capacities (read length / histogram index)";
+        default: return "";
+    }
+}
+
+extern "C" int bqc_get_error(bqc_engine* e, bqc_error_info* out) {
+    memset(out, 0, sizeof(*out));
+    if (e->host_error.code) { *out = e->host_error; return 0; }
+    CU(cudaSetDevice(e->cfg.device));
+    unsigned long long key = ~0ull;
+    CU(cudaMemcpy(&key, e->d_error, 8, cudaMemcpyDeviceToHost));
+    if (key != ~0ull) {
+        out->code = (int32_t)(key & 255);
+        out->record = key >> 8;
+        snprintf(out->message, sizeof(out->message), "%s (record %llu)", reference_message(out->code), (unsigned long long)out->record);
+    }
+    return 0;
+}
+
+extern "C" int bqc_sync(bqc_engine* e) {
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->copy));
+    CU(cudaStreamSynchronize(e->compute));
+    bqc_error_info ei;
+    int rc = bqc_get_error(e, &ei);
+    if (rc) return rc;
+    if (ei.code) set_error(e, "%s", ei.message);
+    return ei.code;
+}
+
+extern "C" int32_t bqc_n_lanes(bqc_engine* e) { return (int32_t)e->n_lanes; }
+extern "C" const char* bqc_lane_id(bqc_engine* e, int32_t lane) { return (lane >= 0 && (uint32_t)lane < e->n_lanes) ? e->lane_ids[lane].c_str() : ""; }
+extern "C" void bqc_qk_lists(bqc_engine* e, const int32_t** klist, uint32_t* n_k, const uint64_t** qlist, uint32_t* n_q) {
+    *klist = e->klist.data();
+    *n_k = (uint32_t)e->klist.size();
+    *qlist = e->qlist.data();
+    *n_q = (uint32_t)e->qlist.size();
+}
+extern "C" void* bqc_stream(bqc_engine* e) { return (void*)e->compute; }
+extern "C" uint64_t bqc_kernel_launches(bqc_engine* e) { return e->launches; }
+
+extern "C" int bqc_finish(bqc_engine* e) {
+    CU(cudaSetDevice(e->cfg.device));
+    if (!e->finished) {
+        // src/bamqualcheck.cpp:447-453: update_coverage(); update_vectors(); update_coverage() for every lane
+        for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
+            CovState& st = e->cov[lane];
+            uint64_t to = (st.v1 + 2) * 1000;
+            int rc = launch_cov_flush(e, lane, st.flushed, to);
+            if (rc) return rc;
+            st.flushed = to;
+            st.v1 += 2;
+        }
+        e->finished = true;
+    }
+    e->have_results = false;
+    return bqc_sync(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU merge helpers
+// ------------------------------------------------------------------------------------------------
+extern "C" uint64_t bqc_counters_len(bqc_engine* e) { return (uint64_t)e->n_lanes * e->L.lane_stride; }
+extern "C" int bqc_counters_export(bqc_engine* e, void* dev) {
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaMemcpyAsync(dev, e->d_counters, bqc_counters_len(e) * 8, cudaMemcpyDeviceToDevice, e->compute));
+    CU(cudaStreamSynchronize(e->compute));
+    return 0;
+}
+extern "C" int bqc_counters_import(bqc_engine* e, const void* dev) {
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaMemcpyAsync(e->d_counters, dev, bqc_counters_len(e) * 8, cudaMemcpyDeviceToDevice, e->compute));
+    CU(cudaStreamSynchronize(e->compute));
+    e->have_results = false;
+    return 0;
+}
+extern "C" uint64_t bqc_sketch_len(bqc_engine* e) { return (uint64_t)e->n_lanes * e->n_qk * e->sketch_words_per_qk * 8; }
+extern "C" int bqc_sketch_export_u8(bqc_engine* e, void* dev) {
+    CU(cudaSetDevice(e->cfg.device));
+    uint64_t nwords = bqc_sketch_len(e) / 8;
+    if (nwords) {
+        k_sketch_export_u8<<<e->n_sm * 8, 256, 0, e->compute>>>(e->d_sketch, nwords, (uint8_t*)dev);
+        e->launches += 1;
+    }
+    CU(cudaStreamSynchronize(e->compute));
+    return 0;
+}
+extern "C" int bqc_sketch_import_u8(bqc_engine* e, const void* dev) {
+    CU(cudaSetDevice(e->cfg.device));
+    uint64_t nwords = bqc_sketch_len(e) / 8;
+    if (nwords) {
+        k_sketch_import_u8<<<e->n_sm * 8, 256, 0, e->compute>>>(e->d_sketch, nwords, (const uint8_t*)dev);
+        e->launches += 1;
+    }
+    CU(cudaStreamSynchronize(e->compute));
+    e->have_results = false;
+    return 0;
+}
+extern "C" int bqc_merge_from(bqc_engine* dst, bqc_engine* src) {
+    bqc_engine* e = dst;
+    if (bqc_counters_len(dst) != bqc_counters_len(src) || bqc_sketch_len(dst) != bqc_sketch_len(src)) { set_error(e, "bqc_merge_from: engines differ in configuration"); return BQC_ERR_ARG; }
+    CU(cudaSetDevice(src->cfg.device));
+    CU(cudaStreamSynchronize(src->compute));
+    CU(cudaSetDevice(dst->cfg.device));
+    uint64_t nc = bqc_counters_len(dst), nw = bqc_sketch_len(dst) / 8;
+    uint64_t* tc = nullptr;
+    uint32_t* ts = nullptr;
+    CU(cudaMalloc(&tc, nc * 8));
+    CU(cudaMalloc(&ts, std::max<uint64_t>(4, nw * 4)));
+    CU(cudaMemcpyPeerAsync(tc, dst->cfg.device, src->d_counters, src->cfg.device, nc * 8, dst->compute));
+    if (nw) CU(cudaMemcpyPeerAsync(ts, dst->cfg.device, src->d_sketch, src->cfg.device, nw * 4, dst->compute));
+    k_counters_add<<<dst->n_sm * 4, 256, 0, dst->compute>>>((unsigned long long*)dst->d_counters, (const unsigned long long*)tc, nc);
+    if (nw) k_sketch_merge<<<dst->n_sm * 8, 256, 0, dst->compute>>>(dst->d_sketch, ts, nw);
+    dst->launches += 2;
+    CU(cudaStreamSynchronize(dst->compute));
+    cudaFree(tc);
+    cudaFree(ts);
+    dst->have_results = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+static int fetch_results(bqc_engine* e) {
+    if (e->have_results) return 0;
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->compute));
+    e->h_counters.resize(bqc_counters_len(e));
+    e->h_sketch.resize(bqc_sketch_len(e) / 8);
+    CU(cudaMemcpy(e->h_counters.data(), e->d_counters, e->h_counters.size() * 8, cudaMemcpyDeviceToHost));
+    if (!e->h_sketch.empty()) CU(cudaMemcpy(e->h_sketch.data(), e->d_sketch, e->h_sketch.size() * 4, cudaMemcpyDeviceToHost));
+    e->have_results = true;
+    return 0;
+}
+
+static uint64_t top_nonzero(const uint64_t* p, uint64_t n) {  // highest non-zero index + 1
+    while (n && p[n - 1] == 0) --n;
+    return n;
+}
+
+extern "C" int bqc_result_table(bqc_engine* e, int32_t lane, int32_t field, int32_t sub, uint64_t* out, uint64_t cap, uint64_t* n_out) {
+    int rc = fetch_results(e);
+    if (rc) return rc;
+    if (lane < 0 || (uint32_t)lane >= e->n_lanes) { set_error(e, "bqc_result_table: bad lane"); return BQC_ERR_ARG; }
+    const Layout& L = e->L;
+    const uint64_t* G = e->h_counters.data() + (uint64_t)lane * L.lane_stride;
+    const uint64_t* src = nullptr;
+    uint64_t n = 0;
+    auto mateblk = [&](int m) { return G + L.o_mate0 + (uint64_t)m * L.mate_stride; };
+    auto maxlen = [&](int m) { uint64_t t = top_nonzero(mateblk(m) + L.m_readlen, L.cyc + 1); return t ? t - 1 : 0; };  // max read length seen
+    auto seen = [&](int m) { return top_nonzero(mateblk(m) + L.m_readlen, L.cyc + 1) != 0; };
+    bool per_mate = field >= BQC_F_READLEN_M && field <= BQC_F_READNR_M;
+    if (per_mate && (sub < 0 || sub > 1)) { set_error(e, "bqc_result_table: mate must be 0 or 1"); return BQC_ERR_ARG; }
+    switch (field) {
+        case BQC_F_SCALARS: src = G + L.o_scalars; n = 13; break;
+        case BQC_F_POSCOV: src = G + L.o_poscov; n = 101; break;
+        case BQC_F_INSERT: src = G + L.o_insert; n = L.isize1; break;
+        case BQC_F_EIGHTMER: src = G + L.o_eightmer; n = kEightmer; break;
+        case BQC_F_TRIPLET: src = G + L.o_triplet; n = kTriplet; break;
+        case BQC_F_READLEN_M: src = mateblk(sub) + L.m_readlen; n = top_nonzero(src, L.cyc + 1); break;
+        case BQC_F_NCOUNT_M: src = mateblk(sub) + L.m_ncount; n = seen(sub) ? maxlen(sub) + 1 : 0; break;
+        case BQC_F_GCCOUNT_M: src = mateblk(sub) + L.m_gccount; n = seen(sub) ? maxlen(sub) + 1 : 0; break;
+        case BQC_F_AVGQUAL_M: src = mateblk(sub) + L.m_avgq; n = top_nonzero(mateblk(sub) + L.m_ceilq, kQCap); break;
+        case BQC_F_MAPQ_M: src = mateblk(sub) + L.m_mapq; n = top_nonzero(src, kMapqCap); break;
+        case BQC_F_MISMATCH_M: src = mateblk(sub) + L.m_mismatch; n = top_nonzero(src, L.mmcap); break;
+        case BQC_F_DEL_M: src = mateblk(sub) + L.m_del; n = top_nonzero(src, L.delcap); break;
+        case BQC_F_INS_M: src = mateblk(sub) + L.m_ins; n = top_nonzero(src, L.mmcap); break;
+        case BQC_F_DNA_A_M: case BQC_F_DNA_C_M: case BQC_F_DNA_G_M: case BQC_F_DNA_T_M: case BQC_F_DNA_N_M:
+            src = mateblk(sub) + L.m_pc + (uint64_t)(field - BQC_F_DNA_A_M) * pad8(L.cyc); n = maxlen(sub); break;
+        case BQC_F_QUALSUM_M: src = mateblk(sub) + L.m_pc + (uint64_t)PC_QUAL * pad8(L.cyc); n = maxlen(sub); break;
+        case BQC_F_SC5_M: src = mateblk(sub) + L.m_pc + (uint64_t)PC_SC5 * pad8(L.cyc); n = maxlen(sub); break;
+        case BQC_F_SC3_M: src = mateblk(sub) + L.m_pc + (uint64_t)PC_SC3 * pad8(L.cyc); n = maxlen(sub); break;
+        case BQC_F_READNR_M: src = mateblk(sub) + L.m_readnr; n = 1; break;
+        case BQC_F_SUMCOUNT_QK:
+            if (sub < 0 || (uint32_t)sub >= e->n_qk) { set_error(e, "bqc_result_table: bad (q,k) index"); return BQC_ERR_ARG; }
+            src = G + L.o_qk + (uint64_t)sub * L.qk_stride; n = 1; break;
+        case BQC_F_F2TABLE_QK:
+            if (sub < 0 || (uint32_t)sub >= e->n_qk) { set_error(e, "bqc_result_table: bad (q,k) index"); return BQC_ERR_ARG; }
+            src = G + L.o_qk + (uint64_t)sub * L.qk_stride + 8; n = L.f2size; break;
+        default: set_error(e, "bqc_result_table: unknown field %d", field); return BQC_ERR_ARG;
+    }
+    if (n_out) *n_out = n;
+    if (out) {
+        if (cap < n) { set_error(e, "bqc_result_table: buffer too small"); return BQC_ERR_ARG; }
+        memcpy(out, src, n * 8);
+    }
+    return 0;
+}
+
+extern "C" int bqc_result_sketch(bqc_engine* e, int32_t lane, int32_t qk, uint64_t* out, uint64_t cap, uint64_t* n_out) {
+    int rc = fetch_results(e);
+    if (rc) return rc;
+    if (lane < 0 || (uint32_t)lane >= e->n_lanes || qk < 0 || (uint32_t)qk >= e->n_qk) { set_error(e, "bqc_result_sketch: bad index"); return BQC_ERR_ARG; }
+    uint64_t n = e->sketch_words_per_qk / 2;
+    if (n_out) *n_out = n;
+    if (out) {
+        if (cap < n) { set_error(e, "bqc_result_sketch: buffer too small"); return BQC_ERR_ARG; }
+        memcpy(out, e->h_sketch.data() + ((uint64_t)lane * e->n_qk + qk) * e->sketch_words_per_qk, n * 8);
+    }
+    return 0;
+}
+
+// (size_t)(double) as g++ compiles it on x86-64, including NaN -> 2^63 (empty sketch)
+static uint64_t double_to_size(double v) {
+    if (std::isnan(v)) return 9223372036854775808ULL;
+    if (v >= 9223372036854775808.0) return (uint64_t)(int64_t)(v - 9223372036854775808.0) ^ 0x8000000000000000ULL;
+    return (uint64_t)(int64_t)v;
+}
+
+// KmerStream estimators from per-level nibble statistics (src/kmerstream/StreamCounter.hpp:114-172,308-317)
+extern "C" int bqc_result_estimates(bqc_engine* e, int32_t lane, int32_t qk, uint64_t out4[4]) {
+    int rc = fetch_results(e);
+    if (rc) return rc;
+    if (lane < 0 || (uint32_t)lane >= e->n_lanes || qk < 0 || (uint32_t)qk >= e->n_qk) { set_error(e, "bqc_result_estimates: bad index"); return BQC_ERR_ARG; }
+    const Layout& L = e->L;
+    const uint64_t* G = e->h_counters.data() + (uint64_t)lane * L.lane_stride + L.o_qk + (uint64_t)qk * L.qk_stride;
+    const uint32_t* sk = e->h_sketch.data() + ((uint64_t)lane * e->n_qk + qk) * e->sketch_words_per_qk;
+    const size_t R = (size_t)L.sk_size * 16;
+    size_t nz[32], r0[32], r1[32];
+    for (int lv = 0; lv < 32; ++lv) {
+        size_t z = 0, o = 0;
+        const uint32_t* w = sk + (uint64_t)lv * L.sk_size * 2;
+        for (uint32_t i = 0; i < L.sk_size * 2; ++i) {
+            uint32_t x = w[i];
+            for (int j = 0; j < 8; ++j) {
+                uint32_t v = (x >> (4 * j)) & 15u;
+                z += (v == 0);
+                o += (v == 1);
+            }
+        }
+        r0[lv] = z;
+        r1[lv] = o;
+        nz[lv] = R - z;
+    }
+    out4[0] = G[0];
+    {   // F0
+        double sum = 0;
+        int n = 0;
+        double limit = 0.2;
+        while (n == 0 && limit > 1e-8) {
+            for (size_t i = 0; i < 32; i++) {
+                size_t ts = nz[i];
+                if (ts <= (1 - limit) * R && ts >= limit * R) {
+                    double est = (log(1.0 - ts / ((double)R)) / log(1.0 - 1.0 / R)) * pow(2.0, i + 1);
+                    sum += est;
+                    n++;
+                    break;
+                }
+            }
+            limit = limit / 1.5;
+        }
+        out4[1] = double_to_size(sum / n);
+    }
+    {   // f1
+        double sum = 0;
+        int n = 0;
+        double limit = 0.2;
+        while (n == 0 && limit > 1e-8) {
+            for (size_t i = 0; i < 32; i++) {
+                if ((r0[i] <= (1 - limit) * R) && (r0[i] >= limit * R)) {
+                    sum += (R - 1) * (r1[i] / ((double)r0[i])) * pow(2.0, i + 1);
+                    n++;
+                    break;
+                }
+            }
+            limit = limit / 1.5;
+        }
+        out4[2] = double_to_size(sum / n);
+    }
+    {   // F2, sequential summation order as in the reference
+        double sum = 0, sqsum = 0;
+        for (size_t i = 0; i < L.f2size; i++) {
+            double c = (double)G[8 + i];
+            sum += c;
+            sqsum += c * c;
+        }
+        out4[3] = double_to_size(sqsum + (sqsum - sum * sum) / L.f2size);
+    }
+    return 0;
+}
+
+extern "C" int bqc_result_avgqual(bqc_engine* e, int32_t lane, int32_t mate, double* out, uint64_t cap, uint64_t* n_out) {
+    uint64_t n = 0;
+    int rc = bqc_result_table(e, lane, BQC_F_QUALSUM_M, mate, nullptr, 0, &n);
+    if (rc) return rc;
+    if (n_out) *n_out = n;
+    if (!out) return 0;
+    if (cap < n) { set_error(e, "bqc_result_avgqual: buffer too small"); return BQC_ERR_ARG; }
+    std::vector<uint64_t> q(n);
+    uint64_t nr = 0;
+    bqc_result_table(e, lane, BQC_F_QUALSUM_M, mate, q.data(), n, nullptr);
+    bqc_result_table(e, lane, BQC_F_READNR_M, mate, &nr, 1, nullptr);
+    unsigned readnr = (unsigned)nr;  // `unsigned qualcount_readnr` (src/QualityCheck.hpp:46)
+    for (uint64_t i = 0; i < n; ++i) out[i] = (q[i] / (double)readnr);  // src/QualityCheck.hpp:277
+    return 0;
+}

@@ -1,0 +1,680 @@
+// host_io.cpp -- the host front end that stays on CPU threads (BASELINE.json north_star): BGZF inflate,
+// BAM header parsing (the SeqAn BamStream stand-in, src/bamqualcheck.cpp:262,286,292), FASTA -> 2-bit
+// loading (replaces the streaming cursor of src/TripletCounting.hpp:60-104), the `.bamqc` writer
+// (src/bamqualcheck.cpp:156-233) and the `bamqualcheck` command line (src/CommandLineParser.hpp:43-149).
+// Everything here talks to the GPU engine only through include/bamqc_b200.h.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/bamqc_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// BAM header
+// ------------------------------------------------------------------------------------------------
+static char* dup_cstr(const std::string& s) {
+    char* p = (char*)malloc(s.size() + 1);
+    memcpy(p, s.data(), s.size());
+    p[s.size()] = 0;
+    return p;
+}
+
+extern "C" size_t bqc_parse_bam_header(const uint8_t* d, size_t n, bqc_bam_header* out) {
+    memset(out, 0, sizeof(*out));
+    if (n < 12 || memcmp(d, "BAM\1", 4) != 0) return 0;
+    int32_t l_text;
+    memcpy(&l_text, d + 4, 4);
+    if (l_text < 0 || 8 + (size_t)l_text + 4 > n) return 0;
+    std::string text((const char*)d + 8, (size_t)l_text);
+    size_t p = 8 + (size_t)l_text;
+    int32_t n_ref;
+    memcpy(&n_ref, d + p, 4);
+    p += 4;
+    if (n_ref < 0) return 0;
+    std::vector<std::string> names;
+    std::vector<int64_t> lens;
+    for (int i = 0; i < n_ref; ++i) {
+        if (p + 4 > n) return 0;
+        int32_t l_name;
+        memcpy(&l_name, d + p, 4);
+        p += 4;
+        if (l_name < 0 || p + (size_t)l_name + 4 > n) return 0;
+        names.push_back(std::string((const char*)d + p, l_name > 0 ? (size_t)l_name - 1 : 0));
+        p += (size_t)l_name;
+        int32_t l_ref;
+        memcpy(&l_ref, d + p, 4);
+        p += 4;
+        lens.push_back(l_ref);
+    }
+    // @RG lines: ID -> lane (order of appearance), last SM -> sample id (src/bamqualcheck.cpp:44-66)
+    std::vector<std::string> lanes;
+    std::map<std::string, unsigned> laneNames;
+    std::string sample;
+    std::istringstream hs(text);
+    std::string line;
+    while (std::getline(hs, line)) {
+        if (line.compare(0, 3, "@RG") != 0) continue;
+        std::istringstream ls(line);
+        std::string field;
+        bool firstField = true;
+        while (std::getline(ls, field, '\t')) {
+            if (firstField) { firstField = false; continue; }
+            if (field.size() < 3 || field[2] != ':') continue;
+            std::string key = field.substr(0, 2), value = field.substr(3);
+            if (key == "ID" && !laneNames.count(value)) {
+                laneNames[value] = (unsigned)lanes.size();
+                lanes.push_back(value);
+            }
+            if (key == "SM") sample = value;
+        }
+    }
+    out->text = dup_cstr(text);
+    out->n_ref = n_ref;
+    out->ref_names = (char**)calloc((size_t)std::max(1, n_ref), sizeof(char*));
+    out->ref_lengths = (int64_t*)calloc((size_t)std::max(1, n_ref), sizeof(int64_t));
+    for (int i = 0; i < n_ref; ++i) {
+        out->ref_names[i] = dup_cstr(names[i]);
+        out->ref_lengths[i] = lens[i];
+    }
+    out->n_lanes = (int32_t)lanes.size();
+    out->lane_ids = (char**)calloc(std::max<size_t>(1, lanes.size()), sizeof(char*));
+    for (size_t i = 0; i < lanes.size(); ++i) out->lane_ids[i] = dup_cstr(lanes[i]);
+    out->sample_id = dup_cstr(sample);
+    return p;
+}
+
+extern "C" void bqc_free_bam_header(bqc_bam_header* h) {
+    if (!h) return;
+    free(h->text);
+    for (int i = 0; i < h->n_ref; ++i) free(h->ref_names[i]);
+    free(h->ref_names);
+    free(h->ref_lengths);
+    for (int i = 0; i < h->n_lanes; ++i) free(h->lane_ids[i]);
+    free(h->lane_ids);
+    free(h->sample_id);
+    memset(h, 0, sizeof(*h));
+}
+
+// ------------------------------------------------------------------------------------------------
+// BGZF
+// ------------------------------------------------------------------------------------------------
+struct BgzfBlock {
+    uint64_t cbeg;   // start of the raw deflate payload
+    uint32_t clen;   // payload length
+    uint32_t isize;  // inflated size
+    uint64_t obeg;   // offset in the output
+};
+
+// Index the blocks of in[0..n).  Stops at the first incomplete block; returns bytes consumed.
+static uint64_t bgzf_index(const uint8_t* in, uint64_t n, std::vector<BgzfBlock>& blocks, uint64_t max_out, bool& bad) {
+    uint64_t p = 0, o = 0;
+    bad = false;
+    while (p + 18 <= n) {
+        if (in[p] != 0x1f || in[p + 1] != 0x8b || in[p + 2] != 8 || !(in[p + 3] & 4)) { bad = true; break; }
+        uint16_t xlen;
+        memcpy(&xlen, in + p + 10, 2);
+        if (p + 12 + xlen > n) break;
+        uint64_t x = p + 12, xend = x + xlen;
+        int bsize = -1;
+        while (x + 4 <= xend) {
+            uint16_t slen;
+            memcpy(&slen, in + x + 2, 2);
+            if (in[x] == 'B' && in[x + 1] == 'C' && slen == 2) {
+                uint16_t b;
+                memcpy(&b, in + x + 4, 2);
+                bsize = b;
+            }
+            x += 4 + slen;
+        }
+        if (bsize < 0) { bad = true; break; }
+        uint64_t blen = (uint64_t)bsize + 1;
+        if (p + blen > n) break;
+        if (blen < 12ull + xlen + 8) { bad = true; break; }
+        BgzfBlock b;
+        memcpy(&b.isize, in + p + blen - 4, 4);
+        if (o + b.isize > max_out) break;
+        b.cbeg = p + 12 + xlen;
+        b.clen = (uint32_t)(blen - 12 - xlen - 8);
+        b.obeg = o;
+        o += b.isize;
+        blocks.push_back(b);
+        p += blen;
+    }
+    return p;
+}
+
+static bool inflate_blocks(const uint8_t* in, const std::vector<BgzfBlock>& blocks, uint8_t* out, int threads) {
+    std::atomic<size_t> next(0);
+    std::atomic<bool> ok(true);
+    auto work = [&]() {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { ok = false; return; }
+        for (;;) {
+            size_t i0 = next.fetch_add(16);
+            if (i0 >= blocks.size()) break;
+            for (size_t i = i0; i < std::min(blocks.size(), i0 + 16); ++i) {
+                const BgzfBlock& b = blocks[i];
+                if (!b.isize) continue;
+                inflateReset(&zs);
+                zs.next_in = (Bytef*)(in + b.cbeg);
+                zs.avail_in = b.clen;
+                zs.next_out = out + b.obeg;
+                zs.avail_out = b.isize;
+                if (inflate(&zs, Z_FINISH) != Z_STREAM_END) ok = false;
+            }
+        }
+        inflateEnd(&zs);
+    };
+    threads = std::max(1, threads);
+    if (threads == 1 || blocks.size() < 32) {
+        work();
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+    }
+    return ok;
+}
+
+extern "C" uint64_t bqc_bgzf_inflate(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, int32_t threads) {
+    std::vector<BgzfBlock> blocks;
+    bool bad = false;
+    uint64_t used = bgzf_index(in, n, blocks, cap, bad);
+    if (bad || used != n) return 0;
+    if (!inflate_blocks(in, blocks, out, threads)) return 0;
+    return blocks.empty() ? 0 : blocks.back().obeg + blocks.back().isize;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FASTA -> 2 bit
+// ------------------------------------------------------------------------------------------------
+struct bqc_fasta {
+    std::vector<std::string> names;
+    std::vector<std::vector<uint8_t>> packed;
+    std::vector<int64_t> lengths;
+};
+
+extern "C" bqc_fasta* bqc_fasta_open(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return nullptr;
+    bqc_fasta* fa = new bqc_fasta();
+    std::vector<char> buf(1 << 22);
+    bool in_header = false, at_line_start = true;
+    std::string hdr;
+    std::vector<uint8_t>* cur = nullptr;
+    int64_t len = 0;
+    auto finish_header = [&]() {
+        std::string s = hdr.substr(0, hdr.find(' '));
+        s = s.substr(0, s.find('\t'));  // src/TripletCounting.hpp:99-102
+        while (!s.empty() && (s.back() == '\r' || s.back() == '\n')) s.pop_back();
+        if (cur) fa->lengths.back() = len;
+        fa->names.push_back(s);
+        fa->packed.emplace_back();
+        fa->lengths.push_back(0);
+        cur = &fa->packed.back();
+        len = 0;
+    };
+    size_t got;
+    while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) {
+        for (size_t i = 0; i < got; ++i) {
+            char c = buf[i];
+            if (in_header) {
+                if (c == '\n') { in_header = false; at_line_start = true; finish_header(); }
+                else hdr.push_back(c);
+                continue;
+            }
+            if (c == '\n') { at_line_start = true; continue; }
+            if (at_line_start && c == '>') { in_header = true; hdr.clear(); at_line_start = false; continue; }
+            at_line_start = false;
+            if (!cur || c == '\r' || c == ' ' || c == '\t') continue;
+            uint8_t code;
+            switch (c) {  // Dna5 -> Dna keeps the low two bits: N (4) -> A (0), SURVEY R6
+                case 'C': case 'c': code = 1; break;
+                case 'G': case 'g': code = 2; break;
+                case 'T': case 't': code = 3; break;
+                default: code = 0; break;
+            }
+            if ((len & 3) == 0) cur->push_back(0);
+            cur->back() |= (uint8_t)(code << ((len & 3) * 2));
+            ++len;
+        }
+    }
+    if (in_header) finish_header();
+    if (cur) fa->lengths.back() = len;
+    fclose(f);
+    for (auto& p : fa->packed) p.resize(p.size() + 16, 0);
+    return fa;
+}
+extern "C" int64_t bqc_fasta_contig(bqc_fasta* f, const char* name, const uint8_t** packed) {
+    for (size_t i = 0; i < f->names.size(); ++i)
+        if (f->names[i] == name) {
+            *packed = f->packed[i].data();
+            return f->lengths[i];
+        }
+    return -1;
+}
+extern "C" void bqc_fasta_close(bqc_fasta* f) { delete f; }
+
+// ------------------------------------------------------------------------------------------------
+// `.bamqc` writer  (src/bamqualcheck.cpp:130-233, src/OverallNumbers.hpp:170-216, src/TripletCounting.hpp:271-301)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Table {
+    std::vector<uint64_t> v;
+};
+bool get_table(bqc_engine* e, int lane, int field, int sub, std::vector<uint64_t>& v) {
+    uint64_t n = 0;
+    if (bqc_result_table(e, lane, field, sub, nullptr, 0, &n)) return false;
+    v.assign(n, 0);
+    return bqc_result_table(e, lane, field, sub, v.data(), n, nullptr) == 0;
+}
+void print_u32(std::ostream& o, const std::vector<uint64_t>& v) {  // String<unsigned>
+    for (uint64_t x : v) o << " " << (unsigned)x;
+    o << std::endl;
+}
+void print_u64(std::ostream& o, const std::vector<uint64_t>& v) {  // String<uint64_t>
+    for (uint64_t x : v) o << " " << x;
+    o << std::endl;
+}
+}  // namespace
+
+extern "C" int bqc_write_bamqc(bqc_engine* e, const char* sample_id, const char* path) {
+    std::ofstream out(path, std::ios::out | std::ios::binary);
+    if (!out.good()) return BQC_ERR_ARG;
+    // lanes in std::map<CharString> key order (src/bamqualcheck.cpp:163)
+    int n_lanes = bqc_n_lanes(e);
+    std::map<std::string, int> order;
+    for (int l = 0; l < n_lanes; ++l) order[bqc_lane_id(e, l)] = l;  // duplicates collapse like the reference map
+    uint32_t n_q = 0, n_k = 0;
+    const int32_t* klist = nullptr;
+    const uint64_t* qlist = nullptr;
+    bqc_qk_lists(e, &klist, &n_k, &qlist, &n_q);
+
+    for (auto& kv : order) {
+        int lane = kv.second;
+        std::vector<uint64_t> sc, t;
+        if (!get_table(e, lane, BQC_F_SCALARS, 0, sc)) return BQC_ERR_ARG;
+        out << "sample_id " << sample_id << std::endl;
+        out << "lane " << kv.first << std::endl;
+        out << "total_read_pairs " << (unsigned)sc[4] / 2 << std::endl;
+        out << "total_bps " << sc[5] << std::endl;
+        out << "supplementary_alignments " << (unsigned)sc[0] << std::endl;
+        out << "marked_duplicate " << (unsigned)sc[1] << std::endl;
+        out << "QC_failed " << (unsigned)sc[2] << std::endl;
+        out << "not_primary_alignment " << (unsigned)sc[3] << std::endl;
+        out << "both_reads_unmapped " << (unsigned)sc[6] << std::endl;
+        out << "first_read_unmapped " << (unsigned)sc[7] << std::endl;
+        out << "second_read_unmapped " << (unsigned)sc[8] << std::endl;
+        out << "first_and_or_second_read_mapped " << (unsigned)sc[9] << std::endl;
+        out << "FF_RR_oriented_pairs " << (unsigned)sc[10] << std::endl;
+        out << "total_proper_pairs " << (unsigned)sc[11] << std::endl;
+        out << "total_proper_pairs_autosome " << (unsigned)sc[12] << std::endl;
+        get_table(e, lane, BQC_F_POSCOV, 0, t);
+        out << "genome_coverage_histogram"; print_u32(out, t);
+        get_table(e, lane, BQC_F_INSERT, 0, t);
+        out << "insert_size_histogram"; print_u32(out, t);
+        struct { const char* name; int field; bool wide; } hists[] = {
+            {"read_length_histogram", BQC_F_READLEN_M, false}, {"N_count_histogram", BQC_F_NCOUNT_M, false},
+            {"GC_content_histogram", BQC_F_GCCOUNT_M, true},   {"average_base_qual_histogram", BQC_F_AVGQUAL_M, false},
+            {"mapping_qual_histogram", BQC_F_MAPQ_M, false},   {"mismatch_count_histogram", BQC_F_MISMATCH_M, false},
+            {"deletion_count_histogram", BQC_F_DEL_M, false},  {"insertion_count_histogram", BQC_F_INS_M, false},
+            {"Ns_by_position", BQC_F_DNA_N_M, true},           {"As_by_position", BQC_F_DNA_A_M, true},
+            {"Cs_by_position", BQC_F_DNA_C_M, true},           {"Gs_by_position", BQC_F_DNA_G_M, true},
+            {"Ts_by_position", BQC_F_DNA_T_M, true}};
+        for (auto& h : hists)
+            for (int m = 0; m < 2; ++m) {
+                get_table(e, lane, h.field, m, t);
+                out << h.name << (m ? "_second" : "_first");
+                if (h.wide) print_u64(out, t);
+                else print_u32(out, t);
+            }
+        for (int m = 0; m < 2; ++m) {
+            uint64_t n = 0;
+            bqc_result_avgqual(e, lane, m, nullptr, 0, &n);
+            std::vector<double> aq(n);
+            bqc_result_avgqual(e, lane, m, aq.data(), n, nullptr);
+            out << "average_base_qual_by_position" << (m ? "_second" : "_first");
+            for (double x : aq) out << " " << x;
+            out << std::endl;
+        }
+        for (int m = 0; m < 2; ++m) {
+            get_table(e, lane, BQC_F_SC5_M, m, t);
+            out << "soft_clipping_5_prime_by_position" << (m ? "_second" : "_first"); print_u32(out, t);
+            get_table(e, lane, BQC_F_SC3_M, m, t);
+            out << "soft_clipping_3_prime_by_position" << (m ? "_second" : "_first"); print_u32(out, t);
+        }
+        // ten_most_abundant_kmers: top 10 counts descending, equal counts by ascending table index
+        std::vector<uint64_t> em;
+        get_table(e, lane, BQC_F_EIGHTMER, 0, em);
+        {
+            std::vector<uint64_t> v(em);
+            std::partial_sort(v.begin(), v.begin() + 10, v.end(), std::greater<uint64_t>());
+            std::set<int> used;
+            for (int i = 0; i < 10; ++i) {
+                int pos = (int)(std::find(em.begin(), em.end(), v[i]) - em.begin());
+                while (used.count(pos)) pos = (int)(std::find(em.begin() + pos + 1, em.end(), v[i]) - em.begin());
+                used.insert(pos);
+                char kmer[9];
+                for (int b = 0; b < 8; ++b) kmer[b] = "ACGT"[(pos >> (2 * (7 - b))) & 3];
+                kmer[8] = 0;
+                out << "nr_" << i + 1 << "_most_abundant_8mer " << kmer << " " << v[i] << std::endl;
+            }
+        }
+        out << "8mer_count"; print_u64(out, em);
+        for (uint32_t i = 0; i < n_q; ++i)
+            for (uint32_t j = 0; j < n_k; ++j) {
+                uint64_t est[4];
+                if (bqc_result_estimates(e, lane, (int)(i * n_k + j), est)) return BQC_ERR_ARG;
+                out << klist[j] << "mer_count_after_qual_clipping_" << qlist[i] << " " << est[0] << std::endl;
+                out << "distinct_" << klist[j] << "mer_count_after_qual_clipping_" << qlist[i] << " " << est[1] << std::endl;
+                out << "unique_" << klist[j] << "mer_count_after_qual_clipping_" << qlist[i] << " " << est[2] << std::endl;
+                out << klist[j] << "mer_F2_after_qual_clipping_" << qlist[i] << " " << est[3] << std::endl;
+            }
+        std::vector<uint64_t> tr;
+        get_table(e, lane, BQC_F_TRIPLET, 0, tr);
+        const char bases[] = {'A', 'C', 'G', 'T'};
+        const struct { const char* suffix; int grp; } groups[] = {{"_1st_FW", 0}, {"_1st_RC", 2}, {"_2nd_FW", 1}, {"_2nd_RC", 3}};
+        for (int b = 0; b < 4; ++b)
+            for (auto& g : groups) {
+                out << "triplet_counts_" << bases[b] << g.suffix;
+                for (int ctx = 0; ctx < 64; ++ctx) out << " " << tr[(size_t)ctx * 16 + g.grp * 4 + b];
+                out << std::endl;
+            }
+    }
+    return out.good() ? 0 : BQC_ERR_ARG;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bamqualcheck command line
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Cli {
+    std::string bam, ref = "genome.fa", out;
+    std::string chroms =
+        "chr1,chr2,chr3,chr4,chr5,chr6,chr7,chr8,chr9,chr10,chr11,chr12,chr13,chr14,chr15,chr16,"
+        "chr17,chr18,chr19,chr20,chr21,chr22";
+    std::vector<int32_t> klist;
+    std::vector<uint64_t> qlist;
+    double e = 0.01;
+    int seed = 1, isize = 1000, device = 0, threads = 0;
+    bool timing = false;
+};
+bool read_file(const std::string& path, std::vector<uint8_t>& out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize((size_t)n);
+    size_t got = n ? fread(out.data(), 1, (size_t)n, f) : 0;
+    fclose(f);
+    return got == (size_t)n;
+}
+}  // namespace
+
+extern "C" int bqc_main(int argc, const char* const* argv) {
+    Cli c;
+    std::string kmer = "32", qcut = "17";
+    bool haveR = false, haveO = false;
+    std::vector<std::string> positional;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto need = [&](const char* name) -> std::string {
+            if (i + 1 >= argc) {
+                std::cerr << "bamqualcheck: option requires an argument -- " << name << std::endl;
+                exit(1);
+            }
+            return argv[++i];
+        };
+        if (a == "-h" || a == "--help") {
+            std::cout << "bamqualcheck [OPTIONS] BAMFILE\n  -r, --reference FILENAME   Reference genome filename.\n"
+                         "  -i, --insert-size INT      Upper bound for the insert size in insert size histogram. Default: 1000.\n"
+                         "  -c, --chromosomes STRING   Comma separated list of the main chromosome names.\n"
+                         "  -o, --output-file OUT      Output filename.\n  -k, --kmer-size STRING     Comma-separated list of k-mer sizes. Default: 32.\n"
+                         "  -q, --quality-cutoff STRING Comma-separated list of PHRED quality thresholds. Default: 17.\n"
+                         "  -e, --error-rate DOUBLE    Error rate guaranteed. Default: 0.01.\n  -s, --seed INT             Seed value for the randomness. Default: 1.\n"
+                         "  --device INT, --threads INT, --timing   (engine options)\n";
+            return 0;
+        }
+        if (a == "--version") { std::cout << "bamqualcheck version: dev (bamqc-b200)\n"; return 0; }
+        if (a == "-r" || a == "--reference") { c.ref = need("r"); haveR = true; }
+        else if (a == "-i" || a == "--insert-size") c.isize = atoi(need("i").c_str());
+        else if (a == "-c" || a == "--chromosomes") c.chroms = need("c");
+        else if (a == "-o" || a == "--output-file") { c.out = need("o"); haveO = true; }
+        else if (a == "-k" || a == "--kmer-size") kmer = need("k");
+        else if (a == "-q" || a == "--quality-cutoff") qcut = need("q");
+        else if (a == "-e" || a == "--error-rate") c.e = atof(need("e").c_str());
+        else if (a == "-s" || a == "--seed") c.seed = atoi(need("s").c_str());
+        else if (a == "--device") c.device = atoi(need("device").c_str());
+        else if (a == "--threads") c.threads = atoi(need("threads").c_str());
+        else if (a == "--timing") c.timing = true;
+        else positional.push_back(a);
+    }
+    if (!haveR || !haveO || positional.size() != 1) {
+        std::cerr << "bamqualcheck: options -r and -o and exactly one BAMFILE argument are required" << std::endl;
+        return 1;
+    }
+    c.bam = positional[0];
+    {   // src/CommandLineParser.hpp:121-141
+        std::stringstream sq(qcut);
+        size_t j;
+        while (sq >> j) { c.qlist.push_back(j); if (sq.peek() == ',') sq.ignore(); }
+        std::stringstream sk(kmer);
+        int i;
+        while (sk >> i) { c.klist.push_back(i); if (sk.peek() == ',') sk.ignore(); }
+    }
+    if (c.bam == "-") {
+        std::cerr << "ERROR: SAM on stdin is not supported by this engine (BAM files only)." << std::endl;
+        return 1;
+    }
+    if (c.threads <= 0) c.threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    auto t_start = std::chrono::steady_clock::now();
+    std::vector<uint8_t> file;
+    if (!read_file(c.bam, file)) {
+        std::cerr << "ERROR: Could not open " << c.bam << " for reading.\n";
+        return 1;
+    }
+    std::ofstream probe(c.out.c_str(), std::ios::out | std::ios::binary);
+    if (!probe.good()) {
+        std::cerr << "ERROR: Could not open output file " << c.out << '\n';
+        return 1;
+    }
+    probe.close();
+    const bool raw = file.size() >= 4 && memcmp(file.data(), "BAM\1", 4) == 0;
+
+    // ---- header: inflate a prefix large enough to hold it --------------------------------------------
+    std::vector<BgzfBlock> blocks;
+    std::vector<uint8_t> head;
+    size_t next_block = 0;
+    if (!raw) {
+        bool bad = false;
+        uint64_t used = bgzf_index(file.data(), file.size(), blocks, ~0ull, bad);
+        if (bad || used != file.size() || blocks.empty()) {
+            std::cerr << "ERROR: Could not open " << c.bam << " for reading.\n";
+            return 1;
+        }
+    }
+    bqc_bam_header hdr;
+    size_t hdr_bytes = 0;
+    if (raw) {
+        hdr_bytes = bqc_parse_bam_header(file.data(), file.size(), &hdr);
+    } else {
+        // grow the inflated prefix until the header parses
+        size_t nb = 0;
+        while (nb < blocks.size()) {
+            size_t take = std::min(blocks.size(), nb ? nb * 2 : (size_t)4);
+            std::vector<BgzfBlock> part(blocks.begin(), blocks.begin() + take);
+            head.resize(part.back().obeg + part.back().isize);
+            if (!inflate_blocks(file.data(), part, head.data(), c.threads)) {
+                std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
+                return 1;
+            }
+            nb = take;
+            hdr_bytes = bqc_parse_bam_header(head.data(), head.size(), &hdr);
+            if (hdr_bytes) break;
+        }
+        next_block = nb;
+    }
+    if (!hdr_bytes) {
+        std::cerr << "ERROR: Could not open " << c.bam << " for reading.\n";
+        return 1;
+    }
+
+    // ---- engine --------------------------------------------------------------------------------------
+    std::vector<uint8_t> main_chrom((size_t)std::max(1, hdr.n_ref), 0);
+    {
+        std::istringstream cs(c.chroms);
+        std::string name;
+        while (std::getline(cs, name, ','))
+            for (int i = 0; i < hdr.n_ref; ++i)
+                if (name == hdr.ref_names[i]) { main_chrom[i] = 1; break; }
+    }
+    if (hdr.n_lanes == 0) {
+        std::cerr << "ERROR: BAM header declares no read group (@RG); bamqualcheck needs at least one.\n";
+        return 1;
+    }
+    bqc_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.device = c.device;
+    cfg.isize = c.isize;
+    cfg.n_lanes = hdr.n_lanes;
+    cfg.lane_ids = hdr.lane_ids;
+    cfg.n_ref = hdr.n_ref;
+    cfg.main_chrom = main_chrom.data();
+    cfg.n_k = (int32_t)c.klist.size();
+    cfg.klist = c.klist.data();
+    cfg.n_q = (int32_t)c.qlist.size();
+    cfg.q_cutoff = c.qlist.data();
+    cfg.q_base = 33;
+    cfg.e = c.e;
+    cfg.seed = c.seed;
+    bqc_engine* eng = nullptr;
+    if (bqc_create(&cfg, &eng)) {
+        std::cerr << "ERROR: " << bqc_last_error(nullptr) << std::endl;
+        return 1;
+    }
+    // reference genome: every BAM reference that the FASTA holds goes to HBM
+    bqc_fasta* fa = bqc_fasta_open(c.ref.c_str());
+    if (!fa) std::cerr << "ERROR: Could not open fasta file " << c.ref << std::endl;  // the reference continues too (:291)
+    if (fa)
+        for (int i = 0; i < hdr.n_ref; ++i) {
+            const uint8_t* packed = nullptr;
+            int64_t len = bqc_fasta_contig(fa, hdr.ref_names[i], &packed);
+            if (len >= 0 && bqc_set_reference(eng, i, packed, (uint64_t)len)) {
+                std::cerr << "ERROR: " << bqc_last_error(eng) << std::endl;
+                return 1;
+            }
+        }
+    auto t_setup = std::chrono::steady_clock::now();
+
+    // ---- stream the records through the pinned staging buffers --------------------------------------
+    int rc = 0;
+    uint64_t n_records_total = 0;
+    std::vector<uint8_t> carry;  // partial record at the end of the previous buffer
+    std::vector<uint64_t> offs;
+    auto submit_buffer = [&](uint8_t* buf, size_t filled, bool last) -> int {
+        offs.resize(filled / 36 + 2);
+        uint64_t n = bqc_frame_records(buf, filled, offs.data(), offs.size());
+        size_t whole = (size_t)offs[n];
+        if (last && whole != filled) {
+            std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
+            return 1;
+        }
+        carry.assign(buf + whole, buf + filled);
+        n_records_total += n;
+        if (n && bqc_submit(eng, buf, whole, offs.data(), n)) {
+            std::cerr << "ERROR: " << bqc_last_error(eng) << std::endl;
+            return 1;
+        }
+        return 0;
+    };
+    if (raw) {
+        size_t p = hdr_bytes;
+        while (p < file.size() && !rc) {
+            void* pin;
+            size_t cap;
+            if (bqc_acquire_staging(eng, &pin, &cap)) { rc = 1; break; }
+            uint8_t* buf = (uint8_t*)pin;
+            memcpy(buf, carry.data(), carry.size());
+            size_t take = std::min(cap - carry.size(), file.size() - p);
+            memcpy(buf + carry.size(), file.data() + p, take);
+            size_t filled = carry.size() + take;
+            p += take;
+            rc = submit_buffer(buf, filled, p >= file.size());
+        }
+    } else {
+        // the tail of the header prefix that already holds records
+        std::vector<uint8_t> pending(head.begin() + hdr_bytes, head.end());
+        size_t bi = next_block;
+        bool first = true;
+        while ((bi < blocks.size() || first) && !rc) {
+            void* pin;
+            size_t cap;
+            if (bqc_acquire_staging(eng, &pin, &cap)) { rc = 1; break; }
+            uint8_t* buf = (uint8_t*)pin;
+            size_t filled = 0;
+            if (first) {
+                memcpy(buf, pending.data(), pending.size());
+                filled = pending.size();
+                first = false;
+            } else {
+                memcpy(buf, carry.data(), carry.size());
+                filled = carry.size();
+            }
+            std::vector<BgzfBlock> part;
+            uint64_t o = filled;
+            while (bi < blocks.size() && o + blocks[bi].isize <= cap) {
+                BgzfBlock b = blocks[bi++];
+                b.obeg = o;
+                o += b.isize;
+                part.push_back(b);
+            }
+            if (!part.empty() && !inflate_blocks(file.data(), part, buf, c.threads)) {
+                std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
+                rc = 1;
+                break;
+            }
+            rc = submit_buffer(buf, (size_t)o, bi >= blocks.size());
+        }
+    }
+    if (!rc) {
+        int code = bqc_finish(eng);
+        if (code) {
+            bqc_error_info ei;
+            bqc_get_error(eng, &ei);
+            if (ei.code == BQC_ERR_RG_NOT_Z) std::cout << "Read does not have Z" << "\n";
+            else if (ei.code == BQC_ERR_NO_MATE_FLAG) std::cerr << "ERROR: No first or second flag in read in:  " << c.bam << "\n";
+            else std::cerr << (ei.code ? ei.message : bqc_last_error(eng)) << std::endl;
+            rc = 1;
+        }
+    }
+    auto t_stats = std::chrono::steady_clock::now();
+    if (!rc && bqc_write_bamqc(eng, hdr.sample_id, c.out.c_str())) {
+        std::cerr << "ERROR: Could not open output file " << c.out << '\n';
+        rc = 1;
+    }
+    auto t_end = std::chrono::steady_clock::now();
+    if (c.timing) {
+        auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+        fprintf(stderr, "BAMQC_TIMING records=%llu setup_s=%.4f stats_s=%.4f write_s=%.4f total_s=%.4f threads=%d\n", (unsigned long long)n_records_total, sec(t_start, t_setup), sec(t_setup, t_stats), sec(t_stats, t_end), sec(t_start, t_end), c.threads);
+    }
+    if (fa) bqc_fasta_close(fa);
+    bqc_destroy(eng);
+    bqc_free_bam_header(&hdr);
+    return rc;
+}

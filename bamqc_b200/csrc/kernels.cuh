@@ -1,0 +1,748 @@
+// kernels.cuh -- hand-written CUDA (sm_100a) for the per-record statistics pass of bamqualcheck.
+//
+// Execution model: one THREAD per BAM record, records dealt to persistent CTAs in
+// an interleaved grid-stride order so neighbouring threads read neighbouring records.  Each statistic
+// family gets its own kernel so that its hot table can be privatised in shared memory:
+//   k_stats  : gate + scalars, QualityCheck per-cycle tables and histograms, TripletCounting walk,
+//              coverage difference-array scatter            (~30 KB of smem tables per CTA)
+//   k_eightmer: OverallNumbers::count8mers                 (32768-bin half table = 128 KB smem per CTA)
+//   k_sketch : ReadQualityHasher + RepHash + StreamCounter (F2 table = 128 KB smem per CTA; the 8 MiB
+//              4-bit sketch stays in L2 and is updated with load-test-CAS)
+//   k_cov_*  : coverage windows: prefix sum of the difference ring + histogram
+// Measured on B200 (profiles/ubench): shared-memory atomics sustain ~1700 G/s chip-wide, global REDs to
+// an L2-resident table ~150 G/s and collapse to <14 G/s on hot bins, hence the privatisation.
+//
+// All arithmetic is integer; every table update is a commutative add (or a saturating 4-bit add for
+// the sketch), so results do not depend on scheduling and are bit-exact against the oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "layout.h"
+
+namespace bqc {
+
+// ------------------------------------------------------------------------------------------------
+// views passed to the kernels
+// ------------------------------------------------------------------------------------------------
+struct BatchView {
+    const uint8_t* bytes;      // inflated BAM records, padded with >= 64 readable bytes
+    const uint32_t* offsets;   // n_records + 1 byte offsets
+    const uint32_t* cov;       // per record coverage code (window << 11 | pos) or kNone; may be NULL
+    const uint8_t* rec_lane;   // per record lane (multi-lane runs) or NULL
+    uint32_t n_records;
+    uint32_t cycb;             // per-cycle smem capacity for this batch (>= max l_seq, multiple of 8)
+    uint64_t first_record;     // global index of record 0 (error reporting)
+    uint32_t ring_base;        // ring index of coverage window 0 of this batch
+};
+
+struct EngineView {
+    Layout L;
+    uint64_t* counters;              // [n_lanes][lane_stride]
+    uint32_t* sketch;                // [n_lanes][n_qk][32][sk_size*2] 4-bit counters, 8 per word
+    uint32_t* ring;                  // [n_lanes][ring_mask+1] coverage difference ring
+    uint32_t ring_mask;
+    const uint32_t* const* ref;      // [n_ref] 2-bit packed contigs (16 bases per word) or NULL
+    const uint64_t* ref_len;         // [n_ref]
+    const uint8_t* main_chrom;       // [n_ref]
+    int32_t n_ref;
+    unsigned long long* error;       // min over (record << 8 | code), ~0 if none
+    uint32_t insert_smem;            // insert-size bins kept in shared memory
+};
+
+struct SketchParams {
+    uint32_t k;            // k-mer size (1..63)
+    int32_t q_thresh;      // (char)(q_base + q_cutoff) as signed char
+    uint32_t qk;           // pair index
+};
+
+// hash tables for one k (built on host, see engine.cu build_hash_tables): [strand][which][17] x 128 bit
+struct HashTables {
+    uint64_t t[2][4][17][2];  // which: 0 = h 'in', 1 = h 'out', 2 = ht 'in', 3 = ht 'out'; [..][0]=hi [1]=lo
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ldg8(const uint8_t* p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t ldu32(const uint8_t* p) {  // unaligned little-endian 32-bit load
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t lo = __ldg(w);
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, __ldg(w + 1), sh);
+}
+__device__ __forceinline__ uint64_t ldu64(const uint8_t* p) {  // unaligned little-endian 64-bit load
+    uintptr_t a = (uintptr_t)p;
+    const uint64_t* w = (const uint64_t*)(a & ~(uintptr_t)7);
+    uint32_t sh = (uint32_t)(a & 7) * 8;
+    uint64_t lo = __ldg(w);
+    if (sh == 0) return lo;
+    return (lo >> sh) | (__ldg(w + 1) << (64 - sh));
+}
+// nibble i (0..15) of a 64-bit SEQ chunk: byte i/2, high nibble first
+__device__ __forceinline__ uint32_t nib_of(uint64_t w, uint32_t i) { return (uint32_t)(w >> (4 * (i ^ 1))) & 15u; }
+
+__device__ __forceinline__ void report_error(const EngineView& E, uint64_t rec, uint32_t code) {
+    atomicMin(E.error, (unsigned long long)((rec << 8) | code));
+}
+
+struct RecHdr {
+    const uint8_t* p;
+    uint32_t bs;
+    int32_t rid, pos;
+    uint32_t lname, mapq, ncig, flag;
+    int32_t lseq, nrid, tlen;
+    uint32_t o_cig, o_seq, o_qual, o_aux, o_end;
+};
+
+// BAM record fixed fields (SAM/BAM spec).  Returns false if the record is malformed.
+__device__ __forceinline__ bool decode_hdr(const uint8_t* p, uint32_t avail, RecHdr& h) {
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t v[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] = __ldg(w + i);
+#define BQC_F(i) (sh ? __funnelshift_r(v[i], v[i + 1], sh) : v[i])
+    h.p = p;
+    h.bs = BQC_F(0);
+    h.rid = (int32_t)BQC_F(1);
+    h.pos = (int32_t)BQC_F(2);
+    uint32_t x = BQC_F(3);
+    h.lname = x & 255u;
+    h.mapq = (x >> 8) & 255u;
+    uint32_t y = BQC_F(4);
+    h.ncig = y & 0xFFFFu;
+    h.flag = y >> 16;
+    h.lseq = (int32_t)BQC_F(5);
+    h.nrid = (int32_t)BQC_F(6);
+    h.tlen = (int32_t)BQC_F(8);
+#undef BQC_F
+    if (h.bs + 4u != avail || h.bs < 32u || h.lseq < 0) return false;
+    h.o_cig = 36u + h.lname;
+    h.o_seq = h.o_cig + 4u * h.ncig;
+    h.o_qual = h.o_seq + (((uint32_t)h.lseq + 1u) >> 1);
+    h.o_aux = h.o_qual + (uint32_t)h.lseq;
+    h.o_end = avail;
+    return h.o_aux <= h.o_end && h.o_aux >= h.o_qual;
+}
+
+// BAM 4-bit code -> Dna5 ordinal (A0 C1 G2 T3 else 4) and its complement (SURVEY Appendix F LUTs)
+__device__ __forceinline__ uint32_t dna5_of(uint32_t nib) {
+    // nibbles 1,2,4,8 -> 0..3; packed 3-bit LUT would not fit 16 entries in 32 bits, so: popc test + ffs
+    return (__popc(nib) == 1) ? (uint32_t)(__ffs((int)nib) - 1) : 4u;
+}
+
+struct AuxInfo {
+    uint32_t rg;        // 0 = no RG tag, 1 = RG:Z, 2 = RG of another type
+    uint32_t as_state;  // 0 = no AS tag, 1 = readable, 2 = unreadable type
+    int32_t as_value;
+};
+
+__device__ __forceinline__ uint32_t aux_value_size(uint32_t type, const uint8_t* p, uint32_t pos, uint32_t end) {
+    // size of the value that starts at pos for a tag of `type`; 0xFFFFFFFF if malformed
+    switch (type) {
+        case 'A': case 'c': case 'C': return 1;
+        case 's': case 'S': return 2;
+        case 'i': case 'I': case 'f': return 4;
+        case 'Z': case 'H': {
+            uint32_t q = pos;
+            while (q < end && ldg8(p + q) != 0) ++q;
+            return q - pos + 1;
+        }
+        case 'B': {
+            if (pos + 5 > end) return 0xFFFFFFFFu;
+            uint32_t sub = ldg8(p + pos);
+            uint32_t cnt = ldu32(p + pos + 1);
+            uint32_t es = (sub == 'c' || sub == 'C') ? 1u : (sub == 's' || sub == 'S') ? 2u : 4u;
+            return 5u + cnt * es;
+        }
+        default: return 0xFFFFFFFFu;
+    }
+}
+// SeqAn extractTagValue into an integer (R15)
+__device__ __forceinline__ bool aux_int(uint32_t type, const uint8_t* p, long long& out) {
+    switch (type) {
+        case 'c': out = (int8_t)ldg8(p); return true;
+        case 'C': case 'A': out = (long long)ldg8(p); return true;
+        case 's': out = (int16_t)(ldg8(p) | (ldg8(p + 1) << 8)); return true;
+        case 'S': out = (long long)(ldg8(p) | (ldg8(p + 1) << 8)); return true;
+        case 'i': out = (int32_t)ldu32(p); return true;
+        case 'I': out = (long long)ldu32(p); return true;
+        case 'f': out = (long long)__uint_as_float(ldu32(p)); return true;
+        default: return false;
+    }
+}
+
+// One walk over the aux block: RG type (src/bamqualcheck.cpp:77-99), first AS (src/TripletCounting.hpp:
+// 113-129) and every integer-typed NM (src/QualityCheck.hpp:201-218, via on_nm).
+template <typename OnNM>
+__device__ __forceinline__ AuxInfo aux_walk(const RecHdr& h, OnNM on_nm) {
+    AuxInfo ai = {0u, 0u, 0};
+    uint32_t pos = h.o_aux;
+    const uint8_t* p = h.p;
+    while (pos + 3 <= h.o_end) {
+        uint32_t k0 = ldg8(p + pos), k1 = ldg8(p + pos + 1), ty = ldg8(p + pos + 2);
+        pos += 3;
+        uint32_t sz = aux_value_size(ty, p, pos, h.o_end);
+        if (sz == 0xFFFFFFFFu) break;
+        if (k0 == 'R' && k1 == 'G') {
+            if (ai.rg == 0) ai.rg = (ty == 'Z') ? 1u : 2u;
+        } else if (k0 == 'A' && k1 == 'S') {
+            if (ai.as_state == 0) {
+                long long v;
+                if (aux_int(ty, p + pos, v)) { ai.as_state = 1; ai.as_value = (int32_t)v; }
+                else ai.as_state = 2;
+            }
+        } else if (k0 == 'N' && k1 == 'M') {
+            if (ty == 'c' || ty == 'C' || ty == 'i' || ty == 'I' || ty == 's' || ty == 'S') {
+                long long v = 0;
+                aux_int(ty, p + pos, v);
+                on_nm((uint32_t)v);
+            }
+        }
+        pos += sz;
+    }
+    return ai;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_stats
+// ------------------------------------------------------------------------------------------------
+static const uint32_t kQS = 64;    // smem bins of the average-quality histograms (rest -> global)
+static const uint32_t kHS = 32;    // smem bins of mismatch / del / ins histograms
+static const uint32_t kStatsThreads = 256;
+
+struct StatsSmem {  // word offsets into the dynamic shared array
+    uint32_t pc, rl, nc, gc, aq, cq, mq, mm, dl, in, isz, tri, sc, total;
+};
+__host__ __device__ inline StatsSmem stats_smem_layout(uint32_t cycb, uint32_t insert_smem) {
+    StatsSmem s;
+    uint32_t o = 0;
+    s.pc = o;  o += 2 * PC_ROWS * cycb;
+    s.rl = o;  o += 2 * (cycb + 8);
+    s.nc = o;  o += 2 * (cycb + 8);
+    s.gc = o;  o += 2 * (cycb + 8);
+    s.aq = o;  o += 2 * kQS;
+    s.cq = o;  o += 2 * kQS;
+    s.mq = o;  o += 2 * kMapqCap;
+    s.mm = o;  o += 2 * kHS;
+    s.dl = o;  o += 2 * kHS;
+    s.in = o;  o += 2 * kHS;
+    s.isz = o; o += insert_smem;
+    s.tri = o; o += kTriplet;
+    s.sc = o;  o += S_COUNT;
+    s.total = o;
+    return s;
+}
+
+__device__ __forceinline__ void bump(uint32_t* sm, uint32_t smcap, uint64_t* g, uint32_t gcap, uint32_t idx, const EngineView& E, uint64_t rec) {
+    if (idx < smcap) atomicAdd(sm + idx, 1u);
+    else if (idx < gcap) atomicAdd((unsigned long long*)(g + idx), 1ULL);
+    else report_error(E, rec, 16 /*BQC_ERR_UNSUPPORTED*/);
+}
+
+__global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView B, uint32_t lane) {
+    extern __shared__ uint32_t sm[];
+    const StatsSmem S = stats_smem_layout(B.cycb, E.insert_smem);
+    for (uint32_t i = threadIdx.x; i < S.total; i += blockDim.x) sm[i] = 0;
+    __syncthreads();
+    const Layout& L = E.L;
+    uint64_t* G = E.counters + (uint64_t)lane * L.lane_stride;
+    const uint32_t cycb = B.cycb;
+
+    for (uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x; rec < B.n_records; rec += gridDim.x * blockDim.x) {
+        if (B.rec_lane && B.rec_lane[rec] != lane) continue;
+        const uint64_t grec = B.first_record + rec;
+        const uint32_t off = B.offsets[rec];
+        RecHdr h;
+        if (!decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h)) { report_error(E, grec, 4); continue; }
+        const uint32_t flag = h.flag;
+        const uint32_t Ls = (uint32_t)h.lseq;
+        const bool primary = !(flag & 0x900u);
+        const bool isfirst = (flag & 0x40u) != 0;
+        const bool hasmate = (flag & 0xC0u) != 0;
+        const uint32_t mate = isfirst ? 0u : 1u;
+        const bool rc = (flag & 0x10u) != 0;
+        const bool mapped = !(flag & 0x4u);
+        const bool inmain = h.rid >= 0 && h.rid < E.n_ref && E.main_chrom[h.rid];
+
+        // CIGAR summary (needed by mis_match, cigar_count and the triplet filter)
+        uint32_t delc = 0, insc = 0, clipped = 0, first_op = 0, last_op = 0;
+        if (primary) {
+            for (uint32_t i = 0; i < h.ncig; ++i) {
+                uint32_t c = ldu32(h.p + h.o_cig + 4 * i);
+                uint32_t op = c & 15u, n = c >> 4;
+                if (op == 2) delc += n;
+                else if (op == 1) insc += n;
+                else if (op == 4 || op == 5) clipped += n;
+                if (i == 0) first_op = c;
+                if (i == h.ncig - 1) last_op = c;
+            }
+        }
+        const bool do_cig = primary && hasmate && inmain && mapped;  // src/bamqualcheck.cpp:392-428
+        uint64_t* GM = G + L.o_mate0 + mate * L.mate_stride;
+        AuxInfo ai = aux_walk(h, [&](uint32_t nm) {
+            if (do_cig) bump(sm + S.mm + mate * kHS, kHS, GM + L.m_mismatch, L.mmcap, nm - delc - insc, E, grec);
+        });
+        // getLane(): src/bamqualcheck.cpp:72-100
+        if (ai.rg == 2) { report_error(E, grec, 1); continue; }
+        if (ai.rg == 0) { report_error(E, grec, 5); continue; }
+        // gate: src/bamqualcheck.cpp:318-335
+        if (flag & 0x800u) { atomicAdd(sm + S.sc + S_SUPPLEMENTARY, 1u); continue; }
+        if (flag & 0x100u) { atomicAdd(sm + S.sc + S_NOT_PRIMARY, 1u); continue; }
+        if (flag & 0x400u) atomicAdd(sm + S.sc + S_DUPLICATES, 1u);
+        if (flag & 0x200u) atomicAdd(sm + S.sc + S_QCFAILED, 1u);
+        if (Ls > L.cyc || Ls > cycb) { report_error(E, grec, 16); continue; }
+
+        // ---- TripletCounting (src/TripletCounting.hpp:136-236), aligned orientation -------------------
+        if (!(flag & 0x600u)) {
+            bool elig = (flag & 0x1u) && (flag & 0x2u) && mapped && !(flag & 0x8u) && h.mapq >= 60u;
+            if (elig) {
+                if (ai.as_state != 1 || ai.as_value < 0) { report_error(E, grec, 3); continue; }
+                elig = ai.as_value >= 50 && clipped == 0;
+            }
+            const uint32_t* ref = (elig && E.ref && h.rid >= 0 && h.rid < E.n_ref) ? E.ref[h.rid] : nullptr;
+            if (elig && ref && h.ncig > 0 && Ls >= 3) {
+                const uint64_t reflen = E.ref_len[h.rid];
+                const uint32_t grp = (rc ? 2u : 0u) + (isfirst ? 0u : 1u);
+                uint32_t* tri = sm + S.tri;
+                const uint8_t* seqp = h.p + h.o_seq;
+                const uint8_t* qualp = h.p + h.o_qual;
+                uint32_t it = 0;
+                uint64_t cc = (uint64_t)(first_op >> 4) - 1;  // size_t arithmetic as in the reference (wraps for count 0)
+                uint64_t chromPos = (uint64_t)(uint32_t)h.pos + 1;
+                uint32_t readPos = 1;
+                uint32_t seq_chunk = kNone, qual_chunk = kNone, ref_chunk = kNone;
+                uint64_t seqw = 0, qualw = 0;
+                uint32_t refw = 0;
+                auto nib_at = [&](uint32_t i) -> uint32_t {
+                    if ((i >> 4) != seq_chunk) { seq_chunk = i >> 4; seqw = ldu64(seqp + 8 * seq_chunk); }
+                    return nib_of(seqw, i & 15u);
+                };
+                auto ref_at = [&](uint64_t x) -> uint32_t {
+                    uint32_t c = (uint32_t)(x >> 4);
+                    if (c != ref_chunk) { ref_chunk = c; refw = __ldg(ref + c); }
+                    return (refw >> (2 * ((uint32_t)x & 15u))) & 3u;
+                };
+                bool ok = true;
+                for (; readPos < Ls - 1; ++readPos, ++chromPos, --cc) {
+                    while (cc == 0) {
+                        ++it;
+                        if (it >= h.ncig) { ok = false; break; }  // reference reads past the CIGAR here (undefined)
+                        uint32_t c = ldu32(h.p + h.o_cig + 4 * it);
+                        uint32_t op = c & 15u, n = c >> 4;
+                        if (op == 2 || op == 3 || op == 5 || op == 6) chromPos += n;
+                        else if (op == 4 || op == 1) readPos += n;
+                        else cc = n;
+                    }
+                    if (!ok || readPos >= Ls - 1) break;
+                    if ((readPos >> 3) != qual_chunk) { qual_chunk = readPos >> 3; qualw = ldu64(qualp + 8 * qual_chunk); }
+                    uint32_t q = (uint32_t)(qualw >> (8 * (readPos & 7u))) & 255u;
+                    if ((int8_t)(q + 33u) < (int8_t)53) continue;  // read.qual[readPos] < minBaseQAscii, char compare
+                    uint32_t nb = nib_at(readPos);
+                    uint32_t base = dna5_of(nb);
+                    if (base == 4u) continue;
+                    uint32_t np = nib_at(readPos - 1), nn = nib_at(readPos + 1);
+                    if (np == 15u || nn == 15u) continue;
+                    if (chromPos + 2 > reflen) continue;  // context past the contig end (undefined in the reference)
+                    uint32_t c0 = ref_at(chromPos - 1), c1 = ref_at(chromPos), c2 = ref_at(chromPos + 1);
+                    if (np != (1u << c0) || nn != (1u << c2)) continue;  // flanks must equal the context as chars
+                    atomicAdd(tri + ((c0 << 4) + (c1 << 2) + c2) * 16u + grp * 4u + base, 1u);
+                }
+            }
+        }
+
+        // ---- src/bamqualcheck.cpp:353-389 ------------------------------------------------------------
+        if (!hasmate) { report_error(E, grec, 2); continue; }
+        atomicAdd(sm + S.sc + S_READCOUNT, 1u);
+        atomicAdd(sm + S.sc + S_TOTALBPS, Ls);
+        {   // QualityCheck::get_count (src/QualityCheck.hpp:111-176) on the read-oriented SEQ/QUAL
+            uint32_t* pc = sm + S.pc + mate * PC_ROWS * cycb;
+            const uint8_t* seqp = h.p + h.o_seq;
+            const uint8_t* qualp = h.p + h.o_qual;
+            uint32_t cntN = 0, cntGC = 0, sumQ = 0;
+            uint64_t seqw = 0, qualw = 0;
+            for (uint32_t i = 0; i < Ls; ++i) {
+                if ((i & 15u) == 0) seqw = ldu64(seqp + (i >> 1));
+                if ((i & 7u) == 0) qualw = ldu64(qualp + i);
+                uint32_t nb = nib_of(seqw, i & 15u);
+                uint32_t q = (uint32_t)(qualw >> (8 * (i & 7u))) & 255u;
+                uint32_t d = dna5_of(nb);
+                if (rc && d < 4u) d = 3u - d;
+                uint32_t cyc = rc ? (Ls - 1 - i) : i;
+                atomicAdd(pc + d * cycb + cyc, 1u);
+                atomicAdd(pc + PC_QUAL * cycb + cyc, q);
+                cntN += (nb == 15u);
+                cntGC += (nb == 2u || nb == 4u);
+                sumQ += q;
+            }
+            atomicAdd((unsigned long long*)(GM + L.m_readnr), 1ULL);
+            atomicAdd(sm + S.nc + mate * (cycb + 8) + cntN, 1u);
+            atomicAdd(sm + S.gc + mate * (cycb + 8) + cntGC, 1u);
+            if (Ls > 0) {
+                uint32_t rnd = (2u * sumQ + Ls) / (2u * Ls);   // round(double(S)/L), exact
+                uint32_t cel = (sumQ + Ls - 1u) / Ls;          // ceil(double(S)/L)
+                bump(sm + S.aq + mate * kQS, kQS, GM + L.m_avgq, kQCap, rnd, E, grec);
+                bump(sm + S.cq + mate * kQS, kQS, GM + L.m_ceilq, kQCap, cel, E, grec);
+            }
+            atomicAdd(sm + S.rl + mate * (cycb + 8) + Ls, 1u);
+        }
+        if (isfirst) {
+            if (!mapped) {
+                atomicAdd(sm + S.sc + S_FIRSTUNMAPPED, 1u);
+                if (flag & 0x8u) atomicAdd(sm + S.sc + S_BOTHUNMAPPED, 1u);
+            }
+            if (flag & 0x2u) {
+                atomicAdd(sm + S.sc + S_PROPERPAIR, 1u);
+                if (((flag >> 4) & 1u) == ((flag >> 5) & 1u)) atomicAdd(sm + S.sc + S_FF_RR, 1u);
+            }
+        } else if (!mapped) {
+            atomicAdd(sm + S.sc + S_SECONDUNMAPPED, 1u);
+        }
+
+        // ---- main chromosomes only: src/bamqualcheck.cpp:392-434 ---------------------------------------
+        if (inmain) {
+            if (mapped) {
+                // cigar_count (src/QualityCheck.hpp:222-271) on the read-oriented CIGAR
+                if (h.ncig == 0) { report_error(E, grec, 16); continue; }
+                uint32_t fo = rc ? last_op : first_op, lo = rc ? first_op : last_op;
+                uint32_t* pc = sm + S.pc + mate * PC_ROWS * cycb;
+                if ((fo & 15u) == 4u) {
+                    uint32_t n = min(fo >> 4, cycb);
+                    for (uint32_t j = 0; j < n; ++j) atomicAdd(pc + PC_SC5 * cycb + j, 1u);
+                } else if ((lo & 15u) == 4u) {
+                    uint32_t n = lo >> 4;
+                    for (uint32_t j = (n <= Ls ? Ls - n : Ls); j < Ls; ++j) atomicAdd(pc + PC_SC3 * cycb + j, 1u);
+                }
+                bump(sm + S.dl + mate * kHS, kHS, GM + L.m_del, L.delcap, delc, E, grec);
+                bump(sm + S.in + mate * kHS, kHS, GM + L.m_ins, L.mmcap, insc, E, grec);
+                atomicAdd(sm + S.mq + mate * kMapqCap + h.mapq, 1u);  // map_Q :178-185
+                if (isfirst && !(flag & 0x8u) && h.nrid >= 0 && h.nrid < E.n_ref && E.main_chrom[h.nrid]) {
+                    uint32_t idx = (uint32_t)(h.tlen < 0 ? -(int64_t)h.tlen : (int64_t)h.tlen);  // insert_size :187-196
+                    if (idx >= L.isize1) idx = L.isize1 - 1;
+                    if (idx < E.insert_smem) atomicAdd(sm + S.isz + idx, 1u);
+                    else atomicAdd((unsigned long long*)(G + L.o_insert + idx), 1ULL);
+                }
+            }
+            if (isfirst) {
+                if ((mapped || !(flag & 0x8u)) && !(flag & 0x400u)) atomicAdd(sm + S.sc + S_FIRST_AND_OR_SECOND_MAPPED, 1u);
+                if ((flag & 0x2u) && !(flag & 0x400u)) atomicAdd(sm + S.sc + S_AUTO_PROPERPAIR, 1u);
+            }
+            // coverage (src/OverallNumbers.hpp:79-135): the window anchor comes from the host scan
+            // (cov code), here only the commutative part: +1/-1 into the difference ring.
+            if (mapped && !(flag & 0x400u) && B.cov) {
+                uint32_t code = B.cov[rec];
+                if (code != kNone) {
+                    uint32_t pos = code & 2047u;
+                    uint32_t base_idx = B.ring_base + (code >> 11) * 1000u + pos;
+                    uint32_t lim = 2000u - pos;
+                    uint32_t* ring = E.ring + (uint64_t)lane * ((uint64_t)E.ring_mask + 1);
+                    uint32_t c = 0;
+                    for (uint32_t i = 0; i < h.ncig; ++i) {
+                        uint32_t ce = ldu32(h.p + h.o_cig + 4 * (rc ? (h.ncig - 1 - i) : i));
+                        uint32_t op = ce & 15u, n = ce >> 4;
+                        if (op == 4u) c += n;
+                        if (op == 0u || op == 2u) {
+                            if (c < lim && n > 0) {
+                                uint32_t hi = min(c + n, lim);
+                                atomicAdd(ring + ((base_idx + c) & E.ring_mask), 1u);
+                                atomicAdd(ring + ((base_idx + hi) & E.ring_mask), 0xFFFFFFFFu);
+                            }
+                            c += n;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- flush the CTA-private tables (skip zeros) ---------------------------------------------------
+    auto flush = [&](uint32_t smo, uint32_t n, uint64_t* g) {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            uint32_t v = sm[smo + i];
+            if (v) atomicAdd((unsigned long long*)(g + i), (unsigned long long)v);
+        }
+    };
+    for (uint32_t m = 0; m < 2; ++m) {
+        uint64_t* GMm = G + L.o_mate0 + m * L.mate_stride;
+        for (uint32_t r = 0; r < PC_ROWS; ++r) flush(S.pc + (m * PC_ROWS + r) * cycb, cycb, GMm + L.m_pc + r * pad8(L.cyc));
+        flush(S.rl + m * (cycb + 8), cycb + 1, GMm + L.m_readlen);
+        flush(S.nc + m * (cycb + 8), cycb + 1, GMm + L.m_ncount);
+        flush(S.gc + m * (cycb + 8), cycb + 1, GMm + L.m_gccount);
+        flush(S.aq + m * kQS, kQS, GMm + L.m_avgq);
+        flush(S.cq + m * kQS, kQS, GMm + L.m_ceilq);
+        flush(S.mq + m * kMapqCap, kMapqCap, GMm + L.m_mapq);
+        flush(S.mm + m * kHS, kHS, GMm + L.m_mismatch);
+        flush(S.dl + m * kHS, kHS, GMm + L.m_del);
+        flush(S.in + m * kHS, kHS, GMm + L.m_ins);
+    }
+    flush(S.isz, E.insert_smem, G + L.o_insert);
+    flush(S.tri, kTriplet, G + L.o_triplet);
+    flush(S.sc, S_COUNT, G + L.o_scalars);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_eightmer: OverallNumbers::count8mers (src/OverallNumbers.hpp:137-168)
+// CTA b owns half (b & 1) of the 65536-bin table in shared memory and walks record slab (b >> 1).
+// ------------------------------------------------------------------------------------------------
+static const uint32_t kEightThreads = 1024;
+__global__ void __launch_bounds__(kEightThreads, 1) k_eightmer(EngineView E, BatchView B, uint32_t lane) {
+    extern __shared__ uint32_t sm[];  // 32768 bins
+    for (uint32_t i = threadIdx.x; i < 32768u; i += blockDim.x) sm[i] = 0;
+    __syncthreads();
+    const uint32_t half = blockIdx.x & 1u;
+    const uint32_t slab = blockIdx.x >> 1, nslab = gridDim.x >> 1;
+    // 2-bit codes per BAM nibble: forward C(2)->1 G(4)->2 T(8)->3 else 0; reverse-complement view
+    // A(1)->3 C(2)->2 G(4)->1 else 0  (char->Dna conversion of the complemented char, R5/R7)
+    const uint32_t LUTF = (1u << (2 * 2)) | (2u << (2 * 4)) | (3u << (2 * 8));
+    const uint32_t LUTR = (3u << (2 * 1)) | (2u << (2 * 2)) | (1u << (2 * 4));
+    for (uint32_t rec = slab * blockDim.x + threadIdx.x; rec < B.n_records; rec += nslab * blockDim.x) {
+        if (B.rec_lane && B.rec_lane[rec] != lane) continue;
+        const uint32_t off = B.offsets[rec];
+        RecHdr h;
+        if (!decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h)) continue;
+        if ((h.flag & 0x900u) || !(h.flag & 0xC0u)) continue;
+        const uint32_t Ls = (uint32_t)h.lseq;
+        if (Ls < 8u) continue;
+        const bool rc = (h.flag & 0x10u) != 0;
+        const uint8_t* seqp = h.p + h.o_seq;
+        uint32_t code = 0, since_n = 0;
+        uint64_t seqw = 0;
+        for (uint32_t i = 0; i < Ls; ++i) {
+            if ((i & 15u) == 0) seqw = ldu64(seqp + (i >> 1));
+            uint32_t nb = nib_of(seqw, i & 15u);
+            since_n = (nb == 15u) ? 0u : since_n + 1u;
+            if (!rc) code = ((code << 2) | ((LUTF >> (2 * nb)) & 3u)) & 0xFFFFu;
+            else code = (code >> 2) | (((LUTR >> (2 * nb)) & 3u) << 14);
+            if (i >= 7u && since_n >= 8u && (code >> 15) == half) atomicAdd(sm + (code & 32767u), 1u);
+        }
+    }
+    __syncthreads();
+    uint64_t* g = E.counters + (uint64_t)lane * E.L.lane_stride + E.L.o_eightmer + half * 32768u;
+    for (uint32_t i = threadIdx.x; i < 32768u; i += blockDim.x) {
+        uint32_t v = sm[i];
+        if (v) atomicAdd((unsigned long long*)(g + i), (unsigned long long)v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_sketch: ReadQualityHasher::operator() (src/ReadQualityHasher.hpp:30-68) -> RepHash
+// (src/kmerstream/RepHash.hpp:85-114) -> StreamCounter::operator() (src/kmerstream/StreamCounter.hpp:67-93)
+// ------------------------------------------------------------------------------------------------
+static const uint32_t kSketchThreads = 1024;
+template <bool F2_IN_SMEM>
+__global__ void __launch_bounds__(kSketchThreads, 1) k_sketch(EngineView E, BatchView B, uint32_t lane, SketchParams SP, const HashTables* __restrict__ HT) {
+    extern __shared__ uint32_t sm[];
+    __shared__ ulonglong2 tab[2][4][17];
+    const Layout& L = E.L;
+    const uint32_t f2n = F2_IN_SMEM ? L.f2size : 0u;
+    for (uint32_t i = threadIdx.x; i < f2n; i += blockDim.x) sm[i] = 0;
+    for (uint32_t i = threadIdx.x; i < 2 * 4 * 17; i += blockDim.x) {
+        const uint64_t* src = &HT->t[0][0][0][0] + 2 * i;
+        (&tab[0][0][0])[i] = make_ulonglong2(src[1], src[0]);  // .x = lo, .y = hi
+    }
+    __syncthreads();
+    uint64_t* G = E.counters + (uint64_t)lane * L.lane_stride + L.o_qk + (uint64_t)SP.qk * L.qk_stride;
+    uint32_t* sk = E.sketch + ((uint64_t)lane * L.n_qk + SP.qk) * 32ull * (L.sk_size * 2ull);
+    const uint32_t words_per_level = L.sk_size * 2u;
+    const uint64_t idx_mask = (uint64_t)L.sk_size * 16ull - 1ull;
+    const uint32_t f2mask = L.f2size - 1u;
+    const uint32_t k = SP.k;
+    unsigned long long my_count = 0;
+
+    for (uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x; rec < B.n_records; rec += gridDim.x * blockDim.x) {
+        if (B.rec_lane && B.rec_lane[rec] != lane) continue;
+        const uint32_t off = B.offsets[rec];
+        RecHdr h;
+        if (!decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h)) continue;
+        if ((h.flag & 0xF00u) || !(h.flag & 0xC0u)) continue;  // primary, not QC-fail, not duplicate (:439-442)
+        const uint32_t Ls = (uint32_t)h.lseq;
+        if (Ls < k) continue;
+        const uint32_t s = (h.flag >> 4) & 1u;
+        const uint8_t* seqp = h.p + h.o_seq;
+        const uint8_t* qualp = h.p + h.o_qual;
+        uint64_t hlo = 0, hhi = 0, tlo = 0, thi = 0;
+        uint64_t seqw = 0, qualw = 0, lagw = 0;
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < Ls; ++i) {
+            if ((i & 15u) == 0) seqw = ldu64(seqp + (i >> 1));
+            if ((i & 7u) == 0) qualw = ldu64(qualp + i);
+            uint32_t nin = nib_of(seqw, i & 15u);
+            uint32_t nout = 16u;
+            if (i >= k) {
+                uint32_t j = i - k;
+                if ((j & 15u) == 0 || i == k) lagw = ldu64(seqp + ((j >> 4) << 3));
+                nout = nib_of(lagw, j & 15u);
+            }
+            uint32_t q = (uint32_t)(qualw >> (8 * (i & 7u))) & 255u;
+            // h = rotl1(h) ^ rotl_k(H[out]) ^ H[in]
+            ulonglong2 a = tab[s][0][nin], b = tab[s][1][nout];
+            uint64_t nh = (hhi << 1) | (hlo >> 63);
+            hlo = ((hlo << 1) | (hhi >> 63)) ^ a.x ^ b.x;
+            hhi = nh ^ a.y ^ b.y;
+            // ht = rotr1(ht ^ H[twin[out]] ^ rotl_k(H[twin[in]]))
+            ulonglong2 c = tab[s][2][nin], d = tab[s][3][nout];
+            uint64_t xl = tlo ^ c.x ^ d.x, xh = thi ^ c.y ^ d.y;
+            tlo = (xl >> 1) | (xh << 63);
+            thi = (xh >> 1) | (xl << 63);
+            bool valid = (nin != 15u) && ((int8_t)(q + 33u) >= (int8_t)SP.q_thresh);
+            run = valid ? run + 1u : 0u;
+            if (run >= k) {
+                uint64_t hv = hlo ^ tlo;
+                ++my_count;
+                if (F2_IN_SMEM) atomicAdd(sm + ((uint32_t)hv & f2mask), 1u);
+                else atomicAdd((unsigned long long*)(G + 8 + ((uint32_t)hv & f2mask)), 1ULL);
+                uint32_t w = hv ? (uint32_t)(__ffsll((long long)hv) - 1) : 63u;  // bitScanForward, 63 for 0
+                if (w > 31u) w = 31u;
+                uint64_t index = (hv >> (w + 1u)) & idx_mask;
+                uint32_t* wp = sk + w * words_per_level + (uint32_t)(index >> 3);
+                uint32_t sh = ((uint32_t)index & 7u) * 4u;
+                uint32_t old = __ldcg(wp);
+                while (((old >> sh) & 15u) != 15u) {  // 4-bit saturating increment
+                    uint32_t assumed = old;
+                    old = atomicCAS(wp, assumed, assumed + (1u << sh));
+                    if (old == assumed) break;
+                }
+            }
+        }
+    }
+    // sumCount: warp reduce then one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) my_count += __shfl_xor_sync(0xFFFFFFFFu, my_count, o);
+    if ((threadIdx.x & 31u) == 0 && my_count) atomicAdd((unsigned long long*)G, my_count);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < f2n; i += blockDim.x) {
+        uint32_t v = sm[i];
+        if (v) atomicAdd((unsigned long long*)(G + 8 + i), (unsigned long long)v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// coverage windows (src/OverallNumbers.hpp:59-77): depth = prefix sum of the difference ring over the
+// flushed range, poscov[min(depth,100)]++ for every position, ring range zeroed for reuse.
+// ------------------------------------------------------------------------------------------------
+static const uint32_t kCovChunk = 4096;  // ring entries per CTA step (1024 threads x 4)
+__global__ void __launch_bounds__(1024) k_cov_chunk_sums(const uint32_t* ring, uint32_t ring_mask, uint32_t start, uint64_t len, uint32_t* sums) {
+    __shared__ uint32_t wsum[32];
+    for (uint64_t chunk = blockIdx.x; chunk * kCovChunk < len; chunk += gridDim.x) {
+        uint32_t acc = 0;
+        for (uint32_t j = 0; j < 4; ++j) {
+            uint64_t i = chunk * kCovChunk + j * 1024u + threadIdx.x;
+            if (i < len) acc += ring[(start + (uint32_t)i) & ring_mask];
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+        if ((threadIdx.x & 31u) == 0) wsum[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t v = wsum[threadIdx.x];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            if (threadIdx.x == 0) sums[chunk] = v;
+        }
+        __syncthreads();
+    }
+}
+// exclusive scan of the chunk sums (single CTA), seeded with the carried depth; leaves the new carry
+__global__ void __launch_bounds__(1024) k_cov_scan_sums(uint32_t* sums, uint64_t nchunks, uint32_t* carry) {
+    __shared__ uint32_t part[1024];
+    uint64_t per = (nchunks + 1023) / 1024;
+    uint64_t b = threadIdx.x * per, e = min(b + per, nchunks);
+    uint32_t acc = 0;
+    for (uint64_t i = b; i < e; ++i) acc += sums[i];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = *carry;
+        for (int i = 0; i < 1024; ++i) { uint32_t t = part[i]; part[i] = run; run += t; }
+        *carry = run;
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (uint64_t i = b; i < e; ++i) { uint32_t t = sums[i]; sums[i] = run; run += t; }
+}
+__global__ void __launch_bounds__(1024) k_cov_apply(uint32_t* ring, uint32_t ring_mask, uint32_t start, uint64_t len, const uint32_t* sums, unsigned long long* poscov) {
+    __shared__ uint32_t hist[128];
+    __shared__ uint32_t wsum[32];
+    if (threadIdx.x < 128) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t chunk = blockIdx.x; chunk * kCovChunk < len; chunk += gridDim.x) {
+        // thread t owns 4 consecutive entries
+        uint64_t i0 = chunk * kCovChunk + 4ull * threadIdx.x;
+        uint32_t v[4];
+        uint32_t acc = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            uint64_t i = i0 + j;
+            v[j] = (i < len) ? ring[(start + (uint32_t)i) & ring_mask] : 0u;
+            acc += v[j];
+        }
+        // CTA exclusive scan of acc
+        uint32_t incl = acc;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((threadIdx.x & 31u) >= (uint32_t)o) incl += t;
+        }
+        if ((threadIdx.x & 31u) == 31u) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = wsum[threadIdx.x], wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (threadIdx.x >= (uint32_t)o) wi += t;
+            }
+            wsum[threadIdx.x] = wi - w;
+        }
+        __syncthreads();
+        uint32_t depth = sums[chunk] + wsum[threadIdx.x >> 5] + (incl - acc);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            uint64_t i = i0 + j;
+            if (i < len) {
+                depth += v[j];
+                atomicAdd(hist + min(depth, 100u), 1u);
+                ring[(start + (uint32_t)i) & ring_mask] = 0u;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 101 && hist[threadIdx.x]) atomicAdd(poscov + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sketch export / import / merge (StreamCounter::join, src/kmerstream/StreamCounter.hpp:95-112)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sketch_export_u8(const uint32_t* sk, uint64_t nwords, uint8_t* out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w = sk[i];
+        uint2 o;
+        o.x = (w & 15u) | (((w >> 4) & 15u) << 8) | (((w >> 8) & 15u) << 16) | (((w >> 12) & 15u) << 24);
+        o.y = ((w >> 16) & 15u) | (((w >> 20) & 15u) << 8) | (((w >> 24) & 15u) << 16) | (((w >> 28) & 15u) << 24);
+        reinterpret_cast<uint2*>(out)[i] = o;
+    }
+}
+__global__ void k_sketch_import_u8(uint32_t* sk, uint64_t nwords, const uint8_t* in) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint2 v = reinterpret_cast<const uint2*>(in)[i];
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            w |= min((v.x >> (8 * j)) & 255u, 15u) << (4 * j);
+            w |= min((v.y >> (8 * j)) & 255u, 15u) << (16 + 4 * j);
+        }
+        sk[i] = w;
+    }
+}
+__global__ void k_sketch_merge(uint32_t* dst, const uint32_t* src, uint64_t nwords) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t a = dst[i], b = src[i], w = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w |= min(((a >> (4 * j)) & 15u) + ((b >> (4 * j)) & 15u), 15u) << (4 * j);
+        dst[i] = w;
+    }
+}
+__global__ void k_counters_add(unsigned long long* dst, const unsigned long long* src, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
+}  // namespace bqc

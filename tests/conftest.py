@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_bin():
+    import bqc_testutil as util
+    return util.ensure_oracle()
+
+
+@pytest.fixture(scope="session")
+def lib():
+    import bamqc_b200
+    if not os.path.exists(bamqc_b200.library_path()):
+        bamqc_b200.build()
+    return bamqc_b200.load_library()

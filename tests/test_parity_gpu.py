@@ -1,0 +1,81 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on seeded synthetic data.
+Bit-exact for every integer table; the `.bamqc` text (which also carries the derived doubles at the
+reference's 6 significant digits) must be byte-identical."""
+import numpy as np
+import pytest
+
+import bqc_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+
+def _roundtrip(tmp_path, lib_, genome=None, chroms="chr1,chr2", isize=1000, klist=(32,), qlist=(17,), seed=1,
+               n_batches=1, resident=False, engine_kwargs=None):
+    from bamqc_b200 import synth
+    genome = genome or util.small_genome()
+    records, offsets = synth.generate(genome, lib_)
+    n_bytes = int(offsets[-1])
+    fasta, bam = tmp_path / "ref.fa", tmp_path / "in.ubam"
+    genome.write_fasta(fasta)
+    synth.write_bam(bam, genome, lib_, records, n_bytes)
+    r = util.run_oracle(bam, fasta, tmp_path / "oracle.bamqc", chroms=chroms, isize=isize, klist=klist, qlist=qlist,
+                        seed=seed, dump=tmp_path / "oracle.dump")
+    assert r.returncode == 0, r.stderr
+    eng = util.run_engine(genome, lib_, records, offsets, tmp_path / "gpu.bamqc", chroms=chroms, isize=isize,
+                          klist=klist, qlist=qlist, seed=seed, n_batches=n_batches, resident=resident,
+                          engine_kwargs=engine_kwargs, keep=True)
+    try:
+        diffs = util.diff_bamqc(tmp_path / "oracle.bamqc", tmp_path / "gpu.bamqc")
+        assert not diffs, "\n".join(diffs)
+        # sketch tables and F2 tables themselves, not only the estimators printed in the text
+        nq, nk = len(qlist), len(klist)
+        sk = util.oracle_sketch(tmp_path / "oracle.dump", lib_.n_lanes * nq * nk)
+        lanes_sorted = sorted(range(lib_.n_lanes), key=lambda l: synth.lane_ids(lib_)[l])
+        i = 0
+        for lane in lanes_sorted:  # the oracle dumps lanes in std::map order
+            for qk in range(nq * nk):
+                table, f2 = sk[i]
+                i += 1
+                assert np.array_equal(eng.sketch(lane, qk), table), f"sketch table lane {lane} qk {qk}"
+                assert np.array_equal(eng.table("F2TABLE", lane, qk), f2), f"F2 table lane {lane} qk {qk}"
+    finally:
+        eng.close()
+
+
+def test_standard_library(tmp_path):
+    from bamqc_b200 import synth
+    _roundtrip(tmp_path, synth.Library(seed=11, n_pairs=20000))
+
+
+def test_stress_library(tmp_path):
+    from bamqc_b200 import synth
+    _roundtrip(tmp_path, synth.Library(seed=12, n_pairs=15000).stress())
+
+
+def test_many_batches_and_long_insert(tmp_path):
+    from bamqc_b200 import synth
+    lib_ = synth.Library(seed=13, n_pairs=12000, ins_mean=1500, ins_sd=400, ins_min=150, ins_max=6000)
+    _roundtrip(tmp_path, lib_, isize=3000, n_batches=7)
+
+
+def test_resident_replay(tmp_path):
+    from bamqc_b200 import synth
+    _roundtrip(tmp_path, synth.Library(seed=14, n_pairs=9000), n_batches=3, resident=True)
+
+
+def test_two_lanes_and_kq_grid(tmp_path):
+    from bamqc_b200 import synth
+    _roundtrip(tmp_path, synth.Library(seed=15, n_pairs=8000, n_lanes=2), klist=(15, 32, 63), qlist=(10, 17))
+
+
+def test_sparse_coverage_windows(tmp_path):
+    """Mean gap between reads ~ 600 bp: exercises window rolls, resets and the tiny-ring segmentation."""
+    from bamqc_b200 import synth
+    genome = util.small_genome(seed=9, lengths=(3000000, 2000000, 500000))
+    lib_ = synth.Library(seed=16, n_pairs=4000)
+    _roundtrip(tmp_path, lib_, genome=genome, n_batches=2, engine_kwargs=dict(cov_ring_log2=13))
+
+
+def test_other_read_length_and_seed(tmp_path):
+    from bamqc_b200 import synth
+    _roundtrip(tmp_path, synth.Library(seed=17, n_pairs=6000, read_len=101, ins_mean=300), seed=5)
