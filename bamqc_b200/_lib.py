@@ -87,6 +87,8 @@ PROTOTYPES = {
     "bqc_kernel_launches": (_u64, [_vp]),
     "bqc_get_error": (ctypes.c_int, [_vp, _P(bqc_error_info)]),
     "bqc_finish": (ctypes.c_int, [_vp]),
+    "bqc_profile_enable": (None, [_vp, ctypes.c_int]),
+    "bqc_profile_read": (ctypes.c_int, [_vp, _P(ctypes.c_double), _P(_u64)]),
     "bqc_counters_len": (_u64, [_vp]),
     "bqc_counters_export": (ctypes.c_int, [_vp, _vp]),
     "bqc_counters_import": (ctypes.c_int, [_vp, _vp]),

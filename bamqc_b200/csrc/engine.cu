@@ -116,6 +116,14 @@ struct bqc_engine {
     bqc_error_info host_error = {0, 0, {0}};
     int stats_blocks_per_sm = 0;
 
+    // optional per-kernel-family timing (CUDA events on the compute stream)
+    bool profiling = false;
+    struct ProfEv { int family; cudaEvent_t a, b; };
+    std::vector<ProfEv> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
     // results (after finish)
     bool have_results = false;
     std::vector<uint64_t> h_counters;
@@ -287,7 +295,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     e->staging_bytes = cfg->staging_bytes ? cfg->staging_bytes : (256ull << 20);
     if (e->staging_bytes > 0xF0000000ull) e->staging_bytes = 0xF0000000ull;
     e->max_records_per_slot = e->staging_bytes / 40 + 16;  // a record is at least 36 bytes
-    e->ring_log2 = cfg->cov_ring_log2 ? cfg->cov_ring_log2 : 26;
+    e->ring_log2 = cfg->cov_ring_log2 ? cfg->cov_ring_log2 : 28;
     if (e->ring_log2 < 13 || e->ring_log2 > 30) { set_error(e, "bqc_create: cov_ring_log2 out of range"); delete e; return BQC_ERR_ARG; }
 
     int rc = [&]() -> int {
@@ -470,6 +478,44 @@ static int host_scan(bqc_engine* e, const uint8_t* data, const uint64_t* offs, u
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-family kernel timing
+// ------------------------------------------------------------------------------------------------
+struct ProfScope {  // records an event pair around the launches of one kernel family
+    bqc_engine* e;
+    bqc_engine::ProfEv ev;
+    bool on;
+    ProfScope(bqc_engine* e_, int family) : e(e_), on(e_->profiling) {
+        if (!on) return;
+        auto get = [&]() { cudaEvent_t x; if (e->prof_pool.empty()) cudaEventCreate(&x); else { x = e->prof_pool.back(); e->prof_pool.pop_back(); } return x; };
+        ev.family = family;
+        ev.a = get();
+        ev.b = get();
+        cudaEventRecord(ev.a, e->compute);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(ev.b, e->compute);
+        e->prof_pending.push_back(ev);
+    }
+};
+extern "C" void bqc_profile_enable(bqc_engine* e, int on) { e->profiling = on != 0; }
+// Accumulated device time per kernel family since the last call: 0 k_stats, 1 k_eightmer, 2 k_sketch,
+// 3 coverage flush (3 kernels per launch group), 4 merge/export.  Synchronises the compute stream.
+extern "C" int bqc_profile_read(bqc_engine* e, double ms_out[8], uint64_t n_out[8]) {
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->compute));
+    for (auto& p : e->prof_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { e->prof_ms[p.family] += ms; e->prof_n[p.family] += 1; }
+        e->prof_pool.push_back(p.a);
+        e->prof_pool.push_back(p.b);
+    }
+    e->prof_pending.clear();
+    for (int i = 0; i < 8; ++i) { ms_out[i] = e->prof_ms[i]; n_out[i] = e->prof_n[i]; e->prof_ms[i] = 0; e->prof_n[i] = 0; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // kernel launches for one device-resident batch
 // ------------------------------------------------------------------------------------------------
 static int launch_cov_flush(bqc_engine* e, uint32_t lane, uint64_t from_abs, uint64_t to_abs) {
@@ -482,6 +528,7 @@ static int launch_cov_flush(bqc_engine* e, uint32_t lane, uint64_t from_abs, uin
     if (nchunks > e->cov_sums_cap) { set_error(e, "coverage flush larger than the ring"); return BQC_ERR_ARG; }
     int grid = (int)std::min<uint64_t>(nchunks, (uint64_t)e->n_sm * 2);
     unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
+    ProfScope prof(e, 3);
     k_cov_chunk_sums<<<grid, 1024, 0, e->compute>>>(ring, mask, start, len, e->d_cov_sums);
     k_cov_scan_sums<<<1, 1024, 0, e->compute>>>(e->d_cov_sums, nchunks, e->d_cov_carry + lane);
     k_cov_apply<<<grid, 1024, 0, e->compute>>>(ring, mask, start, len, e->d_cov_sums, poscov);
@@ -517,40 +564,58 @@ static int run_device_batch(bqc_engine* e, const DeviceBatch& d) {
     if (bps < 1) { set_error(e, "k_stats does not fit: %zu bytes of shared memory", stats_smem); return BQC_ERR_ARG; }
     e->stats_blocks_per_sm = bps;
     const uint64_t ring_size = 1ull << e->ring_log2;
+    const uint64_t n = d.n_records;
+    for (uint32_t lane = 0; lane < e->n_lanes && n; ++lane) {
+        // the table kernels see the whole batch once ...
+        BatchView B;
+        B.bytes = d.bytes;
+        B.offsets = d.offsets;
+        B.cov = d.cov;
+        B.rec_lane = d.rec_lane;
+        B.n_records = (uint32_t)n;
+        B.cycb = cycb;
+        B.first_record = d.first_record;
+        B.ring_base = 0;
+        int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * bps);
+        { ProfScope prof(e, 0); k_stats<<<grid, kStatsThreads, stats_smem, e->compute>>>(E, B, lane); }
+        int g8 = (int)std::min<uint64_t>(2 * ((n + kEightThreads - 1) / kEightThreads), (uint64_t)(e->n_sm & ~1));
+        if (g8 < 2) g8 = 2;
+        { ProfScope prof(e, 1); k_eightmer<<<g8, kEightThreads, 32768 * 4, e->compute>>>(E, B, lane); }
+        e->launches += 2;
+        for (uint32_t qi = 0; qi < e->qlist.size(); ++qi)
+            for (uint32_t ki = 0; ki < e->klist.size(); ++ki) {
+                SketchParams SP;
+                SP.k = (uint32_t)e->klist[ki];
+                SP.q_thresh = (int32_t)(int8_t)(char)(e->cfg.q_base + e->qlist[qi]);
+                SP.qk = qi * (uint32_t)e->klist.size() + ki;
+                int gs = (int)std::min<uint64_t>((n + kSketchThreads - 1) / kSketchThreads, (uint64_t)e->n_sm);
+                ProfScope prof(e, 2);
+                if (e->L.f2size <= 32768u)
+                    k_sketch<true><<<gs, kSketchThreads, e->L.f2size * 4, e->compute>>>(E, B, lane, SP, e->d_hash + ki);
+                else
+                    k_sketch<false><<<gs, kSketchThreads, 0, e->compute>>>(E, B, lane, SP, e->d_hash + ki);
+                e->launches += 1;
+            }
+    }
+    // ... the coverage ring is fed and drained segment by segment (a segment is what fits the ring)
     for (const Segment& sg : d.segs) {
-        uint64_t n = sg.r1 - sg.r0;
+        uint64_t ns = sg.r1 - sg.r0;
         for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
-            if (n) {
+            if (ns) {
                 BatchView B;
                 B.bytes = d.bytes;
                 B.offsets = d.offsets + sg.r0;
                 B.cov = d.cov + sg.r0;
                 B.rec_lane = d.rec_lane ? d.rec_lane + sg.r0 : nullptr;
-                B.n_records = (uint32_t)n;
+                B.n_records = (uint32_t)ns;
                 B.cycb = cycb;
                 B.first_record = d.first_record + sg.r0;
                 B.ring_base = (uint32_t)((sg.base_window[lane] * 1000) & (ring_size - 1));
-                int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * bps);
-                k_stats<<<grid, kStatsThreads, stats_smem, e->compute>>>(E, B, lane);
-                int g8 = (int)std::min<uint64_t>(2 * ((n + kEightThreads - 1) / kEightThreads), (uint64_t)(e->n_sm & ~1));
-                if (g8 < 2) g8 = 2;
-                k_eightmer<<<g8, kEightThreads, 32768 * 4, e->compute>>>(E, B, lane);
-                e->launches += 2;
-                for (uint32_t qi = 0; qi < e->qlist.size(); ++qi)
-                    for (uint32_t ki = 0; ki < e->klist.size(); ++ki) {
-                        SketchParams SP;
-                        SP.k = (uint32_t)e->klist[ki];
-                        SP.q_thresh = (int32_t)(int8_t)(char)(e->cfg.q_base + e->qlist[qi]);
-                        SP.qk = qi * (uint32_t)e->klist.size() + ki;
-                        int gs = (int)std::min<uint64_t>((n + kSketchThreads - 1) / kSketchThreads, (uint64_t)e->n_sm);
-                        if (e->L.f2size <= 32768u)
-                            k_sketch<true><<<gs, kSketchThreads, e->L.f2size * 4, e->compute>>>(E, B, lane, SP, e->d_hash + ki);
-                        else
-                            k_sketch<false><<<gs, kSketchThreads, 0, e->compute>>>(E, B, lane, SP, e->d_hash + ki);
-                        e->launches += 1;
-                    }
+                int grid = (int)std::min<uint64_t>((ns + 255) / 256, (uint64_t)e->n_sm * 8);
+                ProfScope prof(e, 3);
+                k_cov_scatter<<<grid, 256, 0, e->compute>>>(E, B, lane);
+                e->launches += 1;
             }
-            // flush the coverage windows this segment completed
             uint64_t from = sg.base_window[lane] * 1000;
             int rc = launch_cov_flush(e, lane, from, sg.flush_to[lane]);
             if (rc) return rc;
@@ -618,9 +683,16 @@ extern "C" int bqc_submit(bqc_engine* e, const void* data, size_t n_bytes, const
     const uint8_t* first = src + record_offsets[0];
     size_t span = (size_t)(record_offsets[n_records] - record_offsets[0]);
     const uint8_t* h2d_src = first;
-    if (first < s.pinned || first + span > s.pinned + e->staging_bytes + 256) {  // not our pinned buffer: stage it
-        memcpy(s.pinned, first, span);
-        h2d_src = s.pinned;
+    if (first < s.pinned || first + span > s.pinned + e->staging_bytes + 256) {
+        // not our staging buffer: page-locked memory of the caller is copied from directly, pageable
+        // memory is staged through the pinned buffer
+        cudaPointerAttributes attr;
+        bool pinned = cudaPointerGetAttributes(&attr, first) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (!pinned) {
+            memcpy(s.pinned, first, span);
+            h2d_src = s.pinned;
+        }
     }
     d.n_records = n_records;
     d.n_bytes = span;

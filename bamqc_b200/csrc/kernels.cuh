@@ -431,31 +431,7 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
                 if ((mapped || !(flag & 0x8u)) && !(flag & 0x400u)) atomicAdd(sm + S.sc + S_FIRST_AND_OR_SECOND_MAPPED, 1u);
                 if ((flag & 0x2u) && !(flag & 0x400u)) atomicAdd(sm + S.sc + S_AUTO_PROPERPAIR, 1u);
             }
-            // coverage (src/OverallNumbers.hpp:79-135): the window anchor comes from the host scan
-            // (cov code), here only the commutative part: +1/-1 into the difference ring.
-            if (mapped && !(flag & 0x400u) && B.cov) {
-                uint32_t code = B.cov[rec];
-                if (code != kNone) {
-                    uint32_t pos = code & 2047u;
-                    uint32_t base_idx = B.ring_base + (code >> 11) * 1000u + pos;
-                    uint32_t lim = 2000u - pos;
-                    uint32_t* ring = E.ring + (uint64_t)lane * ((uint64_t)E.ring_mask + 1);
-                    uint32_t c = 0;
-                    for (uint32_t i = 0; i < h.ncig; ++i) {
-                        uint32_t ce = ldu32(h.p + h.o_cig + 4 * (rc ? (h.ncig - 1 - i) : i));
-                        uint32_t op = ce & 15u, n = ce >> 4;
-                        if (op == 4u) c += n;
-                        if (op == 0u || op == 2u) {
-                            if (c < lim && n > 0) {
-                                uint32_t hi = min(c + n, lim);
-                                atomicAdd(ring + ((base_idx + c) & E.ring_mask), 1u);
-                                atomicAdd(ring + ((base_idx + hi) & E.ring_mask), 0xFFFFFFFFu);
-                            }
-                            c += n;
-                        }
-                    }
-                }
-            }
+            // OverallNumbers::coverage (:430-433) is handled by k_cov_scatter + k_cov_* below.
         }
     }
     __syncthreads();
@@ -553,21 +529,30 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch(EngineView E, Batc
     const uint32_t k = SP.k;
     unsigned long long my_count = 0;
 
-    for (uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x; rec < B.n_records; rec += gridDim.x * blockDim.x) {
-        if (B.rec_lane && B.rec_lane[rec] != lane) continue;
-        const uint32_t off = B.offsets[rec];
+    // Control flow is kept warp-uniform (one record per lane, common trip count, __syncwarp per base):
+    // with independent thread scheduling the lanes otherwise drift apart after the first CAS loop and the
+    // per-base loop runs one lane at a time (measured: 2 active threads per instruction).
+    const uint32_t lane_id = threadIdx.x & 31u;
+    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < B.n_records; r0 += gridDim.x * blockDim.x) {
+        const uint32_t rec = r0 + lane_id;
         RecHdr h;
-        if (!decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h)) continue;
-        if ((h.flag & 0xF00u) || !(h.flag & 0xC0u)) continue;  // primary, not QC-fail, not duplicate (:439-442)
-        const uint32_t Ls = (uint32_t)h.lseq;
-        if (Ls < k) continue;
-        const uint32_t s = (h.flag >> 4) & 1u;
-        const uint8_t* seqp = h.p + h.o_seq;
-        const uint8_t* qualp = h.p + h.o_qual;
+        bool act = rec < B.n_records && !(B.rec_lane && B.rec_lane[rec] != lane);
+        if (act) {
+            const uint32_t off = B.offsets[rec];
+            act = decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h);
+        }
+        // primary, not QC-fail, not duplicate (src/bamqualcheck.cpp:439-442); l >= k (ReadQualityHasher.hpp:35)
+        act = act && !(h.flag & 0xF00u) && (h.flag & 0xC0u) && (uint32_t)h.lseq >= k;
+        const uint32_t Ls = act ? (uint32_t)h.lseq : 0u;
+        const uint32_t maxL = __reduce_max_sync(0xFFFFFFFFu, Ls);
+        const uint32_t s = act ? ((h.flag >> 4) & 1u) : 0u;
+        const uint8_t* seqp = act ? h.p + h.o_seq : B.bytes;
+        const uint8_t* qualp = act ? h.p + h.o_qual : B.bytes;
         uint64_t hlo = 0, hhi = 0, tlo = 0, thi = 0;
         uint64_t seqw = 0, qualw = 0, lagw = 0;
         uint32_t run = 0;
-        for (uint32_t i = 0; i < Ls; ++i) {
+        for (uint32_t i = 0; i < maxL; ++i, __syncwarp()) {
+            if (i >= Ls) continue;
             if ((i & 15u) == 0) seqw = ldu64(seqp + (i >> 1));
             if ((i & 7u) == 0) qualw = ldu64(qualp + i);
             uint32_t nin = nib_of(seqw, i & 15u);
@@ -623,6 +608,42 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch(EngineView E, Batc
 // coverage windows (src/OverallNumbers.hpp:59-77): depth = prefix sum of the difference ring over the
 // flushed range, poscov[min(depth,100)]++ for every position, ring range zeroed for reuse.
 // ------------------------------------------------------------------------------------------------
+// k_cov_scatter: OverallNumbers::coverage (src/OverallNumbers.hpp:79-135).  The window anchor is the only
+// order-dependent piece of the reference; it comes from the host scan as a per-record code
+// (window << 11 | pos).  Here only the commutative part: for every M/D run of the read-oriented CIGAR
+// (S lengths added to the offset, as the reference does) +1 at its first position and -1 one past its
+// last, clipped at pos + j < 2*vsize where the reference's writes leave v2.
+__global__ void __launch_bounds__(256) k_cov_scatter(EngineView E, BatchView B, uint32_t lane) {
+    uint32_t* ring = E.ring + (uint64_t)lane * ((uint64_t)E.ring_mask + 1);
+    for (uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x; rec < B.n_records; rec += gridDim.x * blockDim.x) {
+        const uint32_t code = B.cov[rec];
+        if (code == kNone) continue;
+        if (B.rec_lane && B.rec_lane[rec] != lane) continue;
+        const uint8_t* p = B.bytes + B.offsets[rec];
+        const uint32_t x = ldu32(p + 12), y = ldu32(p + 16);
+        const uint32_t lname = x & 255u, ncig = y & 0xFFFFu;
+        const bool rc = ((y >> 16) & 0x10u) != 0;
+        const uint8_t* cig = p + 36u + lname;
+        const uint32_t pos = code & 2047u;
+        const uint32_t base_idx = B.ring_base + (code >> 11) * 1000u + pos;
+        const uint32_t lim = 2000u - pos;
+        uint32_t c = 0;
+        for (uint32_t i = 0; i < ncig; ++i) {
+            uint32_t ce = ldu32(cig + 4 * (rc ? (ncig - 1 - i) : i));
+            uint32_t op = ce & 15u, n = ce >> 4;
+            if (op == 4u) c += n;
+            if (op == 0u || op == 2u) {
+                if (c < lim && n > 0) {
+                    uint32_t hi = min(c + n, lim);
+                    atomicAdd(ring + ((base_idx + c) & E.ring_mask), 1u);
+                    atomicAdd(ring + ((base_idx + hi) & E.ring_mask), 0xFFFFFFFFu);
+                }
+                c += n;
+            }
+        }
+    }
+}
+
 static const uint32_t kCovChunk = 4096;  // ring entries per CTA step (1024 threads x 4)
 __global__ void __launch_bounds__(1024) k_cov_chunk_sums(const uint32_t* ring, uint32_t ring_mask, uint32_t start, uint64_t len, uint32_t* sums) {
     __shared__ uint32_t wsum[32];

@@ -150,6 +150,17 @@ class Engine:
     def kernel_launches(self):
         return int(self.lib.bqc_kernel_launches(self.handle))
 
+    def profile_enable(self, on=True):
+        self.lib.bqc_profile_enable(self.handle, 1 if on else 0)
+
+    def profile_read(self):
+        """{family: (milliseconds, launch groups)} since the previous read (CUDA events on the compute stream)."""
+        ms = (ctypes.c_double * 8)()
+        n = (ctypes.c_uint64 * 8)()
+        self._check(self.lib.bqc_profile_read(self.handle, ms, n))
+        names = ["k_stats", "k_eightmer", "k_sketch", "k_cov", "merge"]
+        return {names[i]: (float(ms[i]), int(n[i])) for i in range(5)}
+
     # ---- multi-GPU merge ----------------------------------------------------------------------------
     def counters_len(self):
         return int(self.lib.bqc_counters_len(self.handle))

@@ -53,7 +53,7 @@ typedef struct bqc_config {
     int32_t seed;                 /* -s (RepHash table, src/kmerstream/RepHash.cpp:4-17); 0 is rejected */
     int32_t max_read_len;         /* per-cycle table capacity; 0 => 512.  Longer reads => BQC_ERR_UNSUPPORTED */
     uint64_t staging_bytes;       /* capacity of each pinned staging buffer; 0 => 256 MiB */
-    uint32_t cov_ring_log2;       /* log2 entries of the coverage depth ring; 0 => 26 */
+    uint32_t cov_ring_log2;       /* log2 entries of the coverage depth ring; 0 => 28 (1 GiB) */
 } bqc_config;
 
 typedef struct bqc_error_info {
@@ -98,6 +98,12 @@ int bqc_sync(bqc_engine* e);             /* wait for all enqueued work; returns 
 void* bqc_stream(bqc_engine* e);         /* cudaStream_t the kernels run on (for CUDA-event timing) */
 uint64_t bqc_kernel_launches(bqc_engine* e); /* kernels launched by this engine so far */
 int bqc_get_error(bqc_engine* e, bqc_error_info* out); /* sticky device/host error (code 0 if none) */
+
+/* Optional device timing of each kernel family with CUDA events on the compute stream.
+ * bqc_profile_read: milliseconds and launch-group counts accumulated since the previous read, per family:
+ * 0 k_stats, 1 k_eightmer, 2 k_sketch, 3 coverage flush, 4 merge/export. */
+void bqc_profile_enable(bqc_engine* e, int on);
+int bqc_profile_read(bqc_engine* e, double ms_out[8], uint64_t n_out[8]);
 
 /* End of input: flush the last two coverage windows (src/bamqualcheck.cpp:447-453).  After this the
  * device tables are final for this GPU.  Idempotent until the next bqc_reset. */
