@@ -310,8 +310,8 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         CU(cudaMalloc(&e->d_sketch, std::max<uint64_t>(4, e->n_lanes * e->n_qk * e->sketch_words_per_qk * 4)));
         CU(cudaMalloc(&e->d_ring, (uint64_t)e->n_lanes * (1ull << e->ring_log2) * 4));
         CU(cudaMalloc(&e->d_cov_carry, e->n_lanes * 4));
-        e->cov_sums_cap = ((1ull << e->ring_log2) + kCovChunk - 1) / kCovChunk + 1;
-        CU(cudaMalloc(&e->d_cov_sums, e->cov_sums_cap * 4));
+        e->cov_sums_cap = ((1ull << e->ring_log2) + kCovTile - 1) / kCovTile + 2;
+        CU(cudaMalloc(&e->d_cov_sums, e->cov_sums_cap * 8));
         CU(cudaMalloc(&e->d_error, 8));
         int nref = std::max(1, cfg->n_ref);
         CU(cudaMalloc((void**)&e->d_ref, nref * sizeof(uint32_t*)));
@@ -524,15 +524,16 @@ static int launch_cov_flush(bqc_engine* e, uint32_t lane, uint64_t from_abs, uin
     uint32_t mask = (uint32_t)((1ull << e->ring_log2) - 1);
     uint32_t* ring = e->d_ring + (uint64_t)lane * (1ull << e->ring_log2);
     uint32_t start = (uint32_t)(from_abs & mask);
-    uint64_t nchunks = (len + kCovChunk - 1) / kCovChunk;
-    if (nchunks > e->cov_sums_cap) { set_error(e, "coverage flush larger than the ring"); return BQC_ERR_ARG; }
-    int grid = (int)std::min<uint64_t>(nchunks, (uint64_t)e->n_sm * 2);
+    uint64_t ntiles = (len + kCovTile - 1) / kCovTile;
+    if (ntiles + 1 > e->cov_sums_cap) { set_error(e, "coverage flush larger than the ring"); return BQC_ERR_ARG; }
+    int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)e->n_sm * 2);
     unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
     ProfScope prof(e, 3);
-    k_cov_chunk_sums<<<grid, 1024, 0, e->compute>>>(ring, mask, start, len, e->d_cov_sums);
-    k_cov_scan_sums<<<1, 1024, 0, e->compute>>>(e->d_cov_sums, nchunks, e->d_cov_carry + lane);
-    k_cov_apply<<<grid, 1024, 0, e->compute>>>(ring, mask, start, len, e->d_cov_sums, poscov);
-    e->launches += 3;
+    // tile states + ticket live in one buffer: [0] = ticket, [1..] = states
+    CU(cudaMemsetAsync(e->d_cov_sums, 0, (ntiles + 1) * 8, e->compute));
+    k_cov_flush<<<grid, 1024, 0, e->compute>>>(ring, mask, start, len, e->d_cov_carry + lane, (unsigned long long*)e->d_cov_sums + 1,
+                                               (uint32_t*)e->d_cov_sums, poscov);
+    e->launches += 1;
     CU(cudaGetLastError());
     return 0;
 }

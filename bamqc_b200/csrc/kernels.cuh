@@ -244,221 +244,9 @@ __device__ __forceinline__ void bump(uint32_t* sm, uint32_t smcap, uint64_t* g, 
     else report_error(E, rec, 16 /*BQC_ERR_UNSUPPORTED*/);
 }
 
-__global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView B, uint32_t lane) {
-    extern __shared__ uint32_t sm[];
-    const StatsSmem S = stats_smem_layout(B.cycb, E.insert_smem);
-    for (uint32_t i = threadIdx.x; i < S.total; i += blockDim.x) sm[i] = 0;
-    __syncthreads();
-    const Layout& L = E.L;
-    uint64_t* G = E.counters + (uint64_t)lane * L.lane_stride;
-    const uint32_t cycb = B.cycb;
-
-    for (uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x; rec < B.n_records; rec += gridDim.x * blockDim.x) {
-        if (B.rec_lane && B.rec_lane[rec] != lane) continue;
-        const uint64_t grec = B.first_record + rec;
-        const uint32_t off = B.offsets[rec];
-        RecHdr h;
-        if (!decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h)) { report_error(E, grec, 4); continue; }
-        const uint32_t flag = h.flag;
-        const uint32_t Ls = (uint32_t)h.lseq;
-        const bool primary = !(flag & 0x900u);
-        const bool isfirst = (flag & 0x40u) != 0;
-        const bool hasmate = (flag & 0xC0u) != 0;
-        const uint32_t mate = isfirst ? 0u : 1u;
-        const bool rc = (flag & 0x10u) != 0;
-        const bool mapped = !(flag & 0x4u);
-        const bool inmain = h.rid >= 0 && h.rid < E.n_ref && E.main_chrom[h.rid];
-
-        // CIGAR summary (needed by mis_match, cigar_count and the triplet filter)
-        uint32_t delc = 0, insc = 0, clipped = 0, first_op = 0, last_op = 0;
-        if (primary) {
-            for (uint32_t i = 0; i < h.ncig; ++i) {
-                uint32_t c = ldu32(h.p + h.o_cig + 4 * i);
-                uint32_t op = c & 15u, n = c >> 4;
-                if (op == 2) delc += n;
-                else if (op == 1) insc += n;
-                else if (op == 4 || op == 5) clipped += n;
-                if (i == 0) first_op = c;
-                if (i == h.ncig - 1) last_op = c;
-            }
-        }
-        const bool do_cig = primary && hasmate && inmain && mapped;  // src/bamqualcheck.cpp:392-428
-        uint64_t* GM = G + L.o_mate0 + mate * L.mate_stride;
-        AuxInfo ai = aux_walk(h, [&](uint32_t nm) {
-            if (do_cig) bump(sm + S.mm + mate * kHS, kHS, GM + L.m_mismatch, L.mmcap, nm - delc - insc, E, grec);
-        });
-        // getLane(): src/bamqualcheck.cpp:72-100
-        if (ai.rg == 2) { report_error(E, grec, 1); continue; }
-        if (ai.rg == 0) { report_error(E, grec, 5); continue; }
-        // gate: src/bamqualcheck.cpp:318-335
-        if (flag & 0x800u) { atomicAdd(sm + S.sc + S_SUPPLEMENTARY, 1u); continue; }
-        if (flag & 0x100u) { atomicAdd(sm + S.sc + S_NOT_PRIMARY, 1u); continue; }
-        if (flag & 0x400u) atomicAdd(sm + S.sc + S_DUPLICATES, 1u);
-        if (flag & 0x200u) atomicAdd(sm + S.sc + S_QCFAILED, 1u);
-        if (Ls > L.cyc || Ls > cycb) { report_error(E, grec, 16); continue; }
-
-        // ---- TripletCounting (src/TripletCounting.hpp:136-236), aligned orientation -------------------
-        if (!(flag & 0x600u)) {
-            bool elig = (flag & 0x1u) && (flag & 0x2u) && mapped && !(flag & 0x8u) && h.mapq >= 60u;
-            if (elig) {
-                if (ai.as_state != 1 || ai.as_value < 0) { report_error(E, grec, 3); continue; }
-                elig = ai.as_value >= 50 && clipped == 0;
-            }
-            const uint32_t* ref = (elig && E.ref && h.rid >= 0 && h.rid < E.n_ref) ? E.ref[h.rid] : nullptr;
-            if (elig && ref && h.ncig > 0 && Ls >= 3) {
-                const uint64_t reflen = E.ref_len[h.rid];
-                const uint32_t grp = (rc ? 2u : 0u) + (isfirst ? 0u : 1u);
-                uint32_t* tri = sm + S.tri;
-                const uint8_t* seqp = h.p + h.o_seq;
-                const uint8_t* qualp = h.p + h.o_qual;
-                uint32_t it = 0;
-                uint64_t cc = (uint64_t)(first_op >> 4) - 1;  // size_t arithmetic as in the reference (wraps for count 0)
-                uint64_t chromPos = (uint64_t)(uint32_t)h.pos + 1;
-                uint32_t readPos = 1;
-                uint32_t seq_chunk = kNone, qual_chunk = kNone, ref_chunk = kNone;
-                uint64_t seqw = 0, qualw = 0;
-                uint32_t refw = 0;
-                auto nib_at = [&](uint32_t i) -> uint32_t {
-                    if ((i >> 4) != seq_chunk) { seq_chunk = i >> 4; seqw = ldu64(seqp + 8 * seq_chunk); }
-                    return nib_of(seqw, i & 15u);
-                };
-                auto ref_at = [&](uint64_t x) -> uint32_t {
-                    uint32_t c = (uint32_t)(x >> 4);
-                    if (c != ref_chunk) { ref_chunk = c; refw = __ldg(ref + c); }
-                    return (refw >> (2 * ((uint32_t)x & 15u))) & 3u;
-                };
-                bool ok = true;
-                for (; readPos < Ls - 1; ++readPos, ++chromPos, --cc) {
-                    while (cc == 0) {
-                        ++it;
-                        if (it >= h.ncig) { ok = false; break; }  // reference reads past the CIGAR here (undefined)
-                        uint32_t c = ldu32(h.p + h.o_cig + 4 * it);
-                        uint32_t op = c & 15u, n = c >> 4;
-                        if (op == 2 || op == 3 || op == 5 || op == 6) chromPos += n;
-                        else if (op == 4 || op == 1) readPos += n;
-                        else cc = n;
-                    }
-                    if (!ok || readPos >= Ls - 1) break;
-                    if ((readPos >> 3) != qual_chunk) { qual_chunk = readPos >> 3; qualw = ldu64(qualp + 8 * qual_chunk); }
-                    uint32_t q = (uint32_t)(qualw >> (8 * (readPos & 7u))) & 255u;
-                    if ((int8_t)(q + 33u) < (int8_t)53) continue;  // read.qual[readPos] < minBaseQAscii, char compare
-                    uint32_t nb = nib_at(readPos);
-                    uint32_t base = dna5_of(nb);
-                    if (base == 4u) continue;
-                    uint32_t np = nib_at(readPos - 1), nn = nib_at(readPos + 1);
-                    if (np == 15u || nn == 15u) continue;
-                    if (chromPos + 2 > reflen) continue;  // context past the contig end (undefined in the reference)
-                    uint32_t c0 = ref_at(chromPos - 1), c1 = ref_at(chromPos), c2 = ref_at(chromPos + 1);
-                    if (np != (1u << c0) || nn != (1u << c2)) continue;  // flanks must equal the context as chars
-                    atomicAdd(tri + ((c0 << 4) + (c1 << 2) + c2) * 16u + grp * 4u + base, 1u);
-                }
-            }
-        }
-
-        // ---- src/bamqualcheck.cpp:353-389 ------------------------------------------------------------
-        if (!hasmate) { report_error(E, grec, 2); continue; }
-        atomicAdd(sm + S.sc + S_READCOUNT, 1u);
-        atomicAdd(sm + S.sc + S_TOTALBPS, Ls);
-        {   // QualityCheck::get_count (src/QualityCheck.hpp:111-176) on the read-oriented SEQ/QUAL
-            uint32_t* pc = sm + S.pc + mate * PC_ROWS * cycb;
-            const uint8_t* seqp = h.p + h.o_seq;
-            const uint8_t* qualp = h.p + h.o_qual;
-            uint32_t cntN = 0, cntGC = 0, sumQ = 0;
-            uint64_t seqw = 0, qualw = 0;
-            for (uint32_t i = 0; i < Ls; ++i) {
-                if ((i & 15u) == 0) seqw = ldu64(seqp + (i >> 1));
-                if ((i & 7u) == 0) qualw = ldu64(qualp + i);
-                uint32_t nb = nib_of(seqw, i & 15u);
-                uint32_t q = (uint32_t)(qualw >> (8 * (i & 7u))) & 255u;
-                uint32_t d = dna5_of(nb);
-                if (rc && d < 4u) d = 3u - d;
-                uint32_t cyc = rc ? (Ls - 1 - i) : i;
-                atomicAdd(pc + d * cycb + cyc, 1u);
-                atomicAdd(pc + PC_QUAL * cycb + cyc, q);
-                cntN += (nb == 15u);
-                cntGC += (nb == 2u || nb == 4u);
-                sumQ += q;
-            }
-            atomicAdd((unsigned long long*)(GM + L.m_readnr), 1ULL);
-            atomicAdd(sm + S.nc + mate * (cycb + 8) + cntN, 1u);
-            atomicAdd(sm + S.gc + mate * (cycb + 8) + cntGC, 1u);
-            if (Ls > 0) {
-                uint32_t rnd = (2u * sumQ + Ls) / (2u * Ls);   // round(double(S)/L), exact
-                uint32_t cel = (sumQ + Ls - 1u) / Ls;          // ceil(double(S)/L)
-                bump(sm + S.aq + mate * kQS, kQS, GM + L.m_avgq, kQCap, rnd, E, grec);
-                bump(sm + S.cq + mate * kQS, kQS, GM + L.m_ceilq, kQCap, cel, E, grec);
-            }
-            atomicAdd(sm + S.rl + mate * (cycb + 8) + Ls, 1u);
-        }
-        if (isfirst) {
-            if (!mapped) {
-                atomicAdd(sm + S.sc + S_FIRSTUNMAPPED, 1u);
-                if (flag & 0x8u) atomicAdd(sm + S.sc + S_BOTHUNMAPPED, 1u);
-            }
-            if (flag & 0x2u) {
-                atomicAdd(sm + S.sc + S_PROPERPAIR, 1u);
-                if (((flag >> 4) & 1u) == ((flag >> 5) & 1u)) atomicAdd(sm + S.sc + S_FF_RR, 1u);
-            }
-        } else if (!mapped) {
-            atomicAdd(sm + S.sc + S_SECONDUNMAPPED, 1u);
-        }
-
-        // ---- main chromosomes only: src/bamqualcheck.cpp:392-434 ---------------------------------------
-        if (inmain) {
-            if (mapped) {
-                // cigar_count (src/QualityCheck.hpp:222-271) on the read-oriented CIGAR
-                if (h.ncig == 0) { report_error(E, grec, 16); continue; }
-                uint32_t fo = rc ? last_op : first_op, lo = rc ? first_op : last_op;
-                uint32_t* pc = sm + S.pc + mate * PC_ROWS * cycb;
-                if ((fo & 15u) == 4u) {
-                    uint32_t n = min(fo >> 4, cycb);
-                    for (uint32_t j = 0; j < n; ++j) atomicAdd(pc + PC_SC5 * cycb + j, 1u);
-                } else if ((lo & 15u) == 4u) {
-                    uint32_t n = lo >> 4;
-                    for (uint32_t j = (n <= Ls ? Ls - n : Ls); j < Ls; ++j) atomicAdd(pc + PC_SC3 * cycb + j, 1u);
-                }
-                bump(sm + S.dl + mate * kHS, kHS, GM + L.m_del, L.delcap, delc, E, grec);
-                bump(sm + S.in + mate * kHS, kHS, GM + L.m_ins, L.mmcap, insc, E, grec);
-                atomicAdd(sm + S.mq + mate * kMapqCap + h.mapq, 1u);  // map_Q :178-185
-                if (isfirst && !(flag & 0x8u) && h.nrid >= 0 && h.nrid < E.n_ref && E.main_chrom[h.nrid]) {
-                    uint32_t idx = (uint32_t)(h.tlen < 0 ? -(int64_t)h.tlen : (int64_t)h.tlen);  // insert_size :187-196
-                    if (idx >= L.isize1) idx = L.isize1 - 1;
-                    if (idx < E.insert_smem) atomicAdd(sm + S.isz + idx, 1u);
-                    else atomicAdd((unsigned long long*)(G + L.o_insert + idx), 1ULL);
-                }
-            }
-            if (isfirst) {
-                if ((mapped || !(flag & 0x8u)) && !(flag & 0x400u)) atomicAdd(sm + S.sc + S_FIRST_AND_OR_SECOND_MAPPED, 1u);
-                if ((flag & 0x2u) && !(flag & 0x400u)) atomicAdd(sm + S.sc + S_AUTO_PROPERPAIR, 1u);
-            }
-            // OverallNumbers::coverage (:430-433) is handled by k_cov_scatter + k_cov_* below.
-        }
-    }
-    __syncthreads();
-    // ---- flush the CTA-private tables (skip zeros) ---------------------------------------------------
-    auto flush = [&](uint32_t smo, uint32_t n, uint64_t* g) {
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            uint32_t v = sm[smo + i];
-            if (v) atomicAdd((unsigned long long*)(g + i), (unsigned long long)v);
-        }
-    };
-    for (uint32_t m = 0; m < 2; ++m) {
-        uint64_t* GMm = G + L.o_mate0 + m * L.mate_stride;
-        for (uint32_t r = 0; r < PC_ROWS; ++r) flush(S.pc + (m * PC_ROWS + r) * cycb, cycb, GMm + L.m_pc + r * pad8(L.cyc));
-        flush(S.rl + m * (cycb + 8), cycb + 1, GMm + L.m_readlen);
-        flush(S.nc + m * (cycb + 8), cycb + 1, GMm + L.m_ncount);
-        flush(S.gc + m * (cycb + 8), cycb + 1, GMm + L.m_gccount);
-        flush(S.aq + m * kQS, kQS, GMm + L.m_avgq);
-        flush(S.cq + m * kQS, kQS, GMm + L.m_ceilq);
-        flush(S.mq + m * kMapqCap, kMapqCap, GMm + L.m_mapq);
-        flush(S.mm + m * kHS, kHS, GMm + L.m_mismatch);
-        flush(S.dl + m * kHS, kHS, GMm + L.m_del);
-        flush(S.in + m * kHS, kHS, GMm + L.m_ins);
-    }
-    flush(S.isz, E.insert_smem, G + L.o_insert);
-    flush(S.tri, kTriplet, G + L.o_triplet);
-    flush(S.sc, S_COUNT, G + L.o_scalars);
-}
+}  // namespace bqc
+#include "kernel_stats.cuh"
+namespace bqc {
 
 // ------------------------------------------------------------------------------------------------
 // k_eightmer: OverallNumbers::count8mers (src/OverallNumbers.hpp:137-168)
@@ -644,61 +432,39 @@ __global__ void __launch_bounds__(256) k_cov_scatter(EngineView E, BatchView B, 
     }
 }
 
-static const uint32_t kCovChunk = 4096;  // ring entries per CTA step (1024 threads x 4)
-__global__ void __launch_bounds__(1024) k_cov_chunk_sums(const uint32_t* ring, uint32_t ring_mask, uint32_t start, uint64_t len, uint32_t* sums) {
-    __shared__ uint32_t wsum[32];
-    for (uint64_t chunk = blockIdx.x; chunk * kCovChunk < len; chunk += gridDim.x) {
-        uint32_t acc = 0;
-        for (uint32_t j = 0; j < 4; ++j) {
-            uint64_t i = chunk * kCovChunk + j * 1024u + threadIdx.x;
-            if (i < len) acc += ring[(start + (uint32_t)i) & ring_mask];
-        }
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-        if ((threadIdx.x & 31u) == 0) wsum[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t v = wsum[threadIdx.x];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-            if (threadIdx.x == 0) sums[chunk] = v;
-        }
-        __syncthreads();
-    }
-}
-// exclusive scan of the chunk sums (single CTA), seeded with the carried depth; leaves the new carry
-__global__ void __launch_bounds__(1024) k_cov_scan_sums(uint32_t* sums, uint64_t nchunks, uint32_t* carry) {
-    __shared__ uint32_t part[1024];
-    uint64_t per = (nchunks + 1023) / 1024;
-    uint64_t b = threadIdx.x * per, e = min(b + per, nchunks);
-    uint32_t acc = 0;
-    for (uint64_t i = b; i < e; ++i) acc += sums[i];
-    part[threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = *carry;
-        for (int i = 0; i < 1024; ++i) { uint32_t t = part[i]; part[i] = run; run += t; }
-        *carry = run;
-    }
-    __syncthreads();
-    uint32_t run = part[threadIdx.x];
-    for (uint64_t i = b; i < e; ++i) { uint32_t t = sums[i]; sums[i] = run; run += t; }
-}
-__global__ void __launch_bounds__(1024) k_cov_apply(uint32_t* ring, uint32_t ring_mask, uint32_t start, uint64_t len, const uint32_t* sums, unsigned long long* poscov) {
+// Window flush = one pass over the ring range: single-pass prefix sum with decoupled look-back
+// (tile aggregate / inclusive-prefix flags), fused with the min(depth,100) histogram and the re-zeroing of
+// the ring.  8 bytes of HBM traffic per genome position (read + write), 16-byte vector accesses.
+static const uint32_t kCovTile = 8192;  // ring entries per tile (1024 threads x 8)
+static const uint32_t kTileAggregate = 1u, kTileInclusive = 2u;
+__global__ void __launch_bounds__(1024) k_cov_flush(uint32_t* ring, uint32_t ring_mask, uint32_t start, uint64_t len, uint32_t* carry,
+                                                    unsigned long long* tile_state, uint32_t* ticket, unsigned long long* poscov) {
     __shared__ uint32_t hist[128];
     __shared__ uint32_t wsum[32];
+    __shared__ uint32_t s_tile, s_prefix;
+    const uint64_t ntiles = (len + kCovTile - 1) / kCovTile;
     if (threadIdx.x < 128) hist[threadIdx.x] = 0;
     __syncthreads();
-    for (uint64_t chunk = blockIdx.x; chunk * kCovChunk < len; chunk += gridDim.x) {
-        // thread t owns 4 consecutive entries
-        uint64_t i0 = chunk * kCovChunk + 4ull * threadIdx.x;
-        uint32_t v[4];
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);  // tiles are handed out in order => no deadlock
+        __syncthreads();
+        const uint64_t tile = s_tile;
+        if (tile >= ntiles) break;
+        // ring offsets are multiples of 8 entries from a 16-byte aligned base, so the two uint4 never wrap apart
+        const uint64_t i0 = tile * kCovTile + 8ull * threadIdx.x;
+        uint32_t v[8];
+        const uint32_t ridx = (start + (uint32_t)i0) & ring_mask;
+        if (i0 + 8 <= len) {
+            uint4 a = *reinterpret_cast<const uint4*>(ring + ridx);
+            uint4 b = *reinterpret_cast<const uint4*>(ring + ((ridx + 4) & ring_mask));
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) v[j] = (i0 + j < len) ? ring[(ridx + j) & ring_mask] : 0u;
+        }
         uint32_t acc = 0;
 #pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            uint64_t i = i0 + j;
-            v[j] = (i < len) ? ring[(start + (uint32_t)i) & ring_mask] : 0u;
-            acc += v[j];
-        }
-        // CTA exclusive scan of acc
+        for (uint32_t j = 0; j < 8; ++j) acc += v[j];
         uint32_t incl = acc;
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -712,18 +478,58 @@ __global__ void __launch_bounds__(1024) k_cov_apply(uint32_t* ring, uint32_t rin
                 uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
                 if (threadIdx.x >= (uint32_t)o) wi += t;
             }
-            wsum[threadIdx.x] = wi - w;
+            wsum[threadIdx.x] = wi - w;  // exclusive warp offsets
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, wi, 31);
+            // publish, then look back over the predecessor tiles (one warp, one lane per predecessor)
+            uint32_t prefix = 0;
+            if (tile == 0) {
+                prefix = *carry;
+            } else {
+                if (threadIdx.x == 0) {
+                    atomicExch(tile_state + tile, ((unsigned long long)kTileAggregate << 32) | total);
+                }
+                int64_t look = (int64_t)tile - 1;
+                for (;;) {
+                    int64_t t = look - (int64_t)threadIdx.x;
+                    unsigned long long st = 0;
+                    if (t >= 0) {
+                        do { st = *((volatile unsigned long long*)(tile_state + t)); } while ((st >> 32) == 0);
+                    } else {
+                        st = (unsigned long long)kTileInclusive << 32;  // before tile 0: contributes nothing
+                    }
+                    const uint32_t flag = (uint32_t)(st >> 32), val = (uint32_t)st;
+                    const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, flag == kTileInclusive);
+                    // lanes up to and including the first inclusive one contribute
+                    const uint32_t first = incl_mask ? (uint32_t)(__ffs((int)incl_mask) - 1) : 32u;
+                    uint32_t contrib = (threadIdx.x <= first) ? val : 0u;
+                    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, o);
+                    prefix += contrib;
+                    if (incl_mask) break;
+                    look -= 32;
+                }
+            }
+            if (threadIdx.x == 0) {
+                atomicExch(tile_state + tile, ((unsigned long long)kTileInclusive << 32) | (uint32_t)(prefix + total));
+                s_prefix = prefix;
+                if (tile == ntiles - 1) *carry = prefix + total;
+            }
         }
         __syncthreads();
-        uint32_t depth = sums[chunk] + wsum[threadIdx.x >> 5] + (incl - acc);
+        uint32_t depth = s_prefix + wsum[threadIdx.x >> 5] + (incl - acc);
 #pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            uint64_t i = i0 + j;
-            if (i < len) {
+        for (uint32_t j = 0; j < 8; ++j) {
+            if (i0 + j < len) {
                 depth += v[j];
                 atomicAdd(hist + min(depth, 100u), 1u);
-                ring[(start + (uint32_t)i) & ring_mask] = 0u;
             }
+        }
+        if (i0 + 8 <= len) {
+            *reinterpret_cast<uint4*>(ring + ridx) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(ring + ((ridx + 4) & ring_mask)) = make_uint4(0, 0, 0, 0);
+        } else {
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j)
+                if (i0 + j < len) ring[(ridx + j) & ring_mask] = 0u;
         }
         __syncthreads();
     }
