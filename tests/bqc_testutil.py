@@ -103,3 +103,70 @@ def oracle_sketch(dump_path, n_sketches, size=32768, f2size=32768):
     per = 32 * size + f2size
     assert raw.size == per * n_sketches
     return [(raw[i * per:i * per + 32 * size], raw[i * per + 32 * size:(i + 1) * per]) for i in range(n_sketches)]
+
+
+# ------------------------------------------------------------------------------------------------------
+# hand-built BAM records for edge cases
+# ------------------------------------------------------------------------------------------------------
+import struct
+
+NT16 = "=ACMGRSVTWYHKDBN"
+CIGAR_OPS = "MIDNSHP=X"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF_BIN = os.path.join(ORACLE_DIR, "_ref", "bamqualcheck_ref")
+
+
+def bam_record(name="r", flag=0x41, rid=0, pos=100, mapq=60, cigar=((150, "M"),), seq=None, qual=None, nrid=0, npos=300,
+               tlen=350, tags=(("RG", "Z", "L1"), ("NM", "C", 0), ("AS", "C", 150))):
+    """One inflated BAM record (block_size prefix included)."""
+    seq = seq if seq is not None else "ACGT" * 37 + "AC"
+    qual = qual if qual is not None else [30] * len(seq)
+    b = bytearray()
+    nm = name.encode() + b"\0"
+    b += struct.pack("<iiBBHHHiiii", rid, pos, len(nm), mapq, 4680, len(cigar), flag, len(seq), nrid, npos, tlen)
+    b += nm
+    for n, op in cigar:
+        b += struct.pack("<I", (n << 4) | CIGAR_OPS.index(op))
+    codes = [NT16.index(c) for c in seq]
+    for i in range(0, len(codes), 2):
+        b.append((codes[i] << 4) | (codes[i + 1] if i + 1 < len(codes) else 0))
+    b += bytes(qual)
+    for key, ty, val in tags:
+        b += key.encode() + ty.encode()
+        if ty == "Z":
+            b += val.encode() + b"\0"
+        elif ty in "cC":
+            b += struct.pack("<b" if ty == "c" else "<B", val)
+        elif ty in "sS":
+            b += struct.pack("<h" if ty == "s" else "<H", val)
+        elif ty in "iI":
+            b += struct.pack("<i" if ty == "i" else "<I", val)
+        elif ty == "f":
+            b += struct.pack("<f", val)
+        elif ty == "A":
+            b += val.encode()
+        elif ty == "B":  # val = (subtype, [values])
+            sub, vals = val
+            b += sub.encode() + struct.pack("<i", len(vals)) + b"".join(struct.pack("<" + {"c": "b", "C": "B", "s": "h", "S": "H", "i": "i", "I": "I", "f": "f"}[sub], v) for v in vals)
+    return struct.pack("<i", len(b)) + bytes(b)
+
+
+def bam_stream(records, refs=(("chr1", 60000), ("chr2", 40000), ("chrX", 20000)), lanes=("L1",), sample="S1"):
+    """Uncompressed BAM byte stream: header + records."""
+    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs) + \
+        "".join(f"@RG\tID:{l}\tSM:{sample}\n" for l in lanes)
+    h = b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(refs))
+    for n, l in refs:
+        h += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
+    return h + b"".join(records)
+
+
+def golden_genome():
+    from bamqc_b200 import synth
+    return synth.Genome.make(77, ["chr1", "chr2", "chrX"], [60000, 40000, 20000])
+
+
+def run_cli(args):
+    """The product CLI (bamqc_b200/bin/bamqualcheck)."""
+    exe = os.path.join(ROOT, "bamqc_b200", "bin", "bamqualcheck")
+    return subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True)

@@ -1,0 +1,146 @@
+"""The drop-in command (bamqc_b200/bin/bamqualcheck: BGZF inflate on host threads -> pinned staging -> CUDA
+engine through the C ABI -> .bamqc writer) against the committed golden outputs of the reference's own code,
+and edge cases against the oracle."""
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import bqc_testutil as util
+
+pytestmark = pytest.mark.gpu
+GOLD = util.GOLDEN
+CASES = {
+    "standard": ["-c", "chr1,chr2"],
+    "stress": ["-c", "chr1,chr2"],
+    "two_lanes_kq": ["-c", "chr1,chr2", "-k", "15,32,63", "-q", "10,17"],
+    "long_insert": ["-c", "chr1,chr2,chrX", "-i", "3000", "-s", "7"],
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_cli_reproduces_reference_bamqc(case, tmp_path):
+    out = tmp_path / "gpu.bamqc"
+    r = util.run_cli(["-r", os.path.join(GOLD, "genome.fa"), "-o", out] + CASES[case] + [os.path.join(GOLD, case + ".bam")])
+    assert r.returncode == 0, r.stderr + r.stdout
+    diffs = util.diff_bamqc(os.path.join(GOLD, case + ".bamqc"), out)
+    assert not diffs, "\n".join(diffs)
+
+
+def _against_oracle(tmp_path, stream, opts=("-c", "chr1,chr2"), expect_rc=0):
+    fasta = tmp_path / "g.fa"
+    util.golden_genome().write_fasta(fasta)
+    bam = tmp_path / "in.bam"
+    bam.write_bytes(stream)
+    o = subprocess.run([util.ensure_oracle(), "-r", str(fasta), "-o", str(tmp_path / "o.bamqc")] + list(opts) + [str(bam)], capture_output=True, text=True)
+    g = util.run_cli(["-r", fasta, "-o", tmp_path / "g.bamqc"] + list(opts) + [bam])
+    assert o.returncode == expect_rc, o.stderr
+    assert g.returncode == expect_rc, g.stderr + g.stdout
+    if expect_rc == 0:
+        diffs = util.diff_bamqc(tmp_path / "o.bamqc", tmp_path / "g.bamqc")
+        assert not diffs, "\n".join(diffs)
+    return o, g
+
+
+def test_empty_input(tmp_path):
+    """Header only: every lane still flushes two empty coverage windows (src/bamqualcheck.cpp:447-453)."""
+    _against_oracle(tmp_path, util.bam_stream([]))
+    line = [l for l in open(tmp_path / "g.bamqc") if l.startswith("genome_coverage_histogram")][0].split()
+    assert line[1] == "2000"
+
+
+def test_ragged_lengths_iupac_and_odd_tags(tmp_path):
+    rng = random.Random(3)
+    genome = util.golden_genome()
+    recs = []
+    pos = 500
+    for i in range(400):
+        L = rng.choice([32, 33, 50, 75, 100, 101, 149, 150, 151, 200, 250])
+        pos += rng.randint(1, 120)
+        start = pos
+        ref = "".join("ACGT"[(int(genome.packed[0][(start + j) // 4]) >> (2 * ((start + j) % 4))) & 3] for j in range(L))
+        seq = list(ref)
+        for j in range(L):
+            x = rng.random()
+            if x < 0.01:
+                seq[j] = rng.choice("MRWSYKVHDBN=")  # IUPAC codes exercise the non-ACGT paths
+            elif x < 0.03:
+                seq[j] = rng.choice("ACGT")
+        qual = [rng.choice([2, 12, 23, 37, 41, 60, 93]) for _ in range(L)]
+        rev = rng.random() < 0.5
+        first = rng.random() < 0.5
+        flag = 0x1 | 0x2 | (0x10 if rev else 0x20) | (0x40 if first else 0x80)
+        if rng.random() < 0.05:
+            flag |= 0x400
+        nm_type = rng.choice(["c", "C", "s", "S", "i", "I"])
+        tags = [("XA", "Z", "junk"), ("RG", "Z", "L1"), ("XB", "B", ("S", [1, 2, 3])), ("NM", nm_type, rng.randint(0, 5)),
+                ("XF", "f", 1.5), ("AS", rng.choice(["C", "s", "i"]), rng.randint(40, 150)), ("XH", "H", "1AE3")]
+        if rng.random() < 0.1:
+            tags.append(("NM", "C", 2))  # a second NM is counted again by the reference (no break in the loop)
+        recs.append(util.bam_record(name=f"q{i}", flag=flag, rid=0, pos=start, mapq=rng.choice([0, 30, 59, 60]),
+                                    cigar=((L, "M"),), seq="".join(seq), qual=qual, nrid=0, npos=start + 200,
+                                    tlen=rng.choice([-1, 1]) * rng.randint(0, 1500), tags=tuple(tags)))
+    _against_oracle(tmp_path, util.bam_stream(recs))
+
+
+@pytest.mark.parametrize("name,bad", [
+    ("rg_type", dict(flag=0x63, tags=(("RG", "i", 5), ("NM", "C", 0), ("AS", "C", 150)))),
+    ("no_mate_flag", dict(flag=0x1, tags=(("RG", "Z", "L1"), ("NM", "C", 0), ("AS", "C", 150)))),
+    ("no_as", dict(flag=0x63, tags=(("RG", "Z", "L1"), ("NM", "C", 0)))),
+    ("negative_as", dict(flag=0x63, tags=(("RG", "Z", "L1"), ("NM", "C", 0), ("AS", "c", -3)))),
+])
+def test_fatal_conditions_exit_1(tmp_path, name, bad):
+    good = util.bam_record(name="a", flag=0x63, pos=1000, npos=1200, tlen=350)
+    o, g = _against_oracle(tmp_path, util.bam_stream([good, util.bam_record(name="b", pos=1100, **bad), good]), opts=("-c", "chr1"), expect_rc=1)
+    if name == "rg_type":
+        assert "Read does not have Z" in g.stdout
+    if name == "no_mate_flag":
+        assert "No first or second flag" in g.stderr
+
+
+def test_cli_argument_errors(tmp_path):
+    assert util.run_cli(["-o", tmp_path / "x", os.path.join(GOLD, "standard.bam")]).returncode == 1          # -r is required
+    assert util.run_cli(["-r", os.path.join(GOLD, "genome.fa"), os.path.join(GOLD, "standard.bam")]).returncode == 1  # -o is required
+    r = util.run_cli(["-r", os.path.join(GOLD, "genome.fa"), "-o", tmp_path / "x", tmp_path / "missing.bam"])
+    assert r.returncode == 1 and "Could not open" in r.stderr
+    assert util.run_cli(["--help"]).returncode == 0
+
+
+def test_multi_batch_streaming_with_small_staging(tmp_path):
+    """Many tiny staging buffers: records straddling BGZF blocks and buffer boundaries are carried over."""
+    from bamqc_b200 import Engine, synth
+    genome = util.golden_genome()
+    lib_ = synth.Library(seed=31, n_pairs=4000)
+    records, offsets = synth.generate(genome, lib_)
+    fasta, bam = tmp_path / "g.fa", tmp_path / "in.ubam"
+    genome.write_fasta(fasta)
+    synth.write_bam(bam, genome, lib_, records, int(offsets[-1]))
+    r = util.run_oracle(bam, fasta, tmp_path / "o.bamqc", chroms="chr1,chr2")
+    assert r.returncode == 0
+    eng = Engine(lane_ids=["L1"], ref_names=genome.names, chroms="chr1,chr2", staging_bytes=64 << 10)
+    for rid, (p, n) in enumerate(zip(genome.packed, genome.lengths)):
+        eng.set_reference(rid, p, n)
+    n_bytes = int(offsets[-1])
+    pos = 0
+    carry = np.zeros(0, dtype=np.uint8)
+    while pos < n_bytes:
+        buf = eng.acquire_staging()
+        take = min(buf.size - carry.size, n_bytes - pos, 50000)
+        buf[:carry.size] = carry
+        buf[carry.size:carry.size + take] = records[pos:pos + take]
+        filled = carry.size + take
+        pos += take
+        offs = np.zeros(filled // 36 + 2, dtype=np.uint64)
+        n = eng.lib.bqc_frame_records(buf.ctypes.data, filled, offs.ctypes.data, offs.size)
+        whole = int(offs[n])
+        carry = buf[whole:filled].copy()
+        if n:
+            eng.submit(buf, offs[:n + 1], n_bytes=whole)
+    assert carry.size == 0
+    eng.finish()
+    eng.write_bamqc("S1", tmp_path / "g.bamqc")
+    eng.close()
+    diffs = util.diff_bamqc(tmp_path / "o.bamqc", tmp_path / "g.bamqc")
+    assert not diffs, "\n".join(diffs)
