@@ -204,6 +204,25 @@ def run_oracle_timed(bam, fasta, out):
     raise RuntimeError("no timing line from the oracle")
 
 
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bamqualcheck_ref")
+
+
+def run_cpu_timed(bam, fasta, out, n_records):
+    """(records, seconds, kind).  kind "reference": oracle/_ref/bamqualcheck_ref = the reference's own
+    src/bamqualcheck.cpp + statistics headers compiled unmodified over the SeqAn stand-in (whole process wall
+    clock: raw BAM read, lazy FASTA load, statistics loop, output).  kind "port": the oracle restatement
+    (statistics loop only) when the reference build is not in the tree."""
+    if os.path.exists(REF_BIN):
+        t0 = time.perf_counter()
+        r = subprocess.run([REF_BIN, "-r", fasta, "-o", out, bam], capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        if r.returncode == 0:
+            return n_records, dt, "reference"
+        log("reference build failed, falling back to the oracle port: " + r.stderr[-300:])
+    n, s = run_oracle_timed(bam, fasta, out)
+    return n, s, "port"
+
+
 # ------------------------------------------------------------------------------------------------------
 def dist_setup(world):
     import torch
@@ -364,9 +383,13 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         with tempfile.TemporaryDirectory() as td:
             bam, fasta, k = write_cpu_sample(genome, records, offsets, td, "cpu", args.cpu_sample)
-            nrec_o, secs = run_oracle_timed(bam, fasta, os.path.join(td, "cpu.bamqc"))
-            cpu = {"value": nrec_o / secs, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"first {nrec_o} records of the workload (one contig), oracle/bamqualcheck_oracle, single thread, statistics loop only"}
+            nrec_o, secs, kind = run_cpu_timed(bam, fasta, os.path.join(td, "cpu.bamqc"), k)
+            n_p, secs_p = run_oracle_timed(bam, fasta, os.path.join(td, "cpu_port.bamqc"))
+            what = ("oracle/_ref/bamqualcheck_ref (the reference's own sources over the SeqAn stand-in), whole process wall clock "
+                    "on a raw BAM incl. FASTA load and output" if kind == "reference" else "oracle/bamqualcheck_oracle, statistics loop only")
+            cpu = {"value": nrec_o / secs, "unit": UNIT, "cores": 1, "kind": kind,
+                   "sample": f"first {nrec_o} records of the workload (one contig), single thread, {what}",
+                   "port_loop_only": n_p / secs_p}
 
     if rank == 0:
         line = {
@@ -421,20 +444,21 @@ def run_reference(args):
             res = [None] * cores
 
             def w(i):
-                res[i] = run_oracle_timed(shards[i][0], shards[i][1], os.path.join(td, f"o{i}.bamqc"))
+                res[i] = run_cpu_timed(shards[i][0], shards[i][1], os.path.join(td, f"o{i}.bamqc"), shards[i][2])
             ths = [threading.Thread(target=w, args=(i,)) for i in range(cores)]
             t0 = time.perf_counter()
             [t.start() for t in ths]
             [t.join() for t in ths]
-            return sum(r[0] for r in res), time.perf_counter() - t0, max(r[1] for r in res)
+            return sum(r[0] for r in res), time.perf_counter() - t0, max(r[1] for r in res), res[0][2]
 
         for _ in range(args.warmup):
             one_step()
         tot_rec = tot_s = 0.0
+        kind = "port"
         for _ in range(args.steps):
-            n, wall, loop = one_step()
+            n, wall, slowest, kind = one_step()
             tot_rec += n
-            tot_s += loop  # statistics loop only (same scope as the GPU kernels); processes run concurrently
+            tot_s += slowest  # the processes run concurrently: a step lasts as long as its slowest process
         value = tot_rec / tot_s
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -443,9 +467,11 @@ def run_reference(args):
         "config": {"workload": f"cfg2 sample: {int(tot_rec / args.steps)} synthetic 2x150bp records per step over chr1..22,X,Y geometry, "
                                f"{cores} independent single-threaded processes on disjoint shards",
                    "options": "-k 32 -q 17 -e 0.01 -s 1 -i 1000 -c chr1..chr22"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cores} shards x {per} records per step, oracle/bamqualcheck_oracle (CPU restatement of the reference; "
-                                   "SeqAn 1.4.2 is unavailable so the reference binary itself cannot be built)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{cores} shards x up to {per} records per step; " + (
+                             "oracle/_ref/bamqualcheck_ref = the reference's own src/bamqualcheck.cpp + statistics headers compiled unmodified "
+                             "over the SeqAn stand-in (SeqAn 1.4.2 is unavailable), whole process wall clock" if kind == "reference" else
+                             "oracle/bamqualcheck_oracle (CPU restatement of the reference), statistics loop only")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
