@@ -33,7 +33,7 @@ class bqc_config(ctypes.Structure):
         ("klist", ctypes.POINTER(ctypes.c_int32)), ("n_q", ctypes.c_int32),
         ("q_cutoff", ctypes.POINTER(ctypes.c_uint64)), ("q_base", ctypes.c_uint32), ("e", ctypes.c_double),
         ("seed", ctypes.c_int32), ("max_read_len", ctypes.c_int32), ("staging_bytes", ctypes.c_uint64),
-        ("cov_ring_log2", ctypes.c_uint32),
+        ("cov_ring_log2", ctypes.c_uint32), ("host_threads", ctypes.c_int32),
     ]
 
 
@@ -107,6 +107,7 @@ PROTOTYPES = {
     "bqc_parse_bam_header": (ctypes.c_size_t, [_vp, ctypes.c_size_t, _P(bqc_bam_header)]),
     "bqc_free_bam_header": (None, [_P(bqc_bam_header)]),
     "bqc_frame_records": (_u64, [_vp, ctypes.c_size_t, _vp, _u64]),
+    "bqc_frame_records_mt": (_u64, [_vp, ctypes.c_size_t, _vp, _u64, _i32, _i32]),
     "bqc_bgzf_inflate": (_u64, [_vp, _u64, _vp, _u64, _i32]),
     "bqc_fasta_open": (_vp, [ctypes.c_char_p]),
     "bqc_fasta_contig": (ctypes.c_int64, [_vp, ctypes.c_char_p, _P(_vp)]),

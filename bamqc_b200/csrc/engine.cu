@@ -15,6 +15,7 @@
 #include <map>
 #include <random>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -33,6 +34,8 @@ static thread_local std::string g_last_error;
             return BQC_ERR_CUDA;                                                                   \
         }                                                                                          \
     } while (0)
+
+struct ScanMeta { int32_t rid; uint32_t pos; };  // host_scan pass 1 -> pass 2
 
 struct CovState {  // OverallNumbers::{first,id,shift} (src/OverallNumbers.hpp:37-41) + virtual window index
     bool first = true;
@@ -109,6 +112,9 @@ struct bqc_engine {
     cudaEvent_t copied = nullptr;
 
     // host state
+    std::vector<ScanMeta> scan_meta;
+    std::vector<uint64_t> frame_offsets;
+    int host_threads = 1;
     std::vector<CovState> cov;
     uint64_t records_seen = 0, launches = 0;
     bool finished = false;
@@ -296,6 +302,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     if (e->staging_bytes > 0xF0000000ull) e->staging_bytes = 0xF0000000ull;
     e->max_records_per_slot = e->staging_bytes / 40 + 16;  // a record is at least 36 bytes
     e->ring_log2 = cfg->cov_ring_log2 ? cfg->cov_ring_log2 : 28;
+    e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     if (e->ring_log2 < 13 || e->ring_log2 > 30) { set_error(e, "bqc_create: cov_ring_log2 out of range"); delete e; return BQC_ERR_ARG; }
 
     int rc = [&]() -> int {
@@ -373,9 +380,114 @@ extern "C" uint64_t bqc_frame_records(const uint8_t* data, size_t n, uint64_t* o
         if (nrec + 1 >= cap) break;
         offsets[nrec++] = p;
         p += 4 + (size_t)bs;
+        // the chain p -> block_size -> next p is a dependent load per record; records of one library have
+        // nearly the same size, so the header 24 records ahead is prefetched at the predicted address
+        const size_t pf = p + 24 * (4 + (size_t)bs);
+        if (pf + 64 < n) {
+            __builtin_prefetch(data + pf);
+            __builtin_prefetch(data + pf + 64);
+        }
     }
     if (cap) offsets[nrec] = p;
     return nrec;
+}
+
+// Plausibility of "a record starts at p" (SAM/BAM spec field ranges).  Only used to SPECULATE where a
+// thread may start framing; the stitched result is accepted only where the true chain reaches it.
+static inline bool plausible_record(const uint8_t* d, size_t n, size_t p, int64_t n_ref) {
+    if (p + 36 > n) return false;
+    uint32_t bs = rd32(d + p);
+    if (bs < 34 || bs > (1u << 28) || p + 4 + (size_t)bs > n) return false;
+    int32_t rid = (int32_t)rd32(d + p + 4), pos = (int32_t)rd32(d + p + 8), nrid = (int32_t)rd32(d + p + 24), npos = (int32_t)rd32(d + p + 28);
+    if (rid < -1 || rid >= n_ref || nrid < -1 || nrid >= n_ref || pos < -1 || npos < -1) return false;
+    uint32_t lname = d[p + 12], ncig = d[p + 16] | (d[p + 17] << 8);
+    int32_t lseq = (int32_t)rd32(d + p + 20);
+    if (lname < 1 || lseq < 0) return false;
+    uint64_t need = 32ull + lname + 4ull * ncig + ((uint64_t)lseq + 1) / 2 + (uint64_t)lseq;
+    if (need > bs) return false;
+    return d[p + 36 + lname - 1] == 0;
+}
+
+// Multi-threaded framing.  The record chain is a dependent load per record (~20 ns each on a host core),
+// so T threads frame T slices concurrently from speculated starts (first position whose next 6 hops all look
+// like records); the slices are then stitched in order and a slice is accepted only if the chain of the
+// previous slice ends exactly on its start -- otherwise the rest is framed sequentially.  The result is
+// identical to the sequential walk.
+static uint64_t frame_records_mt(const uint8_t* data, size_t n, uint64_t* offsets, uint64_t cap, int threads, int64_t n_ref) {
+    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n >> 22));
+    if (T <= 1) return bqc_frame_records(data, n, offsets, cap);
+    const uint64_t NONE = ~0ull;
+    struct Part { uint64_t start, end; std::vector<uint64_t> offs; };
+    std::vector<Part> parts((size_t)T);
+    auto find_start = [&](int t) {
+        Part& P = parts[(size_t)t];
+        P.start = NONE;
+        if (t == 0) { P.start = 0; return; }
+        size_t lo = n * (size_t)t / (size_t)T, hi = std::min(n, lo + (1u << 20));
+        for (size_t p = lo; p < hi; ++p) {
+            size_t q = p;
+            int hops = 0;
+            while (hops < 6 && plausible_record(data, n, q, n_ref)) { q += 4 + (size_t)rd32(data + q); ++hops; if (q == n) { hops = 6; break; } }
+            if (hops == 6) { P.start = p; return; }
+        }
+    };
+    auto frame_part = [&](int t) {
+        Part& P = parts[(size_t)t];
+        if (P.start == NONE) return;
+        uint64_t stop = n;
+        for (int u = t + 1; u < T; ++u)
+            if (parts[(size_t)u].start != NONE) { stop = parts[(size_t)u].start; break; }
+        P.offs.reserve((size_t)((stop - P.start) / 200 + 16));
+        size_t p = (size_t)P.start;
+        while (p < stop && p + 4 <= n) {
+            uint32_t bs = rd32(data + p);
+            if (bs < 32 || p + 4 + (size_t)bs > n) break;
+            P.offs.push_back(p);
+            p += 4 + (size_t)bs;
+            const size_t pf = p + 24 * (4 + (size_t)bs);
+            if (pf + 64 < n) { __builtin_prefetch(data + pf); __builtin_prefetch(data + pf + 64); }
+        }
+        P.end = p;
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t) pool.emplace_back(find_start, t);
+        for (auto& th : pool) th.join();
+    }
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t) pool.emplace_back(frame_part, t);
+        for (auto& th : pool) th.join();
+    }
+    // stitch
+    uint64_t nrec = 0, pos = 0;
+    bool ok = true;
+    for (int t = 0; t < T && ok; ++t) {
+        Part& P = parts[(size_t)t];
+        if (P.start == NONE) continue;
+        if (P.start != pos) { ok = false; break; }  // speculation missed: the true chain does not land here
+        if (nrec + P.offs.size() + 1 >= cap) { ok = false; break; }
+        memcpy(offsets + nrec, P.offs.data(), P.offs.size() * 8);
+        nrec += P.offs.size();
+        pos = P.end;
+        if (pos < n) {  // the slice stopped early: either at the next start (fine) or on a bad record
+            uint64_t stop = n;
+            for (int u = t + 1; u < T; ++u)
+                if (parts[(size_t)u].start != NONE) { stop = parts[(size_t)u].start; break; }
+            if (pos < stop) { ok = false; break; }
+        }
+    }
+    if (!ok || pos != n) {  // continue sequentially from the last accepted position (rare)
+        uint64_t more = bqc_frame_records(data + pos, n - pos, offsets + nrec, cap - nrec);
+        for (uint64_t i = 0; i <= more; ++i) offsets[nrec + i] += pos;
+        return nrec + more;
+    }
+    offsets[nrec] = pos;
+    return nrec;
+}
+
+extern "C" uint64_t bqc_frame_records_mt(const uint8_t* data, size_t n, uint64_t* offsets, uint64_t cap, int32_t threads, int32_t n_ref) {
+    return frame_records_mt(data, n, offsets, cap, threads, n_ref > 0 ? n_ref : (1 << 24));
 }
 
 // lane of a record from its RG:Z tag (only needed when the header declares several read groups)
@@ -434,22 +546,53 @@ static int host_scan(bqc_engine* e, const uint8_t* data, const uint64_t* offs, u
     open_segment(0);
     max_lseq = 0;
     const uint64_t base_off = offs[0];
+    // Pass 1 (host threads): touch every record header once; 32-bit offsets, lane, longest read and a
+    // compact (rid, pos) pair for the records that take part in the coverage statistic.
+    typedef ScanMeta Meta;
+    std::vector<Meta>& meta = e->scan_meta;
+    if (meta.size() < n_records) meta.resize(n_records);
+    const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)e->host_threads, n_records / 65536));
+    std::vector<uint32_t> tmax((size_t)T, 0);
+    auto pass1 = [&](int t) {
+        uint64_t r0 = n_records * (uint64_t)t / (uint64_t)T, r1 = n_records * (uint64_t)(t + 1) / (uint64_t)T;
+        uint32_t mx = 0;
+        for (uint64_t r = r0; r < r1; ++r) {
+            const uint8_t* p = data + offs[r];
+            if (r + 16 < r1) __builtin_prefetch(data + offs[r + 16]);
+            o32[r] = (uint32_t)(offs[r] - base_off);
+            uint32_t avail = (uint32_t)(offs[r + 1] - offs[r]);
+            Meta m = {-1, 0};  // rid -1 = does not take part
+            uint32_t lane = 0;
+            if (avail >= 36) {
+                int32_t rid = (int32_t)rd32(p + 4);
+                uint32_t flag = p[18] | (p[19] << 8);
+                int32_t lseq = (int32_t)rd32(p + 20);
+                if (lseq > 0 && (uint32_t)lseq > mx) mx = (uint32_t)lseq;
+                if (e->n_lanes > 1) lane = host_lane(e, p, avail);
+                bool q = !(flag & 0x900u) && (flag & 0xC0u) && !(flag & 0x4u) && !(flag & 0x400u) && rid >= 0 && rid < e->cfg.n_ref && e->main_chrom[rid];
+                if (q) { m.rid = rid; m.pos = rd32(p + 8); }
+            }
+            meta[r] = m;
+            if (lane_out) lane_out[r] = (uint8_t)lane;
+        }
+        tmax[(size_t)t] = mx;
+    };
+    if (T == 1) {
+        pass1(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t) pool.emplace_back(pass1, t);
+        for (auto& th : pool) th.join();
+    }
+    for (uint32_t v : tmax) max_lseq = std::max(max_lseq, v);
+    // Pass 2 (sequential, 8 bytes per record): the anchor recurrence of OverallNumbers::coverage
     for (uint64_t r = 0; r < n_records; ++r) {
-        const uint8_t* p = data + offs[r];
-        uint64_t rel = offs[r] - base_off;
-        o32[r] = (uint32_t)rel;
-        uint32_t avail = (uint32_t)(offs[r + 1] - offs[r]);
         uint32_t code = kNone;
-        uint32_t lane = 0;
-        if (avail >= 36) {
-            int32_t rid = (int32_t)rd32(p + 4);
-            uint32_t b = rd32(p + 8);
-            uint32_t flag = p[18] | (p[19] << 8);
-            int32_t lseq = (int32_t)rd32(p + 20);
-            if (lseq > 0 && (uint32_t)lseq > max_lseq) max_lseq = (uint32_t)lseq;
-            if (e->n_lanes > 1) lane = host_lane(e, p, avail);
-            bool q = !(flag & 0x900u) && (flag & 0xC0u) && !(flag & 0x4u) && !(flag & 0x400u) && rid >= 0 && rid < e->cfg.n_ref && e->main_chrom[rid];
-            if (q) {
+        {
+            const int32_t rid = meta[r].rid;
+            const uint32_t b = meta[r].pos;
+            const uint32_t lane = lane_out ? lane_out[r] : 0u;
+            if (rid >= 0) {
                 CovState& st = e->cov[lane];
                 for (int attempt = 0; attempt < 2; ++attempt) {
                     CovState t = st;
@@ -470,7 +613,6 @@ static int host_scan(bqc_engine* e, const uint8_t* data, const uint64_t* offs, u
             }
         }
         cov[r] = code;
-        if (lane_out) lane_out[r] = (uint8_t)lane;
     }
     o32[n_records] = (uint32_t)(offs[n_records] - base_off);
     close_segment(n_records);
@@ -664,10 +806,10 @@ extern "C" int bqc_submit(bqc_engine* e, const void* data, size_t n_bytes, const
         s.in_flight = false;
     }
     const uint8_t* src = (const uint8_t*)data;
-    std::vector<uint64_t> own_offsets;
+    std::vector<uint64_t>& own_offsets = e->frame_offsets;
     if (!record_offsets) {
-        own_offsets.resize(e->max_records_per_slot + 1);
-        n_records = bqc_frame_records(src, n_bytes, own_offsets.data(), own_offsets.size());
+        if (own_offsets.size() < n_bytes / 36 + 2) own_offsets.resize(n_bytes / 36 + 2);
+        n_records = frame_records_mt(src, n_bytes, own_offsets.data(), own_offsets.size(), e->host_threads, std::max(1, e->cfg.n_ref));
         if (own_offsets[n_records] != n_bytes) {
             e->host_error.code = BQC_ERR_BAD_RECORD;
             e->host_error.record = e->records_seen + n_records;
@@ -724,7 +866,7 @@ extern "C" int bqc_batch_prepare(bqc_engine* e, const void* data, size_t n_bytes
     std::vector<uint64_t> own_offsets;
     if (!record_offsets) {
         own_offsets.resize(n_bytes / 36 + 2);
-        n_records = bqc_frame_records(src, n_bytes, own_offsets.data(), own_offsets.size());
+        n_records = frame_records_mt(src, n_bytes, own_offsets.data(), own_offsets.size(), e->host_threads, std::max(1, e->cfg.n_ref));
         record_offsets = own_offsets.data();
     }
     bqc_batch* b = new bqc_batch();

@@ -589,7 +589,7 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
     std::vector<uint64_t> offs;
     auto submit_buffer = [&](uint8_t* buf, size_t filled, bool last) -> int {
         offs.resize(filled / 36 + 2);
-        uint64_t n = bqc_frame_records(buf, filled, offs.data(), offs.size());
+        uint64_t n = bqc_frame_records_mt(buf, filled, offs.data(), offs.size(), c.threads, hdr.n_ref);
         size_t whole = (size_t)offs[n];
         if (last && whole != filled) {
             std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";

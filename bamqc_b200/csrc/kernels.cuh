@@ -339,6 +339,9 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch(EngineView E, Batc
         uint64_t hlo = 0, hhi = 0, tlo = 0, thi = 0;
         uint64_t seqw = 0, qualw = 0, lagw = 0;
         uint32_t run = 0;
+        bool pend = false;
+        uint32_t* pwp = nullptr;
+        uint32_t psh = 0, pold = 0;
         for (uint32_t i = 0; i < maxL; ++i, __syncwarp()) {
             if (i >= Ls) continue;
             if ((i & 15u) == 0) seqw = ldu64(seqp + (i >> 1));
@@ -363,6 +366,17 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch(EngineView E, Batc
             thi = (xh >> 1) | (xl << 63);
             bool valid = (nin != 15u) && ((int8_t)(q + 33u) >= (int8_t)SP.q_thresh);
             run = valid ? run + 1u : 0u;
+            // The sketch probe is software-pipelined: the word is loaded in the iteration that produces the
+            // hash and tested (CAS only while the nibble is < 15) one iteration later, so the L2 latency
+            // overlaps the next base's hash update.
+            if (pend) {
+                while (((pold >> psh) & 15u) != 15u) {  // 4-bit saturating increment
+                    uint32_t assumed = pold;
+                    pold = atomicCAS(pwp, assumed, assumed + (1u << psh));
+                    if (pold == assumed) break;
+                }
+                pend = false;
+            }
             if (run >= k) {
                 uint64_t hv = hlo ^ tlo;
                 ++my_count;
@@ -371,16 +385,21 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch(EngineView E, Batc
                 uint32_t w = hv ? (uint32_t)(__ffsll((long long)hv) - 1) : 63u;  // bitScanForward, 63 for 0
                 if (w > 31u) w = 31u;
                 uint64_t index = (hv >> (w + 1u)) & idx_mask;
-                uint32_t* wp = sk + w * words_per_level + (uint32_t)(index >> 3);
-                uint32_t sh = ((uint32_t)index & 7u) * 4u;
-                uint32_t old = __ldcg(wp);
-                while (((old >> sh) & 15u) != 15u) {  // 4-bit saturating increment
-                    uint32_t assumed = old;
-                    old = atomicCAS(wp, assumed, assumed + (1u << sh));
-                    if (old == assumed) break;
-                }
+                pwp = sk + w * words_per_level + (uint32_t)(index >> 3);
+                psh = ((uint32_t)index & 7u) * 4u;
+                pold = __ldcg(pwp);
+                pend = true;
             }
         }
+        if (pend) {
+            while (((pold >> psh) & 15u) != 15u) {
+                uint32_t assumed = pold;
+                pold = atomicCAS(pwp, assumed, assumed + (1u << psh));
+                if (pold == assumed) break;
+            }
+            pend = false;
+        }
+        __syncwarp();
     }
     // sumCount: warp reduce then one atomic per warp
     for (int o = 16; o > 0; o >>= 1) my_count += __shfl_xor_sync(0xFFFFFFFFu, my_count, o);

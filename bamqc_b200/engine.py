@@ -48,7 +48,7 @@ class Engine:
     """One statistics engine on one GPU (bqc_engine)."""
 
     def __init__(self, lane_ids=("L1",), ref_names=(), chroms=DEFAULT_CHROMS, isize=1000, klist=(32,), qlist=(17,),
-                 e=0.01, seed=1, device=0, max_read_len=0, staging_bytes=0, cov_ring_log2=0):
+                 e=0.01, seed=1, device=0, max_read_len=0, staging_bytes=0, cov_ring_log2=0, host_threads=0):
         self.lib = _lib.load_library()
         self.lane_ids = [l if isinstance(l, str) else l.decode() for l in lane_ids]
         self.ref_names = [r if isinstance(r, str) else r.decode() for r in ref_names]
@@ -69,6 +69,7 @@ class Engine:
         cfg.n_k, cfg.klist, cfg.n_q, cfg.q_cutoff = len(self.klist), ka, len(self.qlist), qa
         cfg.q_base, cfg.e, cfg.seed = 33, e, seed
         cfg.max_read_len, cfg.staging_bytes, cfg.cov_ring_log2 = max_read_len, staging_bytes, cov_ring_log2
+        cfg.host_threads = host_threads
         self._keep += [arr, ka, qa]
         h = ctypes.c_void_p()
         rc = self.lib.bqc_create(ctypes.byref(cfg), ctypes.byref(h))

@@ -128,7 +128,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             pass
 
@@ -282,13 +282,13 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local) if rank == 0 else None  # sampled from the warm-up on (the timed region is short)
     for _ in range(args.warmup):
         step()
     eng.profile_enable(True)
     eng.profile_read()
     launches0 = eng.kernel_launches
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
@@ -322,7 +322,7 @@ def run_b200(args):
         eng.reset()
         for lo, hi in zip(e2e_bounds[:-1], e2e_bounds[1:]):
             o = offsets[lo:hi + 1]
-            eng.submit(pin_np[int(o[0]):int(o[-1])], o - o[0])
+            eng.submit(pin_np[int(o[0]):int(o[-1])], None)  # the engine frames the records itself
         eng.finish()
         if world > 1:
             bdist.reduce_engine(eng, bufs)

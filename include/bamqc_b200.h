@@ -54,6 +54,7 @@ typedef struct bqc_config {
     int32_t max_read_len;         /* per-cycle table capacity; 0 => 512.  Longer reads => BQC_ERR_UNSUPPORTED */
     uint64_t staging_bytes;       /* capacity of each pinned staging buffer; 0 => 256 MiB */
     uint32_t cov_ring_log2;       /* log2 entries of the coverage depth ring; 0 => 28 (1 GiB) */
+    int32_t host_threads;         /* host threads of the framing / anchor pre-pass inside bqc_submit; 0 => min(16, cores) */
 } bqc_config;
 
 typedef struct bqc_error_info {
@@ -176,6 +177,9 @@ void bqc_free_bam_header(bqc_bam_header* h);
 /* Find record boundaries in [data, data+n): fills offsets (cap entries) with the start of each whole
  * record plus the end of the last whole one; returns the number of whole records. */
 uint64_t bqc_frame_records(const uint8_t* data, size_t n, uint64_t* offsets, uint64_t cap);
+/* Same result with `threads` host threads (speculated slice starts, verified when stitching). n_ref bounds
+ * the plausible refID range (0 = unknown). */
+uint64_t bqc_frame_records_mt(const uint8_t* data, size_t n, uint64_t* offsets, uint64_t cap, int32_t threads, int32_t n_ref);
 /* Inflate a BGZF byte range with `threads` host threads.  Returns inflated size, or 0 on error / cap. */
 uint64_t bqc_bgzf_inflate(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, int32_t threads);
 /* Load a FASTA file and pack contig `name` (id up to first space/tab, src/TripletCounting.hpp:99-102)
