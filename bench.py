@@ -34,6 +34,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries (NCCL, torchrun) write banners to file descriptor 1; the contract is ONE JSON line on stdout.
+# Everything written to fd 1 while the benchmark runs is redirected to stderr, the line goes to the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -412,7 +422,7 @@ def run_b200(args):
         }
         if bgzf:
             line["e2e_bgzf"] = bgzf
-        print(json.dumps(line), flush=True)
+        emit(line)
     for b in batches:
         b.free()
     eng.close()
@@ -474,7 +484,7 @@ def run_reference(args):
                              "oracle/bamqualcheck_oracle (CPU restatement of the reference), statistics loop only")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
