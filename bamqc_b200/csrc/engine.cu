@@ -106,7 +106,8 @@ struct bqc_engine {
     HashTables* d_hash = nullptr;  // one per k
     std::vector<uint32_t*> ref_bufs;
     std::vector<uint64_t> ref_len;
-    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaStream_t compute = nullptr, copy = nullptr, covs = nullptr;  // covs: coverage scatter + flush (HBM bound) overlaps the table kernels
+    cudaEvent_t cov_done = nullptr, cov_go = nullptr;
     Slot slots[2];
     int next_slot = 0;
     cudaEvent_t copied = nullptr;
@@ -206,6 +207,7 @@ extern "C" void bqc_destroy(bqc_engine* e) {
     cudaSetDevice(e->cfg.device);
     if (e->compute) cudaStreamSynchronize(e->compute);
     if (e->copy) cudaStreamSynchronize(e->copy);
+    if (e->covs) cudaStreamSynchronize(e->covs);
     for (auto& s : e->slots) {
         if (s.pinned) cudaFreeHost(s.pinned);
         if (s.h_offsets) cudaFreeHost(s.h_offsets);
@@ -226,6 +228,9 @@ extern "C" void bqc_destroy(bqc_engine* e) {
     cudaFree(e->d_main_chrom);
     cudaFree(e->d_hash);
     if (e->copied) cudaEventDestroy(e->copied);
+    if (e->cov_done) cudaEventDestroy(e->cov_done);
+    if (e->cov_go) cudaEventDestroy(e->cov_go);
+    if (e->covs) cudaStreamDestroy(e->covs);
     if (e->compute) cudaStreamDestroy(e->compute);
     if (e->copy) cudaStreamDestroy(e->copy);
     delete e;
@@ -247,11 +252,13 @@ extern "C" int bqc_reset(bqc_engine* e) {
     CU(cudaSetDevice(e->cfg.device));
     CU(cudaStreamSynchronize(e->compute));
     CU(cudaStreamSynchronize(e->copy));
+    CU(cudaStreamSynchronize(e->covs));
     CU(cudaMemsetAsync(e->d_counters, 0, e->n_lanes * e->L.lane_stride * 8, e->compute));
     CU(cudaMemsetAsync(e->d_sketch, 0, e->n_lanes * e->n_qk * e->sketch_words_per_qk * 4, e->compute));
     CU(cudaMemsetAsync(e->d_ring, 0, (uint64_t)e->n_lanes * (1ull << e->ring_log2) * 4, e->compute));
     CU(cudaMemsetAsync(e->d_cov_carry, 0, e->n_lanes * 4, e->compute));
     CU(cudaMemsetAsync(e->d_error, 0xFF, 8, e->compute));
+    CU(cudaStreamSynchronize(e->compute));  // the coverage stream starts from a clean ring
     e->cov.assign(e->n_lanes, CovState());
     e->records_seen = 0;
     e->finished = false;
@@ -312,6 +319,9 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         e->n_sm = prop.multiProcessorCount;
         CU(cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&e->covs, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&e->cov_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&e->cov_go, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&e->copied, cudaEventDisableTiming));
         CU(cudaMalloc(&e->d_counters, e->n_lanes * e->L.lane_stride * 8));
         CU(cudaMalloc(&e->d_sketch, std::max<uint64_t>(4, e->n_lanes * e->n_qk * e->sketch_words_per_qk * 4)));
@@ -341,6 +351,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         CU(cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(k_eightmer, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CU(cudaFuncSetAttribute(k_sketch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        CU(cudaFuncSetAttribute(k_sketch32, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024 + (int)sizeof(HashPairTable)));
         return 0;
     }();
     if (rc) { g_last_error = e->last_error; bqc_destroy(e); return rc; }
@@ -626,17 +637,18 @@ struct ProfScope {  // records an event pair around the launches of one kernel f
     bqc_engine* e;
     bqc_engine::ProfEv ev;
     bool on;
-    ProfScope(bqc_engine* e_, int family) : e(e_), on(e_->profiling) {
+    cudaStream_t st;
+    ProfScope(bqc_engine* e_, int family, cudaStream_t stream = nullptr) : e(e_), on(e_->profiling), st(stream ? stream : e_->compute) {
         if (!on) return;
         auto get = [&]() { cudaEvent_t x; if (e->prof_pool.empty()) cudaEventCreate(&x); else { x = e->prof_pool.back(); e->prof_pool.pop_back(); } return x; };
         ev.family = family;
         ev.a = get();
         ev.b = get();
-        cudaEventRecord(ev.a, e->compute);
+        cudaEventRecord(ev.a, st);
     }
     ~ProfScope() {
         if (!on) return;
-        cudaEventRecord(ev.b, e->compute);
+        cudaEventRecord(ev.b, st);
         e->prof_pending.push_back(ev);
     }
 };
@@ -646,6 +658,7 @@ extern "C" void bqc_profile_enable(bqc_engine* e, int on) { e->profiling = on !=
 extern "C" int bqc_profile_read(bqc_engine* e, double ms_out[8], uint64_t n_out[8]) {
     CU(cudaSetDevice(e->cfg.device));
     CU(cudaStreamSynchronize(e->compute));
+    CU(cudaStreamSynchronize(e->covs));
     for (auto& p : e->prof_pending) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { e->prof_ms[p.family] += ms; e->prof_n[p.family] += 1; }
@@ -668,12 +681,12 @@ static int launch_cov_flush(bqc_engine* e, uint32_t lane, uint64_t from_abs, uin
     uint32_t start = (uint32_t)(from_abs & mask);
     uint64_t ntiles = (len + kCovTile - 1) / kCovTile;
     if (ntiles + 1 > e->cov_sums_cap) { set_error(e, "coverage flush larger than the ring"); return BQC_ERR_ARG; }
-    int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)e->n_sm * 2);
+    int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)e->n_sm * (2048 / kCovThreads));
     unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
-    ProfScope prof(e, 3);
+    ProfScope prof(e, 3, e->covs);
     // tile states + ticket live in one buffer: [0] = ticket, [1..] = states
-    CU(cudaMemsetAsync(e->d_cov_sums, 0, (ntiles + 1) * 8, e->compute));
-    k_cov_flush<<<grid, 1024, 0, e->compute>>>(ring, mask, start, len, e->d_cov_carry + lane, (unsigned long long*)e->d_cov_sums + 1,
+    CU(cudaMemsetAsync(e->d_cov_sums, 0, (ntiles + 1) * 8, e->covs));
+    k_cov_flush<<<grid, kCovThreads, 0, e->covs>>>(ring, mask, start, len, e->d_cov_carry + lane, (unsigned long long*)e->d_cov_sums + 1,
                                                (uint32_t*)e->d_cov_sums, poscov);
     e->launches += 1;
     CU(cudaGetLastError());
@@ -708,8 +721,37 @@ static int run_device_batch(bqc_engine* e, const DeviceBatch& d) {
     e->stats_blocks_per_sm = bps;
     const uint64_t ring_size = 1ull << e->ring_log2;
     const uint64_t n = d.n_records;
+    // The coverage work (scatter + window flush) is HBM bound, the table kernels are issue bound: it runs on
+    // its own stream, launched first, so that the two overlap.
+    CU(cudaEventRecord(e->cov_go, e->compute));
+    CU(cudaStreamWaitEvent(e->covs, e->cov_go, 0));
+    // the coverage ring is fed and drained segment by segment (a segment is what fits the ring)
+    for (const Segment& sg : d.segs) {
+        uint64_t ns = sg.r1 - sg.r0;
+        for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
+            if (ns) {
+                BatchView B;
+                B.bytes = d.bytes;
+                B.offsets = d.offsets + sg.r0;
+                B.cov = d.cov + sg.r0;
+                B.rec_lane = d.rec_lane ? d.rec_lane + sg.r0 : nullptr;
+                B.n_records = (uint32_t)ns;
+                B.cycb = cycb;
+                B.first_record = d.first_record + sg.r0;
+                B.ring_base = (uint32_t)((sg.base_window[lane] * 1000) & (ring_size - 1));
+                int grid = (int)std::min<uint64_t>((ns + 255) / 256, (uint64_t)e->n_sm * 8);
+                ProfScope prof(e, 3, e->covs);
+                k_cov_scatter<<<grid, 256, 0, e->covs>>>(E, B, lane);
+                e->launches += 1;
+            }
+            uint64_t from = sg.base_window[lane] * 1000;
+            int rc = launch_cov_flush(e, lane, from, sg.flush_to[lane]);
+            if (rc) return rc;
+        }
+    }
+    CU(cudaEventRecord(e->cov_done, e->covs));
     for (uint32_t lane = 0; lane < e->n_lanes && n; ++lane) {
-        // the table kernels see the whole batch once ...
+        // the table kernels see the whole batch once
         BatchView B;
         B.bytes = d.bytes;
         B.offsets = d.offsets;
@@ -733,37 +775,16 @@ static int run_device_batch(bqc_engine* e, const DeviceBatch& d) {
                 SP.qk = qi * (uint32_t)e->klist.size() + ki;
                 int gs = (int)std::min<uint64_t>((n + kSketchThreads - 1) / kSketchThreads, (uint64_t)e->n_sm);
                 ProfScope prof(e, 2);
-                if (e->L.f2size <= 32768u)
+                if (SP.k == 32u && e->L.f2size <= 32768u)
+                    k_sketch32<<<gs, kSketchThreads, e->L.f2size * 4 + sizeof(HashPairTable), e->compute>>>(E, B, lane, SP, e->d_hash + ki);
+                else if (e->L.f2size <= 32768u)
                     k_sketch<true><<<gs, kSketchThreads, e->L.f2size * 4, e->compute>>>(E, B, lane, SP, e->d_hash + ki);
                 else
                     k_sketch<false><<<gs, kSketchThreads, 0, e->compute>>>(E, B, lane, SP, e->d_hash + ki);
                 e->launches += 1;
             }
     }
-    // ... the coverage ring is fed and drained segment by segment (a segment is what fits the ring)
-    for (const Segment& sg : d.segs) {
-        uint64_t ns = sg.r1 - sg.r0;
-        for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
-            if (ns) {
-                BatchView B;
-                B.bytes = d.bytes;
-                B.offsets = d.offsets + sg.r0;
-                B.cov = d.cov + sg.r0;
-                B.rec_lane = d.rec_lane ? d.rec_lane + sg.r0 : nullptr;
-                B.n_records = (uint32_t)ns;
-                B.cycb = cycb;
-                B.first_record = d.first_record + sg.r0;
-                B.ring_base = (uint32_t)((sg.base_window[lane] * 1000) & (ring_size - 1));
-                int grid = (int)std::min<uint64_t>((ns + 255) / 256, (uint64_t)e->n_sm * 8);
-                ProfScope prof(e, 3);
-                k_cov_scatter<<<grid, 256, 0, e->compute>>>(E, B, lane);
-                e->launches += 1;
-            }
-            uint64_t from = sg.base_window[lane] * 1000;
-            int rc = launch_cov_flush(e, lane, from, sg.flush_to[lane]);
-            if (rc) return rc;
-        }
-    }
+    CU(cudaStreamWaitEvent(e->compute, e->cov_done, 0));
     CU(cudaGetLastError());
     return 0;
 }
@@ -940,6 +961,7 @@ extern "C" int bqc_get_error(bqc_engine* e, bqc_error_info* out) {
 extern "C" int bqc_sync(bqc_engine* e) {
     CU(cudaSetDevice(e->cfg.device));
     CU(cudaStreamSynchronize(e->copy));
+    CU(cudaStreamSynchronize(e->covs));
     CU(cudaStreamSynchronize(e->compute));
     bqc_error_info ei;
     int rc = bqc_get_error(e, &ei);
@@ -971,6 +993,8 @@ extern "C" int bqc_finish(bqc_engine* e) {
             st.flushed = to;
             st.v1 += 2;
         }
+        CU(cudaEventRecord(e->cov_done, e->covs));
+        CU(cudaStreamWaitEvent(e->compute, e->cov_done, 0));
         e->finished = true;
     }
     e->have_results = false;

@@ -1,0 +1,138 @@
+// kernel_sketch.cuh -- k_sketch32: the default-configuration (k = 32) fast path of the KmerStream sketch
+// update: ReadQualityHasher::operator() (src/ReadQualityHasher.hpp:30-68) -> RepHash::update
+// (src/kmerstream/RepHash.hpp:101-114) -> StreamCounter::operator() (src/kmerstream/StreamCounter.hpp:67-93).
+// Same arithmetic as the generic k_sketch in kernels.cuh; the differences are mechanical:
+//   * 16 bases (one 8-byte SEQ chunk) per outer iteration, fully unrolled, next chunks prefetched one
+//     iteration ahead so the loads overlap the hash updates of the current chunk;
+//   * with k = 32 the base leaving the window sits at the same nibble of the chunk two iterations back,
+//     so the lagging SEQ stream needs no loads at all;
+//   * the four 128-bit table lookups per base collapse into one 32-byte row indexed by (in, out):
+//     row = { H[in] ^ rotl_k(H[out]),  rotl_k(Ht[in]) ^ Ht[out] }.
+#pragma once
+
+namespace bqc {
+
+struct HashPairTable {  // [strand][in 0..15][out 0..16] -> {h.lo, h.hi, t.lo, t.hi}
+    ulonglong2 h[2][16][17];
+    ulonglong2 t[2][16][17];
+};
+
+__global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, BatchView B, uint32_t lane, SketchParams SP, const HashTables* __restrict__ HT) {
+    extern __shared__ uint32_t sm[];                 // F2 table (f2size u32) followed by the pair table
+    const Layout& L = E.L;
+    HashPairTable* PT = reinterpret_cast<HashPairTable*>(sm + L.f2size);
+    for (uint32_t i = threadIdx.x; i < L.f2size; i += blockDim.x) sm[i] = 0;
+    for (uint32_t i = threadIdx.x; i < 2 * 16 * 17; i += blockDim.x) {
+        const uint32_t s = i / (16 * 17), in = (i / 17) % 16, out = i % 17;
+        // HT->t[s][which][n][0] = hi, [1] = lo; which: 0 h-in, 1 h-out, 2 t-in, 3 t-out
+        const uint64_t hlo = HT->t[s][0][in][1] ^ HT->t[s][1][out][1], hhi = HT->t[s][0][in][0] ^ HT->t[s][1][out][0];
+        const uint64_t tlo = HT->t[s][2][in][1] ^ HT->t[s][3][out][1], thi = HT->t[s][2][in][0] ^ HT->t[s][3][out][0];
+        PT->h[s][in][out] = make_ulonglong2(hlo, hhi);
+        PT->t[s][in][out] = make_ulonglong2(tlo, thi);
+    }
+    __syncthreads();
+    uint64_t* G = E.counters + (uint64_t)lane * L.lane_stride + L.o_qk + (uint64_t)SP.qk * L.qk_stride;
+    uint32_t* sk = E.sketch + ((uint64_t)lane * L.n_qk + SP.qk) * 32ull * (L.sk_size * 2ull);
+    const uint32_t words_per_level = L.sk_size * 2u;
+    const uint64_t idx_mask = (uint64_t)L.sk_size * 16ull - 1ull;
+    const uint32_t f2mask = L.f2size - 1u;
+    const int32_t q_thresh = SP.q_thresh;
+    unsigned long long my_count = 0;
+    const uint32_t lane_id = threadIdx.x & 31u;
+
+    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < B.n_records; r0 += gridDim.x * blockDim.x) {
+        const uint32_t rec = r0 + lane_id;
+        RecHdr h;
+        bool act = rec < B.n_records && !(B.rec_lane && B.rec_lane[rec] != lane);
+        if (act) {
+            const uint32_t off = B.offsets[rec];
+            act = decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h);
+        }
+        act = act && !(h.flag & 0xF00u) && (h.flag & 0xC0u) && (uint32_t)h.lseq >= 32u;
+        const uint32_t Ls = act ? (uint32_t)h.lseq : 0u;
+        const uint32_t maxL = __reduce_max_sync(0xFFFFFFFFu, Ls);
+        const uint32_t s = act ? ((h.flag >> 4) & 1u) : 0u;
+        const uint8_t* seqp = act ? h.p + h.o_seq : B.bytes;
+        const uint8_t* qualp = act ? h.p + h.o_qual : B.bytes;
+        const ulonglong2* rowh = &PT->h[s][0][0];
+        const ulonglong2* rowt = &PT->t[s][0][0];
+        uint64_t hlo = 0, hhi = 0, tlo = 0, thi = 0;
+        uint64_t seq_cur = ldu64(seqp), q_lo = ldu64(qualp), q_hi = ldu64(qualp + 8);
+        uint64_t hist1 = 0, hist2 = 0;
+        uint32_t run = 0;
+        bool pend = false;
+        uint32_t* pwp = nullptr;
+        uint32_t psh = 0, pold = 0;
+        const uint32_t nchunks = (maxL + 15u) >> 4;
+        for (uint32_t c = 0; c < nchunks; ++c) {
+            // prefetch the next chunk of both streams (reads past a short record stay inside the padded batch)
+            const uint64_t seq_next = ldu64(seqp + 8 * (c + 1));
+            const uint64_t q_lo_next = ldu64(qualp + 16 * (c + 1)), q_hi_next = ldu64(qualp + 16 * (c + 1) + 8);
+            const bool has_out = c >= 2;
+#pragma unroll
+            for (uint32_t j = 0; j < 16; ++j) {
+                const uint32_t i = c * 16 + j;
+                if (i < Ls) {
+                    const uint32_t nin = (uint32_t)(seq_cur >> (4 * (j ^ 1))) & 15u;
+                    const uint32_t nout = has_out ? ((uint32_t)(hist2 >> (4 * (j ^ 1))) & 15u) : 16u;
+                    const uint32_t q = (uint32_t)((j < 8 ? q_lo : q_hi) >> (8 * (j & 7))) & 255u;
+                    const uint32_t ridx = nin * 17u + nout;
+                    const ulonglong2 a = rowh[ridx], b = rowt[ridx];
+                    // h = rotl1(h) ^ H[in] ^ rotl_k(H[out])
+                    const uint64_t nh = (hhi << 1) | (hlo >> 63);
+                    hlo = ((hlo << 1) | (hhi >> 63)) ^ a.x;
+                    hhi = nh ^ a.y;
+                    // ht = rotr1(ht ^ rotl_k(Ht[in]) ^ Ht[out])
+                    const uint64_t xl = tlo ^ b.x, xh = thi ^ b.y;
+                    tlo = (xl >> 1) | (xh << 63);
+                    thi = (xh >> 1) | (xl << 63);
+                    const bool valid = (nin != 15u) && ((int8_t)(q + 33u) >= (int8_t)q_thresh);
+                    run = valid ? run + 1u : 0u;
+                    if (pend) {  // finish the probe issued for the previous k-mer
+                        while (((pold >> psh) & 15u) != 15u) {
+                            const uint32_t assumed = pold;
+                            pold = atomicCAS(pwp, assumed, assumed + (1u << psh));
+                            if (pold == assumed) break;
+                        }
+                        pend = false;
+                    }
+                    if (run >= 32u) {
+                        const uint64_t hv = hlo ^ tlo;
+                        ++my_count;
+                        atomicAdd(sm + ((uint32_t)hv & f2mask), 1u);
+                        uint32_t w = hv ? (uint32_t)(__ffsll((long long)hv) - 1) : 63u;
+                        if (w > 31u) w = 31u;
+                        const uint64_t index = (hv >> (w + 1u)) & idx_mask;
+                        pwp = sk + w * words_per_level + (uint32_t)(index >> 3);
+                        psh = ((uint32_t)index & 7u) * 4u;
+                        pold = __ldcg(pwp);
+                        pend = true;
+                    }
+                }
+                __syncwarp();
+            }
+            hist2 = hist1;
+            hist1 = seq_cur;
+            seq_cur = seq_next;
+            q_lo = q_lo_next;
+            q_hi = q_hi_next;
+        }
+        if (pend) {
+            while (((pold >> psh) & 15u) != 15u) {
+                const uint32_t assumed = pold;
+                pold = atomicCAS(pwp, assumed, assumed + (1u << psh));
+                if (pold == assumed) break;
+            }
+        }
+        __syncwarp();
+    }
+    for (int o = 16; o > 0; o >>= 1) my_count += __shfl_xor_sync(0xFFFFFFFFu, my_count, o);
+    if ((threadIdx.x & 31u) == 0 && my_count) atomicAdd((unsigned long long*)G, my_count);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < L.f2size; i += blockDim.x) {
+        uint32_t v = sm[i];
+        if (v) atomicAdd((unsigned long long*)(G + 8 + i), (unsigned long long)v);
+    }
+}
+
+}  // namespace bqc

@@ -454,9 +454,10 @@ __global__ void __launch_bounds__(256) k_cov_scatter(EngineView E, BatchView B, 
 // Window flush = one pass over the ring range: single-pass prefix sum with decoupled look-back
 // (tile aggregate / inclusive-prefix flags), fused with the min(depth,100) histogram and the re-zeroing of
 // the ring.  8 bytes of HBM traffic per genome position (read + write), 16-byte vector accesses.
-static const uint32_t kCovTile = 8192;  // ring entries per tile (1024 threads x 8)
+static const uint32_t kCovThreads = 256;                // small CTAs: the look-back of one tile stalls only 8 warps
+static const uint32_t kCovTile = kCovThreads * 8;     // ring entries per tile (8 per thread)
 static const uint32_t kTileAggregate = 1u, kTileInclusive = 2u;
-__global__ void __launch_bounds__(1024) k_cov_flush(uint32_t* ring, uint32_t ring_mask, uint32_t start, uint64_t len, uint32_t* carry,
+__global__ void __launch_bounds__(kCovThreads) k_cov_flush(uint32_t* ring, uint32_t ring_mask, uint32_t start, uint64_t len, uint32_t* carry,
                                                     unsigned long long* tile_state, uint32_t* ticket, unsigned long long* poscov) {
     __shared__ uint32_t hist[128];
     __shared__ uint32_t wsum[32];
@@ -474,8 +475,8 @@ __global__ void __launch_bounds__(1024) k_cov_flush(uint32_t* ring, uint32_t rin
         uint32_t v[8];
         const uint32_t ridx = (start + (uint32_t)i0) & ring_mask;
         if (i0 + 8 <= len) {
-            uint4 a = *reinterpret_cast<const uint4*>(ring + ridx);
-            uint4 b = *reinterpret_cast<const uint4*>(ring + ((ridx + 4) & ring_mask));
+            uint4 a = __ldcs(reinterpret_cast<const uint4*>(ring + ridx));  // streamed once: do not keep in L2
+            uint4 b = __ldcs(reinterpret_cast<const uint4*>(ring + ((ridx + 4) & ring_mask)));
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
         } else {
 #pragma unroll
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(1024) k_cov_flush(uint32_t* ring, uint32_t rin
         if ((threadIdx.x & 31u) == 31u) wsum[threadIdx.x >> 5] = incl;
         __syncthreads();
         if (threadIdx.x < 32) {
-            uint32_t w = wsum[threadIdx.x], wi = w;
+            uint32_t w = threadIdx.x < (kCovThreads >> 5) ? wsum[threadIdx.x] : 0u, wi = w;
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
                 if (threadIdx.x >= (uint32_t)o) wi += t;
@@ -535,16 +536,20 @@ __global__ void __launch_bounds__(1024) k_cov_flush(uint32_t* ring, uint32_t rin
         }
         __syncthreads();
         uint32_t depth = s_prefix + wsum[threadIdx.x >> 5] + (incl - acc);
+        uint32_t zeros = 0;  // depth 0 dominates sparse data: counted in a register, one atomic per warp
 #pragma unroll
         for (uint32_t j = 0; j < 8; ++j) {
             if (i0 + j < len) {
                 depth += v[j];
-                atomicAdd(hist + min(depth, 100u), 1u);
+                if (depth == 0) ++zeros;
+                else atomicAdd(hist + min(depth, 100u), 1u);
             }
         }
+        zeros = __reduce_add_sync(0xFFFFFFFFu, zeros);
+        if ((threadIdx.x & 31u) == 0 && zeros) atomicAdd(hist, zeros);
         if (i0 + 8 <= len) {
-            *reinterpret_cast<uint4*>(ring + ridx) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(ring + ((ridx + 4) & ring_mask)) = make_uint4(0, 0, 0, 0);
+            __stcs(reinterpret_cast<uint4*>(ring + ridx), make_uint4(0, 0, 0, 0));
+            __stcs(reinterpret_cast<uint4*>(ring + ((ridx + 4) & ring_mask)), make_uint4(0, 0, 0, 0));
         } else {
 #pragma unroll
             for (uint32_t j = 0; j < 8; ++j)
@@ -592,3 +597,4 @@ __global__ void k_counters_add(unsigned long long* dst, const unsigned long long
 }
 
 }  // namespace bqc
+#include "kernel_sketch.cuh"
