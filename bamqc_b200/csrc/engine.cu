@@ -7,11 +7,17 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <random>
 #include <string>
@@ -34,6 +40,64 @@ static thread_local std::string g_last_error;
             return BQC_ERR_CUDA;                                                                   \
         }                                                                                          \
     } while (0)
+
+// Persistent host worker pool (framing and the scan pre-pass run once per staging buffer; spawning threads
+// every time costs more than the work for small buffers).
+class HostPool {
+   public:
+    explicit HostPool(int workers) {
+        for (int i = 0; i < workers; ++i) th_.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    // run fn(0..n-1) on the workers and the calling thread; returns when all are done
+    void run(int n, const std::function<void(int)>& fn) {
+        if (n <= 1 || th_.empty()) { for (int i = 0; i < n; ++i) fn(i); return; }
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn; n_ = n; next_ = 0; done_ = 0; ++gen_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> g(m_);
+        cv_done_.wait(g, [this] { return done_ == n_; });
+        fn_ = nullptr;
+    }
+   private:
+    void work() {
+        for (;;) {
+            int i;
+            const std::function<void(int)>* f;
+            { std::lock_guard<std::mutex> g(m_); if (!fn_ || next_ >= n_) return; i = next_++; f = fn_; }
+            (*f)(i);
+            { std::lock_guard<std::mutex> g(m_); if (++done_ == n_) cv_done_.notify_all(); }
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            { std::unique_lock<std::mutex> g(m_); cv_.wait(g, [&] { return gen_ != seen; }); seen = gen_; if (stop_) return; }
+            work();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, cv_done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int n_ = 0, next_ = 0, done_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+static void run_parallel(HostPool* pool, int n, const std::function<void(int)>& fn) {
+    if (pool) { pool->run(n, fn); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < n; ++t) th.emplace_back(fn, t);
+    if (n > 0) fn(0);
+    for (auto& t : th) t.join();
+}
 
 struct ScanMeta { int32_t rid; uint32_t pos; };  // host_scan pass 1 -> pass 2
 
@@ -76,6 +140,8 @@ struct Slot {  // one half of the staging double buffer
     DeviceBatch dev;
     cudaEvent_t done = nullptr;
     bool in_flight = false;
+    bool queued = false;           // handed to the commit thread, not yet enqueued on the GPU
+    std::vector<ScanMeta> meta;    // pass 1 -> pass 2
 };
 
 struct bqc_engine {
@@ -108,7 +174,8 @@ struct bqc_engine {
     std::vector<uint64_t> ref_len;
     cudaStream_t compute = nullptr, copy = nullptr, covs = nullptr;  // covs: coverage scatter + flush (HBM bound) overlaps the table kernels
     cudaEvent_t cov_done = nullptr, cov_go = nullptr;
-    Slot slots[2];
+    static const int kSlots = 4;  // depth of the staging pipeline: framing / anchor pass / H2D / kernels each hold one
+    Slot slots[kSlots];
     int next_slot = 0;
     cudaEvent_t copied = nullptr;
 
@@ -116,6 +183,17 @@ struct bqc_engine {
     std::vector<ScanMeta> scan_meta;
     std::vector<uint64_t> frame_offsets;
     int host_threads = 1;
+    std::unique_ptr<HostPool> pool;
+    // streaming path: the caller thread frames and pre-scans buffer i+1 while the commit thread runs the
+    // sequential anchor pass, the H2D copies and the kernel launches of buffer i
+    struct Task { int slot; const uint8_t* h2d_src; size_t span; uint64_t n_records; uint32_t max_lseq; };
+    std::thread commit_thread;
+    std::mutex cm;
+    std::condition_variable ccv, ccv_idle;
+    std::deque<Task> cq;
+    bool cstop = false, cbusy = false;
+    int async_rc = 0;
+    int tune_stats_bps = 0, tune_sketch_threads = 1024;  // BQC_STATS_BPS / BQC_SKETCH_THREADS (tuning knobs)
     std::vector<CovState> cov;
     uint64_t records_seen = 0, launches = 0;
     bool finished = false;
@@ -205,6 +283,11 @@ static void free_device_batch(DeviceBatch& d) {
 extern "C" void bqc_destroy(bqc_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
+    if (e->commit_thread.joinable()) {
+        { std::lock_guard<std::mutex> g(e->cm); e->cstop = true; }
+        e->ccv.notify_all();
+        e->commit_thread.join();
+    }
     if (e->compute) cudaStreamSynchronize(e->compute);
     if (e->copy) cudaStreamSynchronize(e->copy);
     if (e->covs) cudaStreamSynchronize(e->covs);
@@ -248,8 +331,11 @@ static int alloc_device_batch(bqc_engine* e, DeviceBatch& d, uint64_t bytes_cap,
     return 0;
 }
 
+static int drain_commits(bqc_engine* e);
 extern "C" int bqc_reset(bqc_engine* e) {
     CU(cudaSetDevice(e->cfg.device));
+    drain_commits(e);
+    e->async_rc = 0;
     CU(cudaStreamSynchronize(e->compute));
     CU(cudaStreamSynchronize(e->copy));
     CU(cudaStreamSynchronize(e->covs));
@@ -309,7 +395,10 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     if (e->staging_bytes > 0xF0000000ull) e->staging_bytes = 0xF0000000ull;
     e->max_records_per_slot = e->staging_bytes / 40 + 16;  // a record is at least 36 bytes
     e->ring_log2 = cfg->cov_ring_log2 ? cfg->cov_ring_log2 : 28;
+    if (const char* v = getenv("BQC_STATS_BPS")) e->tune_stats_bps = atoi(v);
+    if (const char* v = getenv("BQC_SKETCH_THREADS")) e->tune_sketch_threads = std::max(32, std::min(1024, atoi(v) & ~31));
     e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (e->host_threads > 1) e->pool.reset(new HostPool(e->host_threads - 1));
     if (e->ring_log2 < 13 || e->ring_log2 > 30) { set_error(e, "bqc_create: cov_ring_log2 out of range"); delete e; return BQC_ERR_ARG; }
 
     int rc = [&]() -> int {
@@ -424,7 +513,7 @@ static inline bool plausible_record(const uint8_t* d, size_t n, size_t p, int64_
 // like records); the slices are then stitched in order and a slice is accepted only if the chain of the
 // previous slice ends exactly on its start -- otherwise the rest is framed sequentially.  The result is
 // identical to the sequential walk.
-static uint64_t frame_records_mt(const uint8_t* data, size_t n, uint64_t* offsets, uint64_t cap, int threads, int64_t n_ref) {
+static uint64_t frame_records_mt(const uint8_t* data, size_t n, uint64_t* offsets, uint64_t cap, int threads, int64_t n_ref, HostPool* pool = nullptr) {
     const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n >> 22));
     if (T <= 1) return bqc_frame_records(data, n, offsets, cap);
     const uint64_t NONE = ~0ull;
@@ -460,16 +549,8 @@ static uint64_t frame_records_mt(const uint8_t* data, size_t n, uint64_t* offset
         }
         P.end = p;
     };
-    {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < T; ++t) pool.emplace_back(find_start, t);
-        for (auto& th : pool) th.join();
-    }
-    {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < T; ++t) pool.emplace_back(frame_part, t);
-        for (auto& th : pool) th.join();
-    }
+    run_parallel(pool, T, find_start);
+    run_parallel(pool, T, frame_part);
     // stitch
     uint64_t nrec = 0, pos = 0;
     bool ok = true;
@@ -531,37 +612,12 @@ static uint32_t host_lane(const bqc_engine* e, const uint8_t* r, uint32_t avail)
     return 0;
 }
 
-// Walk the records of a submission once: 32-bit offsets, per-record lane, the coverage anchor scan
-// (the only order-dependent part of the reference, src/OverallNumbers.hpp:84-110) and the segments
-// that keep the coverage ring within capacity.
-static int host_scan(bqc_engine* e, const uint8_t* data, const uint64_t* offs, uint64_t n_records, uint32_t* o32, uint32_t* cov, uint8_t* lane_out, uint32_t& max_lseq, std::vector<Segment>& segs) {
-    const uint64_t ring_size = 1ull << e->ring_log2;
-    auto open_segment = [&](uint64_t r0) {
-        Segment s;
-        s.r0 = r0;
-        s.r1 = r0;
-        s.base_window.resize(e->n_lanes);
-        s.flush_to.resize(e->n_lanes);
-        for (uint32_t l = 0; l < e->n_lanes; ++l) s.base_window[l] = e->cov[l].flushed / 1000;
-        segs.push_back(s);
-    };
-    auto close_segment = [&](uint64_t r1) {
-        Segment& s = segs.back();
-        s.r1 = r1;
-        for (uint32_t l = 0; l < e->n_lanes; ++l) {
-            s.flush_to[l] = e->cov[l].v1 * 1000;
-            e->cov[l].flushed = s.flush_to[l];
-        }
-    };
-    segs.clear();
-    open_segment(0);
+// Pass 1 of the host pre-pass (host threads): touch every record header once; 32-bit offsets, lane, longest
+// read and a compact (rid, pos) pair for the records that take part in the coverage statistic.
+static void host_scan_pass1(bqc_engine* e, const uint8_t* data, const uint64_t* offs, uint64_t n_records, uint32_t* o32, uint8_t* lane_out, ScanMeta* meta, uint32_t& max_lseq) {
     max_lseq = 0;
     const uint64_t base_off = offs[0];
-    // Pass 1 (host threads): touch every record header once; 32-bit offsets, lane, longest read and a
-    // compact (rid, pos) pair for the records that take part in the coverage statistic.
     typedef ScanMeta Meta;
-    std::vector<Meta>& meta = e->scan_meta;
-    if (meta.size() < n_records) meta.resize(n_records);
     const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)e->host_threads, n_records / 65536));
     std::vector<uint32_t> tmax((size_t)T, 0);
     auto pass1 = [&](int t) {
@@ -588,45 +644,108 @@ static int host_scan(bqc_engine* e, const uint8_t* data, const uint64_t* offs, u
         }
         tmax[(size_t)t] = mx;
     };
-    if (T == 1) {
-        pass1(0);
-    } else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < T; ++t) pool.emplace_back(pass1, t);
-        for (auto& th : pool) th.join();
-    }
+    auto t_p1 = std::chrono::steady_clock::now();
+    run_parallel(e->pool.get(), T, pass1);
     for (uint32_t v : tmax) max_lseq = std::max(max_lseq, v);
-    // Pass 2 (sequential, 8 bytes per record): the anchor recurrence of OverallNumbers::coverage
-    for (uint64_t r = 0; r < n_records; ++r) {
-        uint32_t code = kNone;
-        {
-            const int32_t rid = meta[r].rid;
-            const uint32_t b = meta[r].pos;
-            const uint32_t lane = lane_out ? lane_out[r] : 0u;
-            if (rid >= 0) {
-                CovState& st = e->cov[lane];
-                for (int attempt = 0; attempt < 2; ++attempt) {
-                    CovState t = st;
-                    if (t.first) { t.first = false; t.id = rid; t.shift = b; }
-                    if (t.id != rid || (uint32_t)(b - t.shift) > 2000u) { t.id = rid; t.v1 += 2; t.shift = b; }
-                    uint32_t pos = b - t.shift;
-                    if (pos > 1000u && pos < 2000u) { t.v1 += 1; t.shift += 1000u; pos = b - t.shift; }
-                    // everything this record can touch must fit the ring behind the unflushed position
-                    if (t.v1 * 1000 + 2001 - t.flushed > ring_size - 8 && attempt == 0 && r > segs.back().r0) {
-                        close_segment(r);
-                        open_segment(r);
-                        continue;
-                    }
-                    st = t;
-                    code = (uint32_t)((t.v1 - segs.back().base_window[lane]) << 11) | pos;
-                    break;
-                }
-            }
-        }
-        cov[r] = code;
-    }
     o32[n_records] = (uint32_t)(offs[n_records] - base_off);
+    if (e->profiling) { e->prof_ms[6] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_p1).count(); e->prof_n[6] += 1; }
+}
+
+// Pass 2 (sequential, 8 bytes per record): the anchor recurrence of OverallNumbers::coverage -- the only
+// order-dependent part of the reference (src/OverallNumbers.hpp:84-110) -- and the segments that keep the
+// coverage ring within capacity.
+static void host_scan_pass2(bqc_engine* e, const ScanMeta* meta, uint64_t n_records, uint32_t* cov, const uint8_t* lane_out, std::vector<Segment>& segs) {
+    auto t_p2 = std::chrono::steady_clock::now();
+    const uint64_t ring_size = 1ull << e->ring_log2;
+    auto open_segment = [&](uint64_t r0) {
+        Segment s;
+        s.r0 = r0;
+        s.r1 = r0;
+        s.base_window.resize(e->n_lanes);
+        s.flush_to.resize(e->n_lanes);
+        for (uint32_t l = 0; l < e->n_lanes; ++l) s.base_window[l] = e->cov[l].flushed / 1000;
+        segs.push_back(s);
+    };
+    auto close_segment = [&](uint64_t r1) {
+        Segment& s = segs.back();
+        s.r1 = r1;
+        for (uint32_t l = 0; l < e->n_lanes; ++l) {
+            s.flush_to[l] = e->cov[l].v1 * 1000;
+            e->cov[l].flushed = s.flush_to[l];
+        }
+    };
+    segs.clear();
+    open_segment(0);
+    // (segment changes never alter the anchor state, only which ring window code 0 refers to)
+    const uint64_t* base_window = segs.back().base_window.data();
+    uint64_t seg_r0 = segs.back().r0;
+    if (!lane_out) {
+        // single read group: the anchor state lives in registers
+        CovState& st = e->cov[0];
+        bool first = st.first;
+        int32_t id = st.id;
+        uint32_t shift = st.shift;
+        uint64_t v1 = st.v1, base0 = base_window[0];
+        const uint64_t limit = ring_size - 8 - 2001;
+        for (uint64_t r = 0; r < n_records; ++r) {
+            const int32_t rid = meta[r].rid;
+            uint32_t code = kNone;
+            if (rid >= 0) {
+                const uint32_t b = meta[r].pos;
+                if (first) { first = false; id = rid; shift = b; }
+                if (id != rid || (uint32_t)(b - shift) > 2000u) { id = rid; v1 += 2; shift = b; }
+                uint32_t pos = b - shift;
+                if (pos > 1000u && pos < 2000u) { v1 += 1; shift += 1000u; pos = b - shift; }
+                if (v1 * 1000 - st.flushed > limit && r > seg_r0) {
+                    close_segment(r);  // uses the state stored before this record
+                    open_segment(r);
+                    base0 = segs.back().base_window[0];
+                    seg_r0 = r;
+                }
+                st.first = false;
+                st.id = id;
+                st.shift = shift;
+                st.v1 = v1;
+                code = (uint32_t)((v1 - base0) << 11) | pos;
+            }
+            cov[r] = code;
+        }
+    } else
+    for (uint64_t r = 0; r < n_records; ++r) {
+        const int32_t rid = meta[r].rid;
+        if (rid < 0) { cov[r] = kNone; continue; }
+        const uint32_t b = meta[r].pos;
+        const uint32_t lane = lane_out ? lane_out[r] : 0u;
+        CovState& st = e->cov[lane];
+        int32_t id = st.id;
+        uint32_t shift = st.shift;
+        uint64_t v1 = st.v1;
+        if (st.first) { id = rid; shift = b; }                                   // src/OverallNumbers.hpp:84-89
+        if (id != rid || (uint32_t)(b - shift) > 2000u) { id = rid; v1 += 2; shift = b; }  // :91-100 reset: two windows flushed
+        uint32_t pos = b - shift;
+        if (pos > 1000u && pos < 2000u) { v1 += 1; shift += 1000u; pos = b - shift; }       // :104-110 roll: one window flushed
+        // everything this record can touch must fit the ring behind the unflushed position
+        if (v1 * 1000 + 2001 - st.flushed > ring_size - 8 && r > seg_r0) {
+            close_segment(r);
+            open_segment(r);
+            base_window = segs.back().base_window.data();
+            seg_r0 = r;
+        }
+        st.first = false;
+        st.id = id;
+        st.shift = shift;
+        st.v1 = v1;
+        cov[r] = (uint32_t)((v1 - base_window[lane]) << 11) | pos;
+    }
     close_segment(n_records);
+    if (e->profiling) { e->prof_ms[7] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_p2).count(); e->prof_n[7] += 1; }
+}
+
+// both passes back to back (resident path)
+static int host_scan(bqc_engine* e, const uint8_t* data, const uint64_t* offs, uint64_t n_records, uint32_t* o32, uint32_t* cov, uint8_t* lane_out, uint32_t& max_lseq, std::vector<Segment>& segs) {
+    if (e->scan_meta.size() < n_records) e->scan_meta.resize(n_records);
+    host_scan_pass1(e, data, offs, n_records, o32, lane_out, e->scan_meta.data(), max_lseq);
+    host_scan_pass2(e, e->scan_meta.data(), n_records, cov, lane_out, segs);
     return 0;
 }
 
@@ -657,6 +776,7 @@ extern "C" void bqc_profile_enable(bqc_engine* e, int on) { e->profiling = on !=
 // 3 coverage flush (3 kernels per launch group), 4 merge/export.  Synchronises the compute stream.
 extern "C" int bqc_profile_read(bqc_engine* e, double ms_out[8], uint64_t n_out[8]) {
     CU(cudaSetDevice(e->cfg.device));
+    drain_commits(e);
     CU(cudaStreamSynchronize(e->compute));
     CU(cudaStreamSynchronize(e->covs));
     for (auto& p : e->prof_pending) {
@@ -718,6 +838,7 @@ static int run_device_batch(bqc_engine* e, const DeviceBatch& d) {
     int bps = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats, (int)kStatsThreads, stats_smem));
     if (bps < 1) { set_error(e, "k_stats does not fit: %zu bytes of shared memory", stats_smem); return BQC_ERR_ARG; }
+    if (e->tune_stats_bps > 0 && e->tune_stats_bps < bps) bps = e->tune_stats_bps;
     e->stats_blocks_per_sm = bps;
     const uint64_t ring_size = 1ull << e->ring_log2;
     const uint64_t n = d.n_records;
@@ -776,7 +897,7 @@ static int run_device_batch(bqc_engine* e, const DeviceBatch& d) {
                 int gs = (int)std::min<uint64_t>((n + kSketchThreads - 1) / kSketchThreads, (uint64_t)e->n_sm);
                 ProfScope prof(e, 2);
                 if (SP.k == 32u && e->L.f2size <= 32768u)
-                    k_sketch32<<<gs, kSketchThreads, e->L.f2size * 4 + sizeof(HashPairTable), e->compute>>>(E, B, lane, SP, e->d_hash + ki);
+                    k_sketch32<<<gs, e->tune_sketch_threads, e->L.f2size * 4 + sizeof(HashPairTable), e->compute>>>(E, B, lane, SP, e->d_hash + ki);
                 else if (e->L.f2size <= 32768u)
                     k_sketch<true><<<gs, kSketchThreads, e->L.f2size * 4, e->compute>>>(E, B, lane, SP, e->d_hash + ki);
                 else
@@ -802,14 +923,77 @@ static int ensure_slot(bqc_engine* e, Slot& s) {
     return alloc_device_batch(e, s.dev, e->staging_bytes, e->max_records_per_slot);
 }
 
-extern "C" int bqc_acquire_staging(bqc_engine* e, void** pinned, size_t* capacity) {
-    Slot& s = e->slots[e->next_slot];
-    int rc = ensure_slot(e, s);
+static int commit_task(bqc_engine* e, const bqc_engine::Task& t) {
+    Slot& s = e->slots[t.slot];
+    DeviceBatch& d = s.dev;
+    const uint64_t n_records = t.n_records;
+    host_scan_pass2(e, s.meta.data(), n_records, s.h_cov, e->n_lanes > 1 ? s.h_lane : nullptr, d.segs);
+    d.max_lseq = t.max_lseq;
+    d.n_records = n_records;
+    d.n_bytes = t.span;
+    d.first_record = e->records_seen;
+    CU(cudaMemcpyAsync(d.bytes, t.h2d_src, t.span, cudaMemcpyHostToDevice, e->copy));
+    CU(cudaMemcpyAsync(d.offsets, s.h_offsets, (n_records + 1) * 4, cudaMemcpyHostToDevice, e->copy));
+    CU(cudaMemcpyAsync(d.cov, s.h_cov, n_records * 4, cudaMemcpyHostToDevice, e->copy));
+    if (e->n_lanes > 1) CU(cudaMemcpyAsync(d.rec_lane, s.h_lane, n_records, cudaMemcpyHostToDevice, e->copy));
+    CU(cudaEventRecord(e->copied, e->copy));
+    CU(cudaStreamWaitEvent(e->compute, e->copied, 0));
+    int rc = run_device_batch(e, d);
     if (rc) return rc;
+    CU(cudaEventRecord(s.done, e->compute));
+    e->records_seen += n_records;
+    return 0;
+}
+
+static void commit_loop(bqc_engine* e) {
+    cudaSetDevice(e->cfg.device);
+    for (;;) {
+        bqc_engine::Task t;
+        {
+            std::unique_lock<std::mutex> g(e->cm);
+            e->ccv.wait(g, [&] { return e->cstop || !e->cq.empty(); });
+            if (e->cq.empty()) return;  // stop requested and nothing left
+            t = e->cq.front();
+            e->cq.pop_front();
+            e->cbusy = true;
+        }
+        int rc = e->async_rc ? e->async_rc : commit_task(e, t);
+        {
+            std::lock_guard<std::mutex> g(e->cm);
+            e->slots[t.slot].queued = false;
+            e->slots[t.slot].in_flight = rc == 0;
+            e->cbusy = false;
+            if (rc && !e->async_rc) e->async_rc = rc;
+        }
+        e->ccv_idle.notify_all();
+    }
+}
+
+// wait until the commit thread has enqueued everything handed to it; returns its sticky error
+static int drain_commits(bqc_engine* e) {
+    std::unique_lock<std::mutex> g(e->cm);
+    e->ccv_idle.wait(g, [&] { return e->cq.empty() && !e->cbusy; });
+    return e->async_rc;
+}
+
+static int wait_slot(bqc_engine* e, Slot& s) {
+    {
+        std::unique_lock<std::mutex> g(e->cm);
+        e->ccv_idle.wait(g, [&] { return !s.queued; });
+    }
     if (s.in_flight) {
         CU(cudaEventSynchronize(s.done));
         s.in_flight = false;
     }
+    return 0;
+}
+
+extern "C" int bqc_acquire_staging(bqc_engine* e, void** pinned, size_t* capacity) {
+    Slot& s = e->slots[e->next_slot];
+    int rc = ensure_slot(e, s);
+    if (rc) return rc;
+    rc = wait_slot(e, s);
+    if (rc) return rc;
     *pinned = s.pinned;
     *capacity = e->staging_bytes;
     return 0;
@@ -818,19 +1002,20 @@ extern "C" int bqc_acquire_staging(bqc_engine* e, void** pinned, size_t* capacit
 extern "C" int bqc_submit(bqc_engine* e, const void* data, size_t n_bytes, const uint64_t* record_offsets, uint64_t n_records) {
     if (e->finished) { set_error(e, "bqc_submit after bqc_finish (call bqc_reset)"); return BQC_ERR_ARG; }
     if (n_bytes > e->staging_bytes) { set_error(e, "bqc_submit: %zu bytes exceed the staging capacity %llu", n_bytes, (unsigned long long)e->staging_bytes); return BQC_ERR_ARG; }
+    if (e->async_rc) return e->async_rc;
     CU(cudaSetDevice(e->cfg.device));
     Slot& s = e->slots[e->next_slot];
     int rc = ensure_slot(e, s);
     if (rc) return rc;
-    if (s.in_flight) {
-        CU(cudaEventSynchronize(s.done));
-        s.in_flight = false;
-    }
+    rc = wait_slot(e, s);
+    if (rc) return rc;
     const uint8_t* src = (const uint8_t*)data;
     std::vector<uint64_t>& own_offsets = e->frame_offsets;
     if (!record_offsets) {
         if (own_offsets.size() < n_bytes / 36 + 2) own_offsets.resize(n_bytes / 36 + 2);
-        n_records = frame_records_mt(src, n_bytes, own_offsets.data(), own_offsets.size(), e->host_threads, std::max(1, e->cfg.n_ref));
+        auto t_f0 = std::chrono::steady_clock::now();
+        n_records = frame_records_mt(src, n_bytes, own_offsets.data(), own_offsets.size(), e->host_threads, std::max(1, e->cfg.n_ref), e->pool.get());
+        if (e->profiling) { e->prof_ms[5] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_f0).count(); e->prof_n[5] += 1; }
         if (own_offsets[n_records] != n_bytes) {
             e->host_error.code = BQC_ERR_BAD_RECORD;
             e->host_error.record = e->records_seen + n_records;
@@ -841,38 +1026,34 @@ extern "C" int bqc_submit(bqc_engine* e, const void* data, size_t n_bytes, const
     }
     if (n_records > e->max_records_per_slot) { set_error(e, "bqc_submit: too many records for one staging buffer"); return BQC_ERR_ARG; }
     if (n_records == 0) return 0;
-    DeviceBatch& d = s.dev;
-    rc = host_scan(e, src, record_offsets, n_records, s.h_offsets, s.h_cov, s.h_lane, d.max_lseq, d.segs);
-    if (rc) return rc;
+    // pass 1 on the caller's thread (+ pool); pass 2, copies and launches on the commit thread
+    if (s.meta.size() < n_records) s.meta.resize(n_records);
+    bqc_engine::Task t;
+    t.slot = e->next_slot;
+    t.n_records = n_records;
+    host_scan_pass1(e, src, record_offsets, n_records, s.h_offsets, e->n_lanes > 1 ? s.h_lane : nullptr, s.meta.data(), t.max_lseq);
     const uint8_t* first = src + record_offsets[0];
-    size_t span = (size_t)(record_offsets[n_records] - record_offsets[0]);
-    const uint8_t* h2d_src = first;
-    if (first < s.pinned || first + span > s.pinned + e->staging_bytes + 256) {
-        // not our staging buffer: page-locked memory of the caller is copied from directly, pageable
-        // memory is staged through the pinned buffer
+    t.span = (size_t)(record_offsets[n_records] - record_offsets[0]);
+    t.h2d_src = first;
+    if (first < s.pinned || first + t.span > s.pinned + e->staging_bytes + 256) {
+        // not our staging buffer: page-locked memory of the caller is copied from directly (the caller keeps it
+        // unchanged until bqc_sync), pageable memory is staged through the pinned buffer before returning
         cudaPointerAttributes attr;
         bool pinned = cudaPointerGetAttributes(&attr, first) == cudaSuccess && attr.type == cudaMemoryTypeHost;
         cudaGetLastError();
         if (!pinned) {
-            memcpy(s.pinned, first, span);
-            h2d_src = s.pinned;
+            memcpy(s.pinned, first, t.span);
+            t.h2d_src = s.pinned;
         }
     }
-    d.n_records = n_records;
-    d.n_bytes = span;
-    d.first_record = e->records_seen;
-    CU(cudaMemcpyAsync(d.bytes, h2d_src, span, cudaMemcpyHostToDevice, e->copy));
-    CU(cudaMemcpyAsync(d.offsets, s.h_offsets, (n_records + 1) * 4, cudaMemcpyHostToDevice, e->copy));
-    CU(cudaMemcpyAsync(d.cov, s.h_cov, n_records * 4, cudaMemcpyHostToDevice, e->copy));
-    if (e->n_lanes > 1) CU(cudaMemcpyAsync(d.rec_lane, s.h_lane, n_records, cudaMemcpyHostToDevice, e->copy));
-    CU(cudaEventRecord(e->copied, e->copy));
-    CU(cudaStreamWaitEvent(e->compute, e->copied, 0));
-    rc = run_device_batch(e, d);
-    if (rc) return rc;
-    CU(cudaEventRecord(s.done, e->compute));
-    s.in_flight = true;
-    e->records_seen += n_records;
-    e->next_slot ^= 1;
+    {
+        std::lock_guard<std::mutex> g(e->cm);
+        if (!e->commit_thread.joinable()) e->commit_thread = std::thread(commit_loop, e);
+        s.queued = true;
+        e->cq.push_back(t);
+    }
+    e->ccv.notify_all();
+    e->next_slot = (e->next_slot + 1) % bqc_engine::kSlots;
     return 0;
 }
 
@@ -883,11 +1064,12 @@ extern "C" int bqc_batch_prepare(bqc_engine* e, const void* data, size_t n_bytes
     *out = nullptr;
     if (n_bytes >= 0xFFFFFF00ull) { set_error(e, "bqc_batch_prepare: a batch must be smaller than 4 GiB"); return BQC_ERR_ARG; }
     CU(cudaSetDevice(e->cfg.device));
+    drain_commits(e);
     const uint8_t* src = (const uint8_t*)data;
     std::vector<uint64_t> own_offsets;
     if (!record_offsets) {
         own_offsets.resize(n_bytes / 36 + 2);
-        n_records = frame_records_mt(src, n_bytes, own_offsets.data(), own_offsets.size(), e->host_threads, std::max(1, e->cfg.n_ref));
+        n_records = frame_records_mt(src, n_bytes, own_offsets.data(), own_offsets.size(), e->host_threads, std::max(1, e->cfg.n_ref), e->pool.get());
         record_offsets = own_offsets.data();
     }
     bqc_batch* b = new bqc_batch();
@@ -916,6 +1098,7 @@ extern "C" int bqc_batch_prepare(bqc_engine* e, const void* data, size_t n_bytes
 extern "C" int bqc_batch_run(bqc_engine* e, bqc_batch* b) {
     CU(cudaSetDevice(e->cfg.device));
     if (e->finished) { set_error(e, "bqc_batch_run after bqc_finish (call bqc_reset)"); return BQC_ERR_ARG; }
+    drain_commits(e);
     e->cov = b->d.cov_after;  // replaying a prepared batch restores the anchor state that follows it
     e->records_seen = b->d.records_after;
     return run_device_batch(e, b->d);
@@ -960,6 +1143,7 @@ extern "C" int bqc_get_error(bqc_engine* e, bqc_error_info* out) {
 
 extern "C" int bqc_sync(bqc_engine* e) {
     CU(cudaSetDevice(e->cfg.device));
+    { int arc = drain_commits(e); if (arc) return arc; }
     CU(cudaStreamSynchronize(e->copy));
     CU(cudaStreamSynchronize(e->covs));
     CU(cudaStreamSynchronize(e->compute));
@@ -983,6 +1167,7 @@ extern "C" uint64_t bqc_kernel_launches(bqc_engine* e) { return e->launches; }
 
 extern "C" int bqc_finish(bqc_engine* e) {
     CU(cudaSetDevice(e->cfg.device));
+    { int arc = drain_commits(e); if (arc) return arc; }
     if (!e->finished) {
         // src/bamqualcheck.cpp:447-453: update_coverage(); update_vectors(); update_coverage() for every lane
         for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {

@@ -159,8 +159,8 @@ class Engine:
         ms = (ctypes.c_double * 8)()
         n = (ctypes.c_uint64 * 8)()
         self._check(self.lib.bqc_profile_read(self.handle, ms, n))
-        names = ["k_stats", "k_eightmer", "k_sketch", "k_cov", "merge"]
-        return {names[i]: (float(ms[i]), int(n[i])) for i in range(5)}
+        names = ["k_stats", "k_eightmer", "k_sketch", "k_cov", "merge", "host_framing", "host_scan_pass1", "host_scan_pass2"]
+        return {names[i]: (float(ms[i]), int(n[i])) for i in range(8)}
 
     # ---- multi-GPU merge ----------------------------------------------------------------------------
     def counters_len(self):

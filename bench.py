@@ -341,11 +341,18 @@ def run_b200(args):
     e2e_steps = max(1, min(args.steps, 5))
     e2e_step()
     barrier()
+    eng.profile_enable(True)
+    eng.profile_read()
     w0 = time.perf_counter()
     for _ in range(e2e_steps):
         sc2 = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - w0
+    e2e_prof = eng.profile_read()
+    eng.profile_enable(False)
+    log(f"[rank {rank}] e2e: {e2e_s / e2e_steps * 1e3:.1f} ms/step; per step host framing {e2e_prof['host_framing'][0] / e2e_steps:.1f} ms, "
+        f"scan pass1 {e2e_prof['host_scan_pass1'][0] / e2e_steps:.1f} ms, pass2 {e2e_prof['host_scan_pass2'][0] / e2e_steps:.1f} ms; "
+        f"device kernels {sum(e2e_prof[k][0] for k in ('k_stats', 'k_eightmer', 'k_sketch')) / e2e_steps:.1f} ms")
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -374,6 +381,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (CUDA events on the launching stream, live) --------------------
     peak, which = measured_peak()
+    prof = {k: v for k, v in prof.items() if not k.startswith("host_")}
     fam = max(("k_stats", "k_eightmer", "k_sketch"), key=lambda f: prof[f][0])
     fam_ms, fam_n = prof[fam]
     per_launch_ms = fam_ms / max(1, fam_n)
