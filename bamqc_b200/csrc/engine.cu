@@ -163,6 +163,7 @@ struct bqc_engine {
     uint32_t* d_sketch = nullptr;
     uint32_t* d_ring = nullptr;
     uint32_t* d_cov_carry = nullptr;
+    uint8_t* d_touch = nullptr;  // one byte per 32 ring entries: granules that received coverage events
     uint32_t* d_cov_sums = nullptr;
     uint64_t cov_sums_cap = 0;
     unsigned long long* d_error = nullptr;
@@ -304,6 +305,7 @@ extern "C" void bqc_destroy(bqc_engine* e) {
     cudaFree(e->d_sketch);
     cudaFree(e->d_ring);
     cudaFree(e->d_cov_carry);
+    cudaFree(e->d_touch);
     cudaFree(e->d_cov_sums);
     cudaFree(e->d_error);
     cudaFree((void*)e->d_ref);
@@ -343,6 +345,7 @@ extern "C" int bqc_reset(bqc_engine* e) {
     CU(cudaMemsetAsync(e->d_sketch, 0, e->n_lanes * e->n_qk * e->sketch_words_per_qk * 4, e->compute));
     CU(cudaMemsetAsync(e->d_ring, 0, (uint64_t)e->n_lanes * (1ull << e->ring_log2) * 4, e->compute));
     CU(cudaMemsetAsync(e->d_cov_carry, 0, e->n_lanes * 4, e->compute));
+    CU(cudaMemsetAsync(e->d_touch, 0, (uint64_t)e->n_lanes * ((1ull << e->ring_log2) >> 5), e->compute));
     CU(cudaMemsetAsync(e->d_error, 0xFF, 8, e->compute));
     CU(cudaStreamSynchronize(e->compute));  // the coverage stream starts from a clean ring
     e->cov.assign(e->n_lanes, CovState());
@@ -416,7 +419,8 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         CU(cudaMalloc(&e->d_sketch, std::max<uint64_t>(4, e->n_lanes * e->n_qk * e->sketch_words_per_qk * 4)));
         CU(cudaMalloc(&e->d_ring, (uint64_t)e->n_lanes * (1ull << e->ring_log2) * 4));
         CU(cudaMalloc(&e->d_cov_carry, e->n_lanes * 4));
-        e->cov_sums_cap = ((1ull << e->ring_log2) + kCovTile - 1) / kCovTile + 2;
+        CU(cudaMalloc(&e->d_touch, (uint64_t)e->n_lanes * ((1ull << e->ring_log2) >> 5)));
+        e->cov_sums_cap = ((1ull << e->ring_log2) + kCovTile - 1) / kCovTile + 4;
         CU(cudaMalloc(&e->d_cov_sums, e->cov_sums_cap * 8));
         CU(cudaMalloc(&e->d_error, 8));
         int nref = std::max(1, cfg->n_ref);
@@ -799,14 +803,15 @@ static int launch_cov_flush(bqc_engine* e, uint32_t lane, uint64_t from_abs, uin
     uint32_t mask = (uint32_t)((1ull << e->ring_log2) - 1);
     uint32_t* ring = e->d_ring + (uint64_t)lane * (1ull << e->ring_log2);
     uint32_t start = (uint32_t)(from_abs & mask);
-    uint64_t ntiles = (len + kCovTile - 1) / kCovTile;
+    uint64_t ntiles = (len + 31 + kCovTile - 1) / kCovTile;  // tiles are aligned to 32-entry granules
     if (ntiles + 1 > e->cov_sums_cap) { set_error(e, "coverage flush larger than the ring"); return BQC_ERR_ARG; }
     int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)e->n_sm * (2048 / kCovThreads));
     unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
     ProfScope prof(e, 3, e->covs);
     // tile states + ticket live in one buffer: [0] = ticket, [1..] = states
     CU(cudaMemsetAsync(e->d_cov_sums, 0, (ntiles + 1) * 8, e->covs));
-    k_cov_flush<<<grid, kCovThreads, 0, e->covs>>>(ring, mask, start, len, e->d_cov_carry + lane, (unsigned long long*)e->d_cov_sums + 1,
+    uint8_t* touch = e->d_touch + (uint64_t)lane * ((1ull << e->ring_log2) >> 5);
+    k_cov_flush<<<grid, kCovThreads, 0, e->covs>>>(ring, touch, mask, start, len, e->d_cov_carry + lane, (unsigned long long*)e->d_cov_sums + 1,
                                                (uint32_t*)e->d_cov_sums, poscov);
     e->launches += 1;
     CU(cudaGetLastError());
@@ -819,6 +824,7 @@ static EngineView make_view(bqc_engine* e) {
     E.counters = e->d_counters;
     E.sketch = e->d_sketch;
     E.ring = e->d_ring;
+    E.touch = e->d_touch;
     E.ring_mask = (uint32_t)((1ull << e->ring_log2) - 1);
     E.ref = e->d_ref;
     E.ref_len = e->d_ref_len;

@@ -48,6 +48,7 @@ struct EngineView {
     int32_t n_ref;
     unsigned long long* error;       // min over (record << 8 | code), ~0 if none
     uint32_t insert_smem;            // insert-size bins kept in shared memory
+    uint8_t* touch;                  // [n_lanes][(ring_mask+1)/32] granules of the ring that hold events
 };
 
 struct SketchParams {
@@ -422,6 +423,7 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch(EngineView E, Batc
 // last, clipped at pos + j < 2*vsize where the reference's writes leave v2.
 __global__ void __launch_bounds__(256) k_cov_scatter(EngineView E, BatchView B, uint32_t lane) {
     uint32_t* ring = E.ring + (uint64_t)lane * ((uint64_t)E.ring_mask + 1);
+    uint8_t* touch = E.touch + (uint64_t)lane * (((uint64_t)E.ring_mask + 1) >> 5);  // one byte per 32 ring entries
     for (uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x; rec < B.n_records; rec += gridDim.x * blockDim.x) {
         const uint32_t code = B.cov[rec];
         if (code == kNone) continue;
@@ -442,8 +444,11 @@ __global__ void __launch_bounds__(256) k_cov_scatter(EngineView E, BatchView B, 
             if (op == 0u || op == 2u) {
                 if (c < lim && n > 0) {
                     uint32_t hi = min(c + n, lim);
-                    atomicAdd(ring + ((base_idx + c) & E.ring_mask), 1u);
-                    atomicAdd(ring + ((base_idx + hi) & E.ring_mask), 0xFFFFFFFFu);
+                    const uint32_t i0 = (base_idx + c) & E.ring_mask, i1 = (base_idx + hi) & E.ring_mask;
+                    atomicAdd(ring + i0, 1u);
+                    atomicAdd(ring + i1, 0xFFFFFFFFu);
+                    touch[i0 >> 5] = 1;  // plain stores of the same value: races are benign
+                    touch[i1 >> 5] = 1;
                 }
                 c += n;
             }
@@ -453,16 +458,23 @@ __global__ void __launch_bounds__(256) k_cov_scatter(EngineView E, BatchView B, 
 
 // Window flush = one pass over the ring range: single-pass prefix sum with decoupled look-back
 // (tile aggregate / inclusive-prefix flags), fused with the min(depth,100) histogram and the re-zeroing of
-// the ring.  8 bytes of HBM traffic per genome position (read + write), 16-byte vector accesses.
+// the ring.  A byte map marks the 32-entry granules that received events; untouched granules are neither
+// read nor written (their depth is the running prefix), so sparse coverage costs traffic proportional to the
+// reads, dense coverage 8 bytes per genome position.  16-byte vector accesses, streaming cache hints.
 static const uint32_t kCovThreads = 256;                // small CTAs: the look-back of one tile stalls only 8 warps
 static const uint32_t kCovTile = kCovThreads * 8;     // ring entries per tile (8 per thread)
 static const uint32_t kTileAggregate = 1u, kTileInclusive = 2u;
-__global__ void __launch_bounds__(kCovThreads) k_cov_flush(uint32_t* ring, uint32_t ring_mask, uint32_t start, uint64_t len, uint32_t* carry,
-                                                    unsigned long long* tile_state, uint32_t* ticket, unsigned long long* poscov) {
+// [start, start+len) is the range to flush (ring indices, multiples of 8); tiles are aligned to 32 entries in
+// ring index space: lead = start & 31 entries of the first granule lie before the range.
+__global__ void __launch_bounds__(kCovThreads) k_cov_flush(uint32_t* ring, uint8_t* touch, uint32_t ring_mask, uint32_t start, uint64_t len, uint32_t* carry,
+                                                           unsigned long long* tile_state, uint32_t* ticket, unsigned long long* poscov) {
     __shared__ uint32_t hist[128];
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t s_tile, s_prefix;
-    const uint64_t ntiles = (len + kCovTile - 1) / kCovTile;
+    const uint32_t lead = start & 31u;
+    const uint32_t astart = start - lead;            // aligned ring index of entry 0 of tile 0 (no wrap: start >= lead)
+    const uint64_t alen = len + lead;                // entries from astart to the end of the range
+    const uint64_t ntiles = (alen + kCovTile - 1) / kCovTile;
     if (threadIdx.x < 128) hist[threadIdx.x] = 0;
     __syncthreads();
     for (;;) {
@@ -470,17 +482,19 @@ __global__ void __launch_bounds__(kCovThreads) k_cov_flush(uint32_t* ring, uint3
         __syncthreads();
         const uint64_t tile = s_tile;
         if (tile >= ntiles) break;
-        // ring offsets are multiples of 8 entries from a 16-byte aligned base, so the two uint4 never wrap apart
-        const uint64_t i0 = tile * kCovTile + 8ull * threadIdx.x;
+        const uint64_t i0 = tile * kCovTile + 8ull * threadIdx.x;    // entry index relative to astart
+        const bool inside = i0 >= lead && i0 < alen;                   // range ends are multiples of 8: all or nothing
+        const uint32_t ridx = (astart + (uint32_t)i0) & ring_mask;
+        const uint32_t gidx = ridx >> 5;
+        const bool touched = inside && touch[gidx] != 0;
         uint32_t v[8];
-        const uint32_t ridx = (start + (uint32_t)i0) & ring_mask;
-        if (i0 + 8 <= len) {
-            uint4 a = __ldcs(reinterpret_cast<const uint4*>(ring + ridx));  // streamed once: do not keep in L2
-            uint4 b = __ldcs(reinterpret_cast<const uint4*>(ring + ((ridx + 4) & ring_mask)));
+        if (touched) {
+            uint4 a = __ldcs(reinterpret_cast<const uint4*>(ring + ridx));
+            uint4 b = __ldcs(reinterpret_cast<const uint4*>(ring + ridx + 4));
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
         } else {
 #pragma unroll
-            for (uint32_t j = 0; j < 8; ++j) v[j] = (i0 + j < len) ? ring[(ridx + j) & ring_mask] : 0u;
+            for (uint32_t j = 0; j < 8; ++j) v[j] = 0u;
         }
         uint32_t acc = 0;
 #pragma unroll
@@ -536,25 +550,25 @@ __global__ void __launch_bounds__(kCovThreads) k_cov_flush(uint32_t* ring, uint3
         }
         __syncthreads();
         uint32_t depth = s_prefix + wsum[threadIdx.x >> 5] + (incl - acc);
-        uint32_t zeros = 0;  // depth 0 dominates sparse data: counted in a register, one atomic per warp
+        if (inside) {
+            if (touched) {
+                uint32_t zeros = 0;
 #pragma unroll
-        for (uint32_t j = 0; j < 8; ++j) {
-            if (i0 + j < len) {
-                depth += v[j];
-                if (depth == 0) ++zeros;
-                else atomicAdd(hist + min(depth, 100u), 1u);
+                for (uint32_t j = 0; j < 8; ++j) {
+                    depth += v[j];
+                    if (depth == 0) ++zeros;
+                    else atomicAdd(hist + min(depth, 100u), 1u);
+                }
+                if (zeros) atomicAdd(hist, zeros);
+                __stcs(reinterpret_cast<uint4*>(ring + ridx), make_uint4(0, 0, 0, 0));
+                __stcs(reinterpret_cast<uint4*>(ring + ridx + 4), make_uint4(0, 0, 0, 0));
+            } else {
+                atomicAdd(hist + min(depth, 100u), 8u);  // no events in this granule: constant depth
             }
         }
-        zeros = __reduce_add_sync(0xFFFFFFFFu, zeros);
-        if ((threadIdx.x & 31u) == 0 && zeros) atomicAdd(hist, zeros);
-        if (i0 + 8 <= len) {
-            __stcs(reinterpret_cast<uint4*>(ring + ridx), make_uint4(0, 0, 0, 0));
-            __stcs(reinterpret_cast<uint4*>(ring + ((ridx + 4) & ring_mask)), make_uint4(0, 0, 0, 0));
-        } else {
-#pragma unroll
-            for (uint32_t j = 0; j < 8; ++j)
-                if (i0 + j < len) ring[(ridx + j) & ring_mask] = 0u;
-        }
+        // clear the map byte once the granule's last entry has been flushed (4 threads share a granule; entries
+        // of the granule that precede the range were flushed by the previous call)
+        if ((threadIdx.x & 3u) == 3u && inside && touch[gidx]) touch[gidx] = 0;
         __syncthreads();
     }
     if (threadIdx.x < 101 && hist[threadIdx.x]) atomicAdd(poscov + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
