@@ -77,6 +77,9 @@ PROTOTYPES = {
     "bqc_reset": (ctypes.c_int, [_vp]),
     "bqc_acquire_staging": (ctypes.c_int, [_vp, _P(_vp), _P(ctypes.c_size_t)]),
     "bqc_submit": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, _u64]),
+    "bqc_submit_stream": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_int]),
+    "bqc_frames_repaired": (_u64, [_vp]),
+    "bqc_records_seen": (_u64, [_vp]),
     "bqc_batch_prepare": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, _u64, _P(_vp)]),
     "bqc_batch_run": (ctypes.c_int, [_vp, _vp]),
     "bqc_batch_free": (None, [_vp, _vp]),

@@ -27,6 +27,7 @@
 
 #include "../../include/bamqc_b200.h"
 #include "kernels.cuh"
+#include "kernel_frame.cuh"
 
 using namespace bqc;
 
@@ -99,7 +100,7 @@ static void run_parallel(HostPool* pool, int n, const std::function<void(int)>& 
     for (auto& t : th) t.join();
 }
 
-struct ScanMeta { int32_t rid; uint32_t pos; };  // host_scan pass 1 -> pass 2
+typedef bqc::FrameMeta ScanMeta;  // {rid (< 0: not part of the coverage statistic), pos}: pass 1 (host or k_frame_emit) -> pass 2
 
 struct CovState {  // OverallNumbers::{first,id,shift} (src/OverallNumbers.hpp:37-41) + virtual window index
     bool first = true;
@@ -116,9 +117,12 @@ struct Segment {  // a run of records of one submission that fits the coverage r
 };
 
 struct DeviceBatch {
-    uint8_t* bytes = nullptr;
+    uint8_t* bytes = nullptr;        // allocation: kFrameHead bytes of head room, then the staged data
+    const uint8_t* base = nullptr;   // what the record offsets are relative to (bytes + kFrameHead when the host framed, bytes when the device did)
     uint32_t* offsets = nullptr;
     uint32_t* cov = nullptr;
+    const uint32_t* cov_src = nullptr;  // what k_cov_scatter reads: `cov`, or the slot's pinned host array (device-framed path: 4 bytes per
+                                         // record read once over PCIe instead of an H2D copy that would queue behind the next buffer's copy)
     uint8_t* rec_lane = nullptr;
     uint64_t n_records = 0, n_bytes = 0;
     uint32_t max_lseq = 0;
@@ -141,7 +145,14 @@ struct Slot {  // one half of the staging double buffer
     cudaEvent_t done = nullptr;
     bool in_flight = false;
     bool queued = false;           // handed to the commit thread, not yet enqueued on the GPU
-    std::vector<ScanMeta> meta;    // pass 1 -> pass 2
+    std::vector<ScanMeta> meta;    // pass 1 -> pass 2 (host framing)
+    // device framing (kernel_frame.cuh)
+    FrameResult* h_frame = nullptr;  // pinned
+    FrameResult* d_frame = nullptr;
+    ScanMeta* h_meta = nullptr;      // pinned
+    ScanMeta* d_meta = nullptr;
+    uint32_t *d_ws = nullptr, *d_we = nullptr, *d_wc = nullptr, *d_ws2 = nullptr, *d_we2 = nullptr, *d_wc2 = nullptr, *d_bsum = nullptr, *d_bbase = nullptr;
+    cudaEvent_t framed = nullptr, aux_done = nullptr;
 };
 
 struct bqc_engine {
@@ -174,6 +185,8 @@ struct bqc_engine {
     std::vector<uint32_t*> ref_bufs;
     std::vector<uint64_t> ref_len;
     cudaStream_t compute = nullptr, copy = nullptr, covs = nullptr;  // covs: coverage scatter + flush (HBM bound) overlaps the table kernels
+    cudaStream_t aux = nullptr;    // small D2H / H2D of the device-framing path (must not queue behind the next big H2D)
+    cudaStream_t frames = nullptr; // framing kernels: the H2D copy of the next buffer (copy stream) overlaps them
     cudaEvent_t cov_done = nullptr, cov_go = nullptr;
     static const int kSlots = 4;  // depth of the staging pipeline: framing / anchor pass / H2D / kernels each hold one
     Slot slots[kSlots];
@@ -187,7 +200,17 @@ struct bqc_engine {
     std::unique_ptr<HostPool> pool;
     // streaming path: the caller thread frames and pre-scans buffer i+1 while the commit thread runs the
     // sequential anchor pass, the H2D copies and the kernel launches of buffer i
-    struct Task { int slot; const uint8_t* h2d_src; size_t span; uint64_t n_records; uint32_t max_lseq; };
+    struct Task {
+        int slot; const uint8_t* h2d_src; size_t span; uint64_t n_records; uint32_t max_lseq;
+        int mode;          // 0: framed by the host (offsets + meta in the slot), 1: raw stream bytes, framed on the device
+        bool must_align;   // the bytes must end on a record boundary (whole-record submissions, last stream chunk)
+    };
+    std::deque<Task> ingest;       // stream tasks whose H2D copy + framing kernels are enqueued, not yet launched
+    int last_stream_slot = -1;     // slot of the previous stream submission (source of the carried partial record)
+    bool device_framing = true;    // BQC_HOST_FRAMING=1 turns it off (A/B tests)
+    bool trace = false;            // BQC_TRACE=1: per-buffer timings of the commit thread on stderr
+    bool force_bad_frames = false; // BQC_FRAME_FORCE_REPAIR=1: every speculation is treated as failed (tests the repair path)
+    std::vector<uint8_t> host_carry;  // partial record carried between stream submissions when the host frames
     std::thread commit_thread;
     std::mutex cm;
     std::condition_variable ccv, ccv_idle;
@@ -196,7 +219,7 @@ struct bqc_engine {
     int async_rc = 0;
     int tune_stats_bps = 0, tune_sketch_threads = 1024;  // BQC_STATS_BPS / BQC_SKETCH_THREADS (tuning knobs)
     std::vector<CovState> cov;
-    uint64_t records_seen = 0, launches = 0;
+    uint64_t records_seen = 0, launches = 0, frames_repaired = 0;
     bool finished = false;
     std::string last_error;
     bqc_error_info host_error = {0, 0, {0}};
@@ -292,13 +315,20 @@ extern "C" void bqc_destroy(bqc_engine* e) {
     if (e->compute) cudaStreamSynchronize(e->compute);
     if (e->copy) cudaStreamSynchronize(e->copy);
     if (e->covs) cudaStreamSynchronize(e->covs);
+    if (e->aux) cudaStreamSynchronize(e->aux);
+    if (e->frames) cudaStreamSynchronize(e->frames);
     for (auto& s : e->slots) {
         if (s.pinned) cudaFreeHost(s.pinned);
         if (s.h_offsets) cudaFreeHost(s.h_offsets);
         if (s.h_cov) cudaFreeHost(s.h_cov);
         if (s.h_lane) cudaFreeHost(s.h_lane);
+        if (s.h_frame) cudaFreeHost(s.h_frame);
+        if (s.h_meta) cudaFreeHost(s.h_meta);
+        cudaFree(s.d_frame); cudaFree(s.d_meta); cudaFree(s.d_ws); cudaFree(s.d_we); cudaFree(s.d_wc); cudaFree(s.d_ws2); cudaFree(s.d_we2); cudaFree(s.d_wc2); cudaFree(s.d_bsum); cudaFree(s.d_bbase);
         free_device_batch(s.dev);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.framed) cudaEventDestroy(s.framed);
+        if (s.aux_done) cudaEventDestroy(s.aux_done);
     }
     for (auto p : e->ref_bufs) cudaFree(p);
     cudaFree(e->d_counters);
@@ -316,6 +346,8 @@ extern "C" void bqc_destroy(bqc_engine* e) {
     if (e->cov_done) cudaEventDestroy(e->cov_done);
     if (e->cov_go) cudaEventDestroy(e->cov_go);
     if (e->covs) cudaStreamDestroy(e->covs);
+    if (e->aux) cudaStreamDestroy(e->aux);
+    if (e->frames) cudaStreamDestroy(e->frames);
     if (e->compute) cudaStreamDestroy(e->compute);
     if (e->copy) cudaStreamDestroy(e->copy);
     delete e;
@@ -325,8 +357,9 @@ extern "C" const char* bqc_last_error(bqc_engine* e) { return e ? e->last_error.
 
 static int alloc_device_batch(bqc_engine* e, DeviceBatch& d, uint64_t bytes_cap, uint64_t rec_cap) {
     d.owns = true;
-    CU(cudaMalloc(&d.bytes, bytes_cap + 256));
-    CU(cudaMemset(d.bytes, 0, bytes_cap + 256));
+    CU(cudaMalloc(&d.bytes, kFrameHead + bytes_cap + 256));
+    CU(cudaMemset(d.bytes, 0, kFrameHead + bytes_cap + 256));
+    d.base = d.bytes + kFrameHead;
     CU(cudaMalloc(&d.offsets, (rec_cap + 1) * sizeof(uint32_t)));
     CU(cudaMalloc(&d.cov, (rec_cap + 1) * sizeof(uint32_t)));
     if (e->n_lanes > 1) CU(cudaMalloc(&d.rec_lane, rec_cap + 1));
@@ -341,6 +374,10 @@ extern "C" int bqc_reset(bqc_engine* e) {
     CU(cudaStreamSynchronize(e->compute));
     CU(cudaStreamSynchronize(e->copy));
     CU(cudaStreamSynchronize(e->covs));
+    CU(cudaStreamSynchronize(e->aux));
+    CU(cudaStreamSynchronize(e->frames));
+    e->last_stream_slot = -1;
+    e->host_carry.clear();
     CU(cudaMemsetAsync(e->d_counters, 0, e->n_lanes * e->L.lane_stride * 8, e->compute));
     CU(cudaMemsetAsync(e->d_sketch, 0, e->n_lanes * e->n_qk * e->sketch_words_per_qk * 4, e->compute));
     CU(cudaMemsetAsync(e->d_ring, 0, (uint64_t)e->n_lanes * (1ull << e->ring_log2) * 4, e->compute));
@@ -399,6 +436,9 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     e->max_records_per_slot = e->staging_bytes / 40 + 16;  // a record is at least 36 bytes
     e->ring_log2 = cfg->cov_ring_log2 ? cfg->cov_ring_log2 : 28;
     if (const char* v = getenv("BQC_STATS_BPS")) e->tune_stats_bps = atoi(v);
+    if (const char* v = getenv("BQC_HOST_FRAMING")) e->device_framing = atoi(v) == 0;
+    if (const char* v = getenv("BQC_TRACE")) e->trace = atoi(v) != 0;
+    if (const char* v = getenv("BQC_FRAME_FORCE_REPAIR")) e->force_bad_frames = atoi(v) != 0;
     if (const char* v = getenv("BQC_SKETCH_THREADS")) e->tune_sketch_threads = std::max(32, std::min(1024, atoi(v) & ~31));
     e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     if (e->host_threads > 1) e->pool.reset(new HostPool(e->host_threads - 1));
@@ -412,6 +452,8 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         CU(cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&e->covs, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&e->frames, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&e->cov_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&e->cov_go, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&e->copied, cudaEventDisableTiming));
@@ -439,7 +481,11 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
             CU(cudaMalloc(&e->d_hash, sizeof(HashTables) * cfg->n_k));
             CU(cudaMemcpy(e->d_hash, ht.data(), sizeof(HashTables) * cfg->n_k, cudaMemcpyHostToDevice));
         }
-        for (auto& s : e->slots) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        for (auto& s : e->slots) {
+            CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s.framed, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s.aux_done, cudaEventDisableTiming));
+        }
         // opt in to large dynamic shared memory
         CU(cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(k_eightmer, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
@@ -684,7 +730,8 @@ static void host_scan_pass2(bqc_engine* e, const ScanMeta* meta, uint64_t n_reco
     const uint64_t* base_window = segs.back().base_window.data();
     uint64_t seg_r0 = segs.back().r0;
     if (!lane_out) {
-        // single read group: the anchor state lives in registers
+        // single read group: the anchor state lives in registers.  (A branch-free form of this loop was measured
+        // slower: the predicted branches break the dependency chain through `shift`.)
         CovState& st = e->cov[0];
         bool first = st.first;
         int32_t id = st.id;
@@ -835,40 +882,49 @@ static EngineView make_view(bqc_engine* e) {
     return E;
 }
 
-static int run_device_batch(bqc_engine* e, const DeviceBatch& d) {
-    EngineView E = make_view(e);
+struct BatchLaunch {  // launch geometry shared by the coverage and the table kernels of one batch
+    EngineView E;
+    uint32_t cycb;
+    size_t stats_smem;
+    int bps;
+};
+static int batch_launch_setup(bqc_engine* e, const DeviceBatch& d, BatchLaunch& BL) {
+    BL.E = make_view(e);
     uint32_t cycb = pad8(std::max<uint32_t>(d.max_lseq, 8u));
     if (cycb > e->L.cyc) cycb = e->L.cyc;  // longer reads are reported as unsupported by the kernel
-    StatsSmem S = stats_smem_layout(cycb, E.insert_smem);
-    size_t stats_smem = (size_t)S.total * 4;
+    BL.cycb = cycb;
+    StatsSmem S = stats_smem_layout(cycb, BL.E.insert_smem);
+    BL.stats_smem = (size_t)S.total * 4;
     int bps = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats, (int)kStatsThreads, stats_smem));
-    if (bps < 1) { set_error(e, "k_stats does not fit: %zu bytes of shared memory", stats_smem); return BQC_ERR_ARG; }
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats, (int)kStatsThreads, BL.stats_smem));
+    if (bps < 1) { set_error(e, "k_stats does not fit: %zu bytes of shared memory", BL.stats_smem); return BQC_ERR_ARG; }
     if (e->tune_stats_bps > 0 && e->tune_stats_bps < bps) bps = e->tune_stats_bps;
+    BL.bps = bps;
     e->stats_blocks_per_sm = bps;
+    return 0;
+}
+
+// The coverage work (scatter + window flush) is HBM bound, the table kernels are issue bound: it runs on its own
+// stream so that the two overlap.  The caller has made e->covs wait for the batch's data.
+static int launch_cov(bqc_engine* e, const DeviceBatch& d, const BatchLaunch& BL) {
     const uint64_t ring_size = 1ull << e->ring_log2;
-    const uint64_t n = d.n_records;
-    // The coverage work (scatter + window flush) is HBM bound, the table kernels are issue bound: it runs on
-    // its own stream, launched first, so that the two overlap.
-    CU(cudaEventRecord(e->cov_go, e->compute));
-    CU(cudaStreamWaitEvent(e->covs, e->cov_go, 0));
     // the coverage ring is fed and drained segment by segment (a segment is what fits the ring)
     for (const Segment& sg : d.segs) {
         uint64_t ns = sg.r1 - sg.r0;
         for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
             if (ns) {
                 BatchView B;
-                B.bytes = d.bytes;
+                B.bytes = d.base;
                 B.offsets = d.offsets + sg.r0;
-                B.cov = d.cov + sg.r0;
+                B.cov = (d.cov_src ? d.cov_src : d.cov) + sg.r0;
                 B.rec_lane = d.rec_lane ? d.rec_lane + sg.r0 : nullptr;
                 B.n_records = (uint32_t)ns;
-                B.cycb = cycb;
+                B.cycb = BL.cycb;
                 B.first_record = d.first_record + sg.r0;
                 B.ring_base = (uint32_t)((sg.base_window[lane] * 1000) & (ring_size - 1));
                 int grid = (int)std::min<uint64_t>((ns + 255) / 256, (uint64_t)e->n_sm * 8);
                 ProfScope prof(e, 3, e->covs);
-                k_cov_scatter<<<grid, 256, 0, e->covs>>>(E, B, lane);
+                k_cov_scatter<<<grid, 256, 0, e->covs>>>(BL.E, B, lane);
                 e->launches += 1;
             }
             uint64_t from = sg.base_window[lane] * 1000;
@@ -877,19 +933,26 @@ static int run_device_batch(bqc_engine* e, const DeviceBatch& d) {
         }
     }
     CU(cudaEventRecord(e->cov_done, e->covs));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int launch_tables(bqc_engine* e, const DeviceBatch& d, const BatchLaunch& BL) {
+    const uint64_t n = d.n_records;
+    const EngineView& E = BL.E;
     for (uint32_t lane = 0; lane < e->n_lanes && n; ++lane) {
         // the table kernels see the whole batch once
         BatchView B;
-        B.bytes = d.bytes;
+        B.bytes = d.base;
         B.offsets = d.offsets;
         B.cov = d.cov;
         B.rec_lane = d.rec_lane;
         B.n_records = (uint32_t)n;
-        B.cycb = cycb;
+        B.cycb = BL.cycb;
         B.first_record = d.first_record;
         B.ring_base = 0;
-        int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * bps);
-        { ProfScope prof(e, 0); k_stats<<<grid, kStatsThreads, stats_smem, e->compute>>>(E, B, lane); }
+        int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * BL.bps);
+        { ProfScope prof(e, 0); k_stats<<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane); }
         int g8 = (int)std::min<uint64_t>(2 * ((n + kEightThreads - 1) / kEightThreads), (uint64_t)(e->n_sm & ~1));
         if (g8 < 2) g8 = 2;
         { ProfScope prof(e, 1); k_eightmer<<<g8, kEightThreads, 32768 * 4, e->compute>>>(E, B, lane); }
@@ -911,8 +974,22 @@ static int run_device_batch(bqc_engine* e, const DeviceBatch& d) {
                 e->launches += 1;
             }
     }
-    CU(cudaStreamWaitEvent(e->compute, e->cov_done, 0));
     CU(cudaGetLastError());
+    return 0;
+}
+
+// coverage first (its own stream, released once the compute stream has reached this batch), then the tables
+static int run_device_batch(bqc_engine* e, const DeviceBatch& d) {
+    BatchLaunch BL;
+    int rc = batch_launch_setup(e, d, BL);
+    if (rc) return rc;
+    CU(cudaEventRecord(e->cov_go, e->compute));
+    CU(cudaStreamWaitEvent(e->covs, e->cov_go, 0));
+    rc = launch_cov(e, d, BL);
+    if (rc) return rc;
+    rc = launch_tables(e, d, BL);
+    if (rc) return rc;
+    CU(cudaStreamWaitEvent(e->compute, e->cov_done, 0));
     return 0;
 }
 
@@ -922,13 +999,30 @@ static int run_device_batch(bqc_engine* e, const DeviceBatch& d) {
 static int ensure_slot(bqc_engine* e, Slot& s) {
     if (s.pinned) return 0;
     CU(cudaSetDevice(e->cfg.device));
-    CU(cudaHostAlloc((void**)&s.pinned, e->staging_bytes + 256, cudaHostAllocDefault));
-    CU(cudaHostAlloc((void**)&s.h_offsets, (e->max_records_per_slot + 1) * 4, cudaHostAllocDefault));
-    CU(cudaHostAlloc((void**)&s.h_cov, (e->max_records_per_slot + 1) * 4, cudaHostAllocDefault));
-    if (e->n_lanes > 1) CU(cudaHostAlloc((void**)&s.h_lane, e->max_records_per_slot + 1, cudaHostAllocDefault));
-    return alloc_device_batch(e, s.dev, e->staging_bytes, e->max_records_per_slot);
+    const uint64_t rc_ = e->max_records_per_slot;
+    // kFrameHead bytes of head room in front of the staging area: a carried partial record goes there
+    CU(cudaHostAlloc((void**)&s.pinned, kFrameHead + e->staging_bytes + 256, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&s.h_offsets, (rc_ + 1) * 4, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&s.h_cov, (rc_ + 1) * 4, cudaHostAllocDefault));
+    if (e->n_lanes > 1) CU(cudaHostAlloc((void**)&s.h_lane, rc_ + 1, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&s.h_frame, sizeof(FrameResult), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&s.h_meta, (rc_ + 1) * sizeof(ScanMeta), cudaHostAllocDefault));
+    const uint64_t nwin = (kFrameHead + e->staging_bytes + kFrameWindow - 1) / kFrameWindow + 1;
+    const uint64_t nblk = (nwin + kFrameThreads - 1) / kFrameThreads;
+    CU(cudaMalloc(&s.d_frame, sizeof(FrameResult)));
+    CU(cudaMalloc(&s.d_meta, (rc_ + 1) * sizeof(ScanMeta)));
+    CU(cudaMalloc(&s.d_ws, nwin * 4));
+    CU(cudaMalloc(&s.d_we, nwin * 4));
+    CU(cudaMalloc(&s.d_wc, nwin * 4));
+    CU(cudaMalloc(&s.d_ws2, nwin * 4));
+    CU(cudaMalloc(&s.d_we2, nwin * 4));
+    CU(cudaMalloc(&s.d_wc2, nwin * 4));
+    CU(cudaMalloc(&s.d_bsum, nblk * 4));
+    CU(cudaMalloc(&s.d_bbase, nblk * 4));
+    return alloc_device_batch(e, s.dev, e->staging_bytes, rc_);
 }
 
+// host-framed task: anchor pass, copies and launches
 static int commit_task(bqc_engine* e, const bqc_engine::Task& t) {
     Slot& s = e->slots[t.slot];
     DeviceBatch& d = s.dev;
@@ -938,7 +1032,9 @@ static int commit_task(bqc_engine* e, const bqc_engine::Task& t) {
     d.n_records = n_records;
     d.n_bytes = t.span;
     d.first_record = e->records_seen;
-    CU(cudaMemcpyAsync(d.bytes, t.h2d_src, t.span, cudaMemcpyHostToDevice, e->copy));
+    d.base = d.bytes + kFrameHead;
+    d.cov_src = nullptr;
+    CU(cudaMemcpyAsync(d.bytes + kFrameHead, t.h2d_src, t.span, cudaMemcpyHostToDevice, e->copy));
     CU(cudaMemcpyAsync(d.offsets, s.h_offsets, (n_records + 1) * 4, cudaMemcpyHostToDevice, e->copy));
     CU(cudaMemcpyAsync(d.cov, s.h_cov, n_records * 4, cudaMemcpyHostToDevice, e->copy));
     if (e->n_lanes > 1) CU(cudaMemcpyAsync(d.rec_lane, s.h_lane, n_records, cudaMemcpyHostToDevice, e->copy));
@@ -951,23 +1047,138 @@ static int commit_task(bqc_engine* e, const bqc_engine::Task& t) {
     return 0;
 }
 
+// stream task, stage A: carry the partial record of the previous buffer, copy the new bytes, frame on the device
+static int stream_stage_a(bqc_engine* e, const bqc_engine::Task& t) {
+    Slot& s = e->slots[t.slot];
+    DeviceBatch& d = s.dev;
+    const Slot* prev = e->last_stream_slot >= 0 ? &e->slots[e->last_stream_slot] : nullptr;
+    k_frame_tail<<<1, 256, 0, e->frames>>>(prev ? prev->dev.bytes : nullptr, prev ? prev->d_frame : nullptr, d.bytes, s.d_frame, (uint32_t)t.span);
+    CU(cudaMemcpyAsync(d.bytes + kFrameHead, t.h2d_src, t.span, cudaMemcpyHostToDevice, e->copy));
+    CU(cudaEventRecord(e->copied, e->copy));
+    CU(cudaStreamWaitEvent(e->frames, e->copied, 0));
+    const uint32_t nwin = (uint32_t)((kFrameHead + t.span + kFrameWindow - 1) / kFrameWindow);
+    const uint32_t nblk = (nwin + kFrameThreads - 1) / kFrameThreads;
+    const uint32_t rec_cap = (uint32_t)e->max_records_per_slot;
+    k_frame_speculate<<<nblk, kFrameThreads, 0, e->frames>>>(d.bytes, s.d_frame, std::max(1, e->cfg.n_ref), nwin, s.d_ws, s.d_we, s.d_wc);
+    for (int round = 0; round < 2; ++round) {  // two Jacobi rounds each way: the final state is back in d_ws/d_we/d_wc
+        k_frame_relax<<<nblk, kFrameThreads, 0, e->frames>>>(d.bytes, s.d_frame, nwin, s.d_ws, s.d_we, s.d_wc, s.d_ws2, s.d_we2, s.d_wc2);
+        k_frame_relax<<<nblk, kFrameThreads, 0, e->frames>>>(d.bytes, s.d_frame, nwin, s.d_ws2, s.d_we2, s.d_wc2, s.d_ws, s.d_we, s.d_wc);
+    }
+    k_frame_blocksum<<<nblk, kFrameThreads, 0, e->frames>>>(nwin, s.d_wc, s.d_bsum);
+    k_frame_verify<<<1, 1024, 0, e->frames>>>(s.d_frame, nwin, nblk, s.d_ws, s.d_we, s.d_bsum, s.d_bbase, d.offsets, rec_cap, e->force_bad_frames ? 1u : 0u);
+    k_frame_repair<<<1, 32, 0, e->frames>>>(d.bytes, s.d_frame, e->cfg.n_ref, e->d_main_chrom, d.offsets, s.d_meta, rec_cap);
+    k_frame_emit<<<nblk, kFrameThreads, 0, e->frames>>>(d.bytes, s.d_frame, e->cfg.n_ref, e->d_main_chrom, nwin, s.d_ws, s.d_wc, s.d_bbase, d.offsets, s.d_meta);
+    e->launches += 10;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s.h_frame, s.d_frame, sizeof(FrameResult), cudaMemcpyDeviceToHost, e->frames));
+    CU(cudaEventRecord(s.framed, e->frames));
+    e->last_stream_slot = t.slot;
+    return 0;
+}
+
+// stage B: read the frame header back, launch the table kernels, run the anchor pass on the (rid, pos) pairs of
+// the buffer and launch the coverage kernels
+static int stream_stage_b(bqc_engine* e, const bqc_engine::Task& t) {
+    Slot& s = e->slots[t.slot];
+    DeviceBatch& d = s.dev;
+    auto t_b0 = std::chrono::steady_clock::now();
+    CU(cudaEventSynchronize(s.framed));
+    auto t_b1 = std::chrono::steady_clock::now();
+    const FrameResult fr = *s.h_frame;
+    if (fr.tail_overflow) {
+        e->host_error.code = fr.tail_overflow == 2 ? BQC_ERR_ARG : BQC_ERR_BAD_RECORD;
+        e->host_error.record = e->records_seen + fr.n_records;
+        snprintf(e->host_error.message, sizeof(e->host_error.message), "%s", fr.tail_overflow == 2 ? "too many records for one staging buffer" : "ERROR: Could not read record from BAM File (record chain broken or record larger than 1 MiB)");
+        set_error(e, "%s", e->host_error.message);
+        return e->host_error.code;
+    }
+    if (t.must_align && fr.end != fr.total) {
+        e->host_error.code = BQC_ERR_BAD_RECORD;
+        e->host_error.record = e->records_seen + fr.n_records;
+        snprintf(e->host_error.message, sizeof(e->host_error.message), "bqc_submit: bytes do not end on a record boundary");
+        set_error(e, "%s", e->host_error.message);
+        return BQC_ERR_BAD_RECORD;
+    }
+    if (fr.repaired) e->frames_repaired += 1;
+    const uint64_t n = fr.n_records;
+    d.max_lseq = fr.max_lseq;
+    d.n_records = n;
+    d.n_bytes = fr.end - fr.start;
+    d.first_record = e->records_seen;
+    d.base = d.bytes;
+    e->records_seen += n;
+    if (n) {
+        // the (rid, pos) pairs come back on the aux stream while the table kernels are being launched
+        CU(cudaStreamWaitEvent(e->aux, s.framed, 0));
+        CU(cudaMemcpyAsync(s.h_meta, s.d_meta, n * sizeof(ScanMeta), cudaMemcpyDeviceToHost, e->aux));
+        CU(cudaEventRecord(s.aux_done, e->aux));
+        BatchLaunch BL;
+        int rc = batch_launch_setup(e, d, BL);
+        if (rc) return rc;
+        CU(cudaStreamWaitEvent(e->compute, s.framed, 0));
+        CU(cudaEventRecord(e->cov_go, e->compute));  // coverage of this batch does not overtake the previous batch's tables
+        rc = launch_tables(e, d, BL);
+        if (rc) return rc;
+        auto t_b2 = std::chrono::steady_clock::now();
+        CU(cudaEventSynchronize(s.aux_done));
+        auto t_b3 = std::chrono::steady_clock::now();
+        host_scan_pass2(e, s.h_meta, n, s.h_cov, nullptr, d.segs);
+        if (e->trace) {
+            auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "[bqc trace] slot %d: repaired %u, wait framed %.2f ms, launch tables %.2f ms, wait meta %.2f ms, pass2 %.2f ms, n=%llu segs=%zu\n", t.slot, fr.repaired, ms(t_b0, t_b1), ms(t_b1, t_b2), ms(t_b2, t_b3),
+                    ms(t_b3, std::chrono::steady_clock::now()), (unsigned long long)n, d.segs.size());
+        }
+        d.cov_src = s.h_cov;
+        CU(cudaStreamWaitEvent(e->covs, e->cov_go, 0));
+        rc = launch_cov(e, d, BL);
+        if (rc) return rc;
+        CU(cudaStreamWaitEvent(e->compute, e->cov_done, 0));
+    }
+    CU(cudaEventRecord(s.done, e->compute));
+    return 0;
+}
+
 static void commit_loop(bqc_engine* e) {
     cudaSetDevice(e->cfg.device);
     for (;;) {
         bqc_engine::Task t;
+        bool have_new = false, have_old = false;
         {
             std::unique_lock<std::mutex> g(e->cm);
-            e->ccv.wait(g, [&] { return e->cstop || !e->cq.empty(); });
-            if (e->cq.empty()) return;  // stop requested and nothing left
-            t = e->cq.front();
-            e->cq.pop_front();
+            e->ccv.wait(g, [&] { return e->cstop || !e->cq.empty() || !e->ingest.empty(); });
+            if (e->cq.empty() && e->ingest.empty()) return;  // stop requested and nothing left
+            // keep up to two stream buffers in the copy + framing stage so that the H2D copy of the next buffer
+            // overlaps the anchor pass and the launches of this one
+            // (tasks complete in submission order: a host-framed task waits for the stream tasks before it)
+            const bool take_new = !e->cq.empty() && (e->cq.front().mode == 1 ? e->ingest.size() < 2 : e->ingest.empty());
+            if (take_new) {
+                t = e->cq.front();
+                e->cq.pop_front();
+                have_new = true;
+            } else {
+                t = e->ingest.front();
+                e->ingest.pop_front();
+                have_old = true;
+            }
             e->cbusy = true;
         }
-        int rc = e->async_rc ? e->async_rc : commit_task(e, t);
+        int rc = e->async_rc;
+        bool finished_slot = false;
+        if (have_new) {
+            if (t.mode == 0) { if (!rc) rc = commit_task(e, t); finished_slot = true; }
+            else if (!rc) { rc = stream_stage_a(e, t); if (rc) finished_slot = true; }
+            else finished_slot = true;
+        } else if (have_old) {
+            if (!rc) rc = stream_stage_b(e, t);
+            finished_slot = true;
+        }
         {
             std::lock_guard<std::mutex> g(e->cm);
-            e->slots[t.slot].queued = false;
-            e->slots[t.slot].in_flight = rc == 0;
+            if (have_new && t.mode == 1 && !finished_slot) e->ingest.push_back(t);
+            if (finished_slot) {
+                e->slots[t.slot].queued = false;
+                e->slots[t.slot].in_flight = rc == 0;
+            }
             e->cbusy = false;
             if (rc && !e->async_rc) e->async_rc = rc;
         }
@@ -978,7 +1189,7 @@ static void commit_loop(bqc_engine* e) {
 // wait until the commit thread has enqueued everything handed to it; returns its sticky error
 static int drain_commits(bqc_engine* e) {
     std::unique_lock<std::mutex> g(e->cm);
-    e->ccv_idle.wait(g, [&] { return e->cq.empty() && !e->cbusy; });
+    e->ccv_idle.wait(g, [&] { return e->cq.empty() && e->ingest.empty() && !e->cbusy; });
     return e->async_rc;
 }
 
@@ -1000,22 +1211,35 @@ extern "C" int bqc_acquire_staging(bqc_engine* e, void** pinned, size_t* capacit
     if (rc) return rc;
     rc = wait_slot(e, s);
     if (rc) return rc;
-    *pinned = s.pinned;
+    *pinned = s.pinned + kFrameHead;
     *capacity = e->staging_bytes;
     return 0;
 }
 
-extern "C" int bqc_submit(bqc_engine* e, const void* data, size_t n_bytes, const uint64_t* record_offsets, uint64_t n_records) {
-    if (e->finished) { set_error(e, "bqc_submit after bqc_finish (call bqc_reset)"); return BQC_ERR_ARG; }
-    if (n_bytes > e->staging_bytes) { set_error(e, "bqc_submit: %zu bytes exceed the staging capacity %llu", n_bytes, (unsigned long long)e->staging_bytes); return BQC_ERR_ARG; }
-    if (e->async_rc) return e->async_rc;
-    CU(cudaSetDevice(e->cfg.device));
-    Slot& s = e->slots[e->next_slot];
-    int rc = ensure_slot(e, s);
-    if (rc) return rc;
-    rc = wait_slot(e, s);
-    if (rc) return rc;
-    const uint8_t* src = (const uint8_t*)data;
+// where the H2D copy of a submission reads from: the caller's page-locked memory directly (it stays unchanged
+// until bqc_sync), pageable memory is staged through the slot's pinned buffer before returning
+static const uint8_t* h2d_source(bqc_engine* e, Slot& s, const uint8_t* first, size_t span) {
+    if (first >= s.pinned && first + span <= s.pinned + kFrameHead + e->staging_bytes + 256) return first;
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, first) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) return first;
+    memcpy(s.pinned + kFrameHead, first, span);
+    return s.pinned + kFrameHead;
+}
+
+static void enqueue_task(bqc_engine* e, Slot& s, const bqc_engine::Task& t) {
+    {
+        std::lock_guard<std::mutex> g(e->cm);
+        if (!e->commit_thread.joinable()) e->commit_thread = std::thread(commit_loop, e);
+        s.queued = true;
+        e->cq.push_back(t);
+    }
+    e->ccv.notify_all();
+    e->next_slot = (e->next_slot + 1) % bqc_engine::kSlots;
+}
+
+static int submit_host_framed(bqc_engine* e, Slot& s, const uint8_t* src, size_t n_bytes, const uint64_t* record_offsets, uint64_t n_records) {
     std::vector<uint64_t>& own_offsets = e->frame_offsets;
     if (!record_offsets) {
         if (own_offsets.size() < n_bytes / 36 + 2) own_offsets.resize(n_bytes / 36 + 2);
@@ -1037,31 +1261,75 @@ extern "C" int bqc_submit(bqc_engine* e, const void* data, size_t n_bytes, const
     bqc_engine::Task t;
     t.slot = e->next_slot;
     t.n_records = n_records;
+    t.mode = 0;
+    t.must_align = true;
     host_scan_pass1(e, src, record_offsets, n_records, s.h_offsets, e->n_lanes > 1 ? s.h_lane : nullptr, s.meta.data(), t.max_lseq);
     const uint8_t* first = src + record_offsets[0];
     t.span = (size_t)(record_offsets[n_records] - record_offsets[0]);
-    t.h2d_src = first;
-    if (first < s.pinned || first + t.span > s.pinned + e->staging_bytes + 256) {
-        // not our staging buffer: page-locked memory of the caller is copied from directly (the caller keeps it
-        // unchanged until bqc_sync), pageable memory is staged through the pinned buffer before returning
-        cudaPointerAttributes attr;
-        bool pinned = cudaPointerGetAttributes(&attr, first) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-        cudaGetLastError();
-        if (!pinned) {
-            memcpy(s.pinned, first, t.span);
-            t.h2d_src = s.pinned;
-        }
-    }
-    {
-        std::lock_guard<std::mutex> g(e->cm);
-        if (!e->commit_thread.joinable()) e->commit_thread = std::thread(commit_loop, e);
-        s.queued = true;
-        e->cq.push_back(t);
-    }
-    e->ccv.notify_all();
-    e->next_slot = (e->next_slot + 1) % bqc_engine::kSlots;
+    t.h2d_src = h2d_source(e, s, first, t.span);
+    enqueue_task(e, s, t);
     return 0;
 }
+
+static int submit_common(bqc_engine* e, const void* data, size_t n_bytes, const uint64_t* record_offsets, uint64_t n_records, bool stream, bool last) {
+    if (e->finished) { set_error(e, "bqc_submit after bqc_finish (call bqc_reset)"); return BQC_ERR_ARG; }
+    if (n_bytes > e->staging_bytes) { set_error(e, "bqc_submit: %zu bytes exceed the staging capacity %llu", n_bytes, (unsigned long long)e->staging_bytes); return BQC_ERR_ARG; }
+    if (e->async_rc) return e->async_rc;
+    CU(cudaSetDevice(e->cfg.device));
+    Slot& s = e->slots[e->next_slot];
+    int rc = ensure_slot(e, s);
+    if (rc) return rc;
+    rc = wait_slot(e, s);
+    if (rc) return rc;
+    const uint8_t* src = (const uint8_t*)data;
+    const bool on_device = !record_offsets && e->device_framing && e->n_lanes == 1;
+    if (on_device) {
+        if (n_bytes == 0 && !(stream && last)) return 0;
+        bqc_engine::Task t;
+        t.slot = e->next_slot;
+        t.n_records = 0;
+        t.max_lseq = 0;
+        t.mode = 1;
+        t.must_align = !stream || last;
+        t.span = n_bytes;
+        t.h2d_src = n_bytes ? h2d_source(e, s, src, n_bytes) : s.pinned + kFrameHead;
+        enqueue_task(e, s, t);
+        return 0;
+    }
+    if (!stream) return submit_host_framed(e, s, src, n_bytes, record_offsets, n_records);
+    // stream bytes framed by the host (several read groups, or BQC_HOST_FRAMING=1): the partial record at the end
+    // of a chunk is kept on the host and put in front of the next chunk inside the pinned buffer's head room
+    const size_t carry = e->host_carry.size();
+    uint8_t* buf = s.pinned + kFrameHead - carry;
+    if (src != s.pinned + kFrameHead) memmove(s.pinned + kFrameHead, src, n_bytes);
+    if (carry) memcpy(buf, e->host_carry.data(), carry);
+    const size_t filled = carry + n_bytes;
+    std::vector<uint64_t>& offs = e->frame_offsets;
+    if (offs.size() < filled / 36 + 2) offs.resize(filled / 36 + 2);
+    n_records = frame_records_mt(buf, filled, offs.data(), offs.size(), e->host_threads, std::max(1, e->cfg.n_ref), e->pool.get());
+    const size_t whole = (size_t)offs[n_records];
+    if (filled - whole > kFrameHead || (last && whole != filled)) {
+        e->host_error.code = BQC_ERR_BAD_RECORD;
+        e->host_error.record = e->records_seen + n_records;
+        snprintf(e->host_error.message, sizeof(e->host_error.message), "ERROR: Could not read record from BAM File (record chain broken or record larger than 1 MiB)");
+        set_error(e, "%s", e->host_error.message);
+        return BQC_ERR_BAD_RECORD;
+    }
+    e->host_carry.assign(buf + whole, buf + filled);
+    if (n_records == 0) return 0;
+    return submit_host_framed(e, s, buf, whole, offs.data(), n_records);
+}
+
+extern "C" int bqc_submit(bqc_engine* e, const void* data, size_t n_bytes, const uint64_t* record_offsets, uint64_t n_records) {
+    return submit_common(e, data, n_bytes, record_offsets, n_records, false, false);
+}
+
+extern "C" int bqc_submit_stream(bqc_engine* e, const void* data, size_t n_bytes, int last) {
+    return submit_common(e, data, n_bytes, nullptr, 0, true, last != 0);
+}
+
+extern "C" uint64_t bqc_frames_repaired(bqc_engine* e) { drain_commits(e); return e->frames_repaired; }
+extern "C" uint64_t bqc_records_seen(bqc_engine* e) { drain_commits(e); return e->records_seen; }
 
 // ------------------------------------------------------------------------------------------------
 // resident path
@@ -1093,7 +1361,7 @@ extern "C" int bqc_batch_prepare(bqc_engine* e, const void* data, size_t n_bytes
     d.cov_after = e->cov;
     d.records_after = e->records_seen;
     if (n_records) {
-        CU(cudaMemcpy(d.bytes, src + record_offsets[0], span, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.bytes + kFrameHead, src + record_offsets[0], span, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.offsets, o32.data(), (n_records + 1) * 4, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.cov, cov.data(), n_records * 4, cudaMemcpyHostToDevice));
         if (e->n_lanes > 1) CU(cudaMemcpy(d.rec_lane, lanes.data(), n_records, cudaMemcpyHostToDevice));

@@ -582,40 +582,31 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
         }
     auto t_setup = std::chrono::steady_clock::now();
 
-    // ---- stream the records through the pinned staging buffers --------------------------------------
+    // ---- stream the inflated bytes through the pinned staging buffers; the engine frames the records --------
     int rc = 0;
-    uint64_t n_records_total = 0;
-    std::vector<uint8_t> carry;  // partial record at the end of the previous buffer
-    std::vector<uint64_t> offs;
-    auto submit_buffer = [&](uint8_t* buf, size_t filled, bool last) -> int {
-        offs.resize(filled / 36 + 2);
-        uint64_t n = bqc_frame_records_mt(buf, filled, offs.data(), offs.size(), c.threads, hdr.n_ref);
-        size_t whole = (size_t)offs[n];
-        if (last && whole != filled) {
-            std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
-            return 1;
-        }
-        carry.assign(buf + whole, buf + filled);
-        n_records_total += n;
-        if (n && bqc_submit(eng, buf, whole, offs.data(), n)) {
-            std::cerr << "ERROR: " << bqc_last_error(eng) << std::endl;
+    auto submit_chunk = [&](uint8_t* buf, size_t filled, bool last) -> int {
+        if (bqc_submit_stream(eng, buf, filled, last ? 1 : 0)) {
+            bqc_error_info ei;
+            bqc_get_error(eng, &ei);
+            if (ei.code == BQC_ERR_BAD_RECORD) std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
+            else std::cerr << "ERROR: " << bqc_last_error(eng) << std::endl;
             return 1;
         }
         return 0;
     };
     if (raw) {
         size_t p = hdr_bytes;
-        while (p < file.size() && !rc) {
+        bool first = true;
+        while ((p < file.size() || first) && !rc) {
+            first = false;
             void* pin;
             size_t cap;
             if (bqc_acquire_staging(eng, &pin, &cap)) { rc = 1; break; }
             uint8_t* buf = (uint8_t*)pin;
-            memcpy(buf, carry.data(), carry.size());
-            size_t take = std::min(cap - carry.size(), file.size() - p);
-            memcpy(buf + carry.size(), file.data() + p, take);
-            size_t filled = carry.size() + take;
+            size_t take = std::min(cap, file.size() - p);
+            memcpy(buf, file.data() + p, take);
             p += take;
-            rc = submit_buffer(buf, filled, p >= file.size());
+            rc = submit_chunk(buf, take, p >= file.size());
         }
     } else {
         // the tail of the header prefix that already holds records
@@ -632,9 +623,6 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
                 memcpy(buf, pending.data(), pending.size());
                 filled = pending.size();
                 first = false;
-            } else {
-                memcpy(buf, carry.data(), carry.size());
-                filled = carry.size();
             }
             std::vector<BgzfBlock> part;
             uint64_t o = filled;
@@ -649,7 +637,7 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
                 rc = 1;
                 break;
             }
-            rc = submit_buffer(buf, (size_t)o, bi >= blocks.size());
+            rc = submit_chunk(buf, (size_t)o, bi >= blocks.size());
         }
     }
     if (!rc) {
@@ -658,6 +646,7 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
             bqc_error_info ei;
             bqc_get_error(eng, &ei);
             if (ei.code == BQC_ERR_RG_NOT_Z) std::cout << "Read does not have Z" << "\n";
+            else if (ei.code == BQC_ERR_BAD_RECORD) std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
             else if (ei.code == BQC_ERR_NO_MATE_FLAG) std::cerr << "ERROR: No first or second flag in read in:  " << c.bam << "\n";
             else std::cerr << (ei.code ? ei.message : bqc_last_error(eng)) << std::endl;
             rc = 1;
@@ -671,7 +660,7 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
     auto t_end = std::chrono::steady_clock::now();
     if (c.timing) {
         auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
-        fprintf(stderr, "BAMQC_TIMING records=%llu setup_s=%.4f stats_s=%.4f write_s=%.4f total_s=%.4f threads=%d\n", (unsigned long long)n_records_total, sec(t_start, t_setup), sec(t_setup, t_stats), sec(t_stats, t_end), sec(t_start, t_end), c.threads);
+        fprintf(stderr, "BAMQC_TIMING records=%llu setup_s=%.4f stats_s=%.4f write_s=%.4f total_s=%.4f threads=%d\n", (unsigned long long)bqc_records_seen(eng), sec(t_start, t_setup), sec(t_setup, t_stats), sec(t_stats, t_end), sec(t_start, t_end), c.threads);
     }
     if (fa) bqc_fasta_close(fa);
     bqc_destroy(eng);

@@ -123,6 +123,20 @@ class Engine:
             o = np.ascontiguousarray(offsets, dtype=np.uint64)
             self._check(self.lib.bqc_submit(self.handle, a.ctypes.data, n, o.ctypes.data, o.size - 1))
 
+    def submit_stream(self, data, last=False, n_bytes=None):
+        """Next chunk of the inflated record stream (need not end on a record boundary)."""
+        a = _as_u8(data)
+        n = a.size if n_bytes is None else n_bytes
+        self._check(self.lib.bqc_submit_stream(self.handle, a.ctypes.data if n else None, n, 1 if last else 0))
+
+    @property
+    def frames_repaired(self):
+        return int(self.lib.bqc_frames_repaired(self.handle))
+
+    @property
+    def records_seen(self):
+        return int(self.lib.bqc_records_seen(self.handle))
+
     def prepare(self, data, offsets=None):
         a = _as_u8(data)
         h = ctypes.c_void_p()

@@ -325,8 +325,10 @@ def run_b200(args):
     pinned.numpy()[:n_bytes + 64] = records[:n_bytes + 64]
     pin_np = pinned.numpy()
     e2e_bounds = split_batches(offsets, (args.staging_mb << 20) - 4096)
-    h2d = n_bytes + (n_rec + len(e2e_bounds)) * 4 + n_rec * 4
-    d2h = eng.counters_len() * 8 + eng.sketch_len() // 2
+    # records H2D; the coverage codes (4 B/record) are read by the scatter kernel straight from pinned host memory;
+    # back come the (rid, pos) pairs of the anchor recurrence (8 B/record), the frame headers and the result block
+    h2d = n_bytes + n_rec * 4
+    d2h = eng.counters_len() * 8 + eng.sketch_len() // 2 + n_rec * 8 + 48 * (len(e2e_bounds) - 1)
 
     def e2e_step():
         eng.reset()
@@ -419,7 +421,7 @@ def run_b200(args):
                        "batches_per_gpu": len(batches), "batch_mb": args.batch_mb, "l2": "inputs larger than L2 (no flush needed)",
                        "options": "-k 32 -q 17 -e 0.01 -s 1 -i 1000 -c chr1..chr22", "sharding": "genome slices, 5 kb holes, one NCCL all-reduce at the end"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "path": "bqc_submit from pinned host buffers: host framing + coverage anchor scan, H2D, kernels, D2H of results"},
+                    "path": "bqc_submit from pinned host buffers: H2D, device-side record framing, host coverage-anchor recurrence on the (rid,pos) pairs read back, kernels, D2H of results"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -81,9 +81,21 @@ int bqc_reset(bqc_engine* e);
 int bqc_acquire_staging(bqc_engine* e, void** pinned, size_t* capacity);
 /* Submit n_bytes of whole inflated BAM records (block_size prefixes included) that start at `data`.
  * `data` may be a staging buffer from bqc_acquire_staging (zero extra copies) or any host memory.
- * record_offsets (n_records+1 entries) may be NULL: the engine then frames the records itself.
+ * record_offsets (n_records+1 entries) may be NULL: the engine then frames the records itself (on the device;
+ * n_bytes must end on a record boundary).
  * Asynchronous: returns once the copies and kernels are enqueued. */
 int bqc_submit(bqc_engine* e, const void* data, size_t n_bytes, const uint64_t* record_offsets, uint64_t n_records);
+/* Submit the next n_bytes of the inflated record stream; chunks need not end on record boundaries (what
+ * readRecord() hides at src/bamqualcheck.cpp:306).  The partial record at the end of a chunk is carried into the
+ * next one on the device; the records are framed on the device (speculated window starts, verified against the
+ * sequential chain; kernel_frame.cuh).  `last` != 0 marks the end of the stream: a trailing partial record is then
+ * the reference's "Could not read record" error (BQC_ERR_BAD_RECORD).  With several read groups, or with
+ * BQC_HOST_FRAMING=1 in the environment, the host framer is used instead (same results). */
+int bqc_submit_stream(bqc_engine* e, const void* data, size_t n_bytes, int last);
+/* Number of stream buffers whose speculative framing failed verification and were re-framed sequentially. */
+uint64_t bqc_frames_repaired(bqc_engine* e);
+/* Records submitted so far (waits for the submissions in flight to be framed). */
+uint64_t bqc_records_seen(bqc_engine* e);
 
 /* ---- resident path (records already in HBM; kernel-only timing and replay) --------------------- */
 int bqc_batch_prepare(bqc_engine* e, const void* data, size_t n_bytes, const uint64_t* record_offsets,

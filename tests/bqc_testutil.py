@@ -62,8 +62,11 @@ def diff_bamqc(a_path, b_path, max_report=8):
 
 
 def run_engine(genome, lib_, records, offsets, out_path, chroms="chr1,chr2", isize=1000, klist=(32,), qlist=(17,),
-               e=0.01, seed=1, n_batches=1, sample_id="S1", resident=False, engine_kwargs=None, keep=False):
-    """Push `records` through the CUDA engine via the C ABI and write the .bamqc text."""
+               e=0.01, seed=1, n_batches=1, sample_id="S1", resident=False, engine_kwargs=None, keep=False, mode="offsets",
+               chunk_bytes=None):
+    """Push `records` through the CUDA engine via the C ABI and write the .bamqc text.
+    mode: "offsets" (host-framed, offsets given), "whole" (whole-record slices, framed by the engine),
+    "stream" (arbitrary chunk_bytes-sized chunks of the byte stream through bqc_submit_stream)."""
     from bamqc_b200 import Engine, synth
     eng = Engine(lane_ids=synth.lane_ids(lib_), ref_names=genome.names, chroms=chroms, isize=isize, klist=klist,
                  qlist=qlist, e=e, seed=seed, **(engine_kwargs or {}))
@@ -72,6 +75,17 @@ def run_engine(genome, lib_, records, offsets, out_path, chroms="chr1,chr2", isi
     nrec = len(offsets) - 1
     bounds = [nrec * i // n_batches for i in range(n_batches + 1)]
     batches = []
+    if mode == "stream":
+        total = int(offsets[-1])
+        step = chunk_bytes or max(1, total // max(1, n_batches))
+        p = 0
+        while True:
+            q = min(total, p + step)
+            eng.submit_stream(records[p:q], last=q >= total)
+            p = q
+            if p >= total:
+                break
+        n_batches = 0
     for i in range(n_batches):
         lo, hi = bounds[i], bounds[i + 1]
         if hi == lo:
@@ -79,6 +93,8 @@ def run_engine(genome, lib_, records, offsets, out_path, chroms="chr1,chr2", isi
         o = offsets[lo:hi + 1]
         if resident:
             batches.append(eng.prepare(records[int(o[0]):int(o[-1])], o - o[0]))
+        elif mode == "whole":
+            eng.submit(records[int(o[0]):int(o[-1])], None)
         else:
             eng.submit(records, o)
     if resident:

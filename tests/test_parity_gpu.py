@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _roundtrip(tmp_path, lib_, genome=None, chroms="chr1,chr2", isize=1000, klist=(32,), qlist=(17,), seed=1,
-               n_batches=1, resident=False, engine_kwargs=None):
+               n_batches=1, resident=False, engine_kwargs=None, mode="offsets", chunk_bytes=None, expect_repaired=None):
     from bamqc_b200 import synth
     genome = genome or util.small_genome()
     records, offsets = synth.generate(genome, lib_)
@@ -23,8 +23,11 @@ def _roundtrip(tmp_path, lib_, genome=None, chroms="chr1,chr2", isize=1000, klis
     assert r.returncode == 0, r.stderr
     eng = util.run_engine(genome, lib_, records, offsets, tmp_path / "gpu.bamqc", chroms=chroms, isize=isize,
                           klist=klist, qlist=qlist, seed=seed, n_batches=n_batches, resident=resident,
-                          engine_kwargs=engine_kwargs, keep=True)
+                          engine_kwargs=engine_kwargs, keep=True, mode=mode, chunk_bytes=chunk_bytes)
     try:
+        assert eng.records_seen == len(offsets) - 1
+        if expect_repaired is not None:
+            assert (eng.frames_repaired > 0) == expect_repaired
         diffs = util.diff_bamqc(tmp_path / "oracle.bamqc", tmp_path / "gpu.bamqc")
         assert not diffs, "\n".join(diffs)
         # sketch tables and F2 tables themselves, not only the estimators printed in the text
@@ -79,3 +82,61 @@ def test_sparse_coverage_windows(tmp_path):
 def test_other_read_length_and_seed(tmp_path):
     from bamqc_b200 import synth
     _roundtrip(tmp_path, synth.Library(seed=17, n_pairs=6000, read_len=101, ins_mean=300), seed=5)
+
+
+# ---- device-side framing (kernel_frame.cuh): the engine finds the record boundaries itself ----------------------
+def test_device_framing_whole_record_slices(tmp_path):
+    from bamqc_b200 import synth
+    _roundtrip(tmp_path, synth.Library(seed=21, n_pairs=20000), n_batches=3, mode="whole", expect_repaired=False)
+
+
+def test_stream_chunks_cut_records_anywhere(tmp_path):
+    """Chunks of 1,000,003 bytes: every chunk ends inside a record; the partial record is carried on the device."""
+    from bamqc_b200 import synth
+    _roundtrip(tmp_path, synth.Library(seed=22, n_pairs=20000).stress(), mode="stream", chunk_bytes=1000003,
+               expect_repaired=False)
+
+
+def test_stream_tiny_chunks_and_tiny_staging(tmp_path):
+    """Chunks smaller than a record and than the speculation window; staging buffers of 64 KiB."""
+    from bamqc_b200 import synth
+    _roundtrip(tmp_path, synth.Library(seed=23, n_pairs=1500), mode="stream", chunk_bytes=173,
+               engine_kwargs=dict(staging_bytes=1 << 16), expect_repaired=False)
+    _roundtrip(tmp_path, synth.Library(seed=24, n_pairs=6000), mode="stream", chunk_bytes=50021,
+               engine_kwargs=dict(staging_bytes=1 << 16), expect_repaired=False)
+
+
+def test_stream_repair_path(tmp_path, monkeypatch):
+    """Every speculation is declared failed: k_frame_repair frames sequentially, results are the same."""
+    from bamqc_b200 import synth
+    monkeypatch.setenv("BQC_FRAME_FORCE_REPAIR", "1")
+    _roundtrip(tmp_path, synth.Library(seed=25, n_pairs=5000), mode="stream", chunk_bytes=300007, expect_repaired=True)
+
+
+def test_stream_host_framing_switch(tmp_path, monkeypatch):
+    """BQC_HOST_FRAMING=1: same stream API, records framed by the host framer."""
+    from bamqc_b200 import synth
+    monkeypatch.setenv("BQC_HOST_FRAMING", "1")
+    _roundtrip(tmp_path, synth.Library(seed=26, n_pairs=5000), mode="stream", chunk_bytes=300007, expect_repaired=False)
+
+
+def test_stream_two_lanes_uses_host_framer(tmp_path):
+    from bamqc_b200 import synth
+    _roundtrip(tmp_path, synth.Library(seed=27, n_pairs=5000, n_lanes=2), mode="stream", chunk_bytes=400009)
+
+
+def test_stream_truncated_record_is_an_error(tmp_path):
+    from bamqc_b200 import Engine, synth
+    from bamqc_b200.engine import BamQCError
+    genome = util.small_genome()
+    lib_ = synth.Library(seed=28, n_pairs=2000)
+    records, offsets = synth.generate(genome, lib_)
+    eng = Engine(lane_ids=synth.lane_ids(lib_), ref_names=genome.names, chroms="chr1,chr2")
+    try:
+        cut = int(offsets[-1]) - 17
+        with pytest.raises(BamQCError) as ei:
+            eng.submit_stream(records[:cut], last=True)
+            eng.finish()
+        assert ei.value.code == 4
+    finally:
+        eng.close()
