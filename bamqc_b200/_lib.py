@@ -78,6 +78,7 @@ PROTOTYPES = {
     "bqc_acquire_staging": (ctypes.c_int, [_vp, _P(_vp), _P(ctypes.c_size_t)]),
     "bqc_submit": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, _u64]),
     "bqc_submit_stream": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_int]),
+    "bqc_submit_bgzf": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]),
     "bqc_frames_repaired": (_u64, [_vp]),
     "bqc_records_seen": (_u64, [_vp]),
     "bqc_batch_prepare": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, _u64, _P(_vp)]),

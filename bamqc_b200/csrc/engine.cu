@@ -28,6 +28,7 @@
 #include "../../include/bamqc_b200.h"
 #include "kernels.cuh"
 #include "kernel_frame.cuh"
+#include "kernel_inflate.cuh"
 
 using namespace bqc;
 
@@ -153,6 +154,11 @@ struct Slot {  // one half of the staging double buffer
     ScanMeta* d_meta = nullptr;
     uint32_t *d_ws = nullptr, *d_we = nullptr, *d_wc = nullptr, *d_ws2 = nullptr, *d_we2 = nullptr, *d_wc2 = nullptr, *d_bsum = nullptr, *d_bbase = nullptr;
     cudaEvent_t framed = nullptr, aux_done = nullptr;
+    // device inflate (kernel_inflate.cuh)
+    uint8_t* d_cin = nullptr;          // compressed BGZF bytes of the submission
+    InflateBlock* h_blocks = nullptr;  // pinned
+    InflateBlock* d_blocks = nullptr;
+    uint32_t* d_ictl = nullptr;        // ticket, error
 };
 
 struct bqc_engine {
@@ -202,7 +208,9 @@ struct bqc_engine {
     // sequential anchor pass, the H2D copies and the kernel launches of buffer i
     struct Task {
         int slot; const uint8_t* h2d_src; size_t span; uint64_t n_records; uint32_t max_lseq;
-        int mode;          // 0: framed by the host (offsets + meta in the slot), 1: raw stream bytes, framed on the device
+        int mode;          // 0: framed by the host (offsets + meta in the slot), 1: raw stream bytes, framed on the device,
+                           // 2: BGZF blocks, inflated and framed on the device
+        uint32_t n_blocks = 0, inflated = 0, skip = 0;  // mode 2: BGZF blocks, their total inflated size, leading non-record bytes
         bool must_align;   // the bytes must end on a record boundary (whole-record submissions, last stream chunk)
     };
     std::deque<Task> ingest;       // stream tasks whose H2D copy + framing kernels are enqueued, not yet launched
@@ -230,8 +238,10 @@ struct bqc_engine {
     struct ProfEv { int family; cudaEvent_t a, b; };
     std::vector<ProfEv> prof_pending;
     std::vector<cudaEvent_t> prof_pool;
-    double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint64_t prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double prof_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t prof_n[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t blocks_per_slot = 0;  // capacity of the BGZF block table of a slot
+    int inflate_bps = 0;
 
     // results (after finish)
     bool have_results = false;
@@ -324,6 +334,8 @@ extern "C" void bqc_destroy(bqc_engine* e) {
         if (s.h_lane) cudaFreeHost(s.h_lane);
         if (s.h_frame) cudaFreeHost(s.h_frame);
         if (s.h_meta) cudaFreeHost(s.h_meta);
+        if (s.h_blocks) cudaFreeHost(s.h_blocks);
+        cudaFree(s.d_cin); cudaFree(s.d_blocks); cudaFree(s.d_ictl);
         cudaFree(s.d_frame); cudaFree(s.d_meta); cudaFree(s.d_ws); cudaFree(s.d_we); cudaFree(s.d_wc); cudaFree(s.d_ws2); cudaFree(s.d_we2); cudaFree(s.d_wc2); cudaFree(s.d_bsum); cudaFree(s.d_bbase);
         free_device_batch(s.dev);
         if (s.done) cudaEventDestroy(s.done);
@@ -434,6 +446,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     e->staging_bytes = cfg->staging_bytes ? cfg->staging_bytes : (256ull << 20);
     if (e->staging_bytes > 0xF0000000ull) e->staging_bytes = 0xF0000000ull;
     e->max_records_per_slot = e->staging_bytes / 40 + 16;  // a record is at least 36 bytes
+    e->blocks_per_slot = e->staging_bytes / 4096 + 4096;   // BGZF blocks per submission (larger inputs are split)
     e->ring_log2 = cfg->cov_ring_log2 ? cfg->cov_ring_log2 : 28;
     if (const char* v = getenv("BQC_STATS_BPS")) e->tune_stats_bps = atoi(v);
     if (const char* v = getenv("BQC_HOST_FRAMING")) e->device_framing = atoi(v) == 0;
@@ -487,6 +500,8 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
             CU(cudaEventCreateWithFlags(&s.aux_done, cudaEventDisableTiming));
         }
         // opt in to large dynamic shared memory
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->inflate_bps, k_inflate, (int)kInflateWarps * 32, 0));
+        if (e->inflate_bps < 1) e->inflate_bps = 1;
         CU(cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(k_eightmer, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CU(cudaFuncSetAttribute(k_sketch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
@@ -825,11 +840,12 @@ struct ProfScope {  // records an event pair around the launches of one kernel f
 extern "C" void bqc_profile_enable(bqc_engine* e, int on) { e->profiling = on != 0; }
 // Accumulated device time per kernel family since the last call: 0 k_stats, 1 k_eightmer, 2 k_sketch,
 // 3 coverage flush (3 kernels per launch group), 4 merge/export.  Synchronises the compute stream.
-extern "C" int bqc_profile_read(bqc_engine* e, double ms_out[8], uint64_t n_out[8]) {
+extern "C" int bqc_profile_read(bqc_engine* e, double ms_out[12], uint64_t n_out[12]) {
     CU(cudaSetDevice(e->cfg.device));
     drain_commits(e);
     CU(cudaStreamSynchronize(e->compute));
     CU(cudaStreamSynchronize(e->covs));
+    CU(cudaStreamSynchronize(e->frames));
     for (auto& p : e->prof_pending) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { e->prof_ms[p.family] += ms; e->prof_n[p.family] += 1; }
@@ -837,7 +853,7 @@ extern "C" int bqc_profile_read(bqc_engine* e, double ms_out[8], uint64_t n_out[
         e->prof_pool.push_back(p.b);
     }
     e->prof_pending.clear();
-    for (int i = 0; i < 8; ++i) { ms_out[i] = e->prof_ms[i]; n_out[i] = e->prof_n[i]; e->prof_ms[i] = 0; e->prof_n[i] = 0; }
+    for (int i = 0; i < 12; ++i) { ms_out[i] = e->prof_ms[i]; n_out[i] = e->prof_n[i]; e->prof_ms[i] = 0; e->prof_n[i] = 0; }
     return 0;
 }
 
@@ -1019,6 +1035,11 @@ static int ensure_slot(bqc_engine* e, Slot& s) {
     CU(cudaMalloc(&s.d_wc2, nwin * 4));
     CU(cudaMalloc(&s.d_bsum, nblk * 4));
     CU(cudaMalloc(&s.d_bbase, nblk * 4));
+    CU(cudaMalloc(&s.d_cin, e->staging_bytes + 256));
+    CU(cudaMemset(s.d_cin, 0, e->staging_bytes + 256));
+    CU(cudaHostAlloc((void**)&s.h_blocks, e->blocks_per_slot * sizeof(InflateBlock), cudaHostAllocDefault));
+    CU(cudaMalloc(&s.d_blocks, e->blocks_per_slot * sizeof(InflateBlock)));
+    CU(cudaMalloc(&s.d_ictl, 8));
     return alloc_device_batch(e, s.dev, e->staging_bytes, rc_);
 }
 
@@ -1052,11 +1073,28 @@ static int stream_stage_a(bqc_engine* e, const bqc_engine::Task& t) {
     Slot& s = e->slots[t.slot];
     DeviceBatch& d = s.dev;
     const Slot* prev = e->last_stream_slot >= 0 ? &e->slots[e->last_stream_slot] : nullptr;
-    k_frame_tail<<<1, 256, 0, e->frames>>>(prev ? prev->dev.bytes : nullptr, prev ? prev->d_frame : nullptr, d.bytes, s.d_frame, (uint32_t)t.span);
-    CU(cudaMemcpyAsync(d.bytes + kFrameHead, t.h2d_src, t.span, cudaMemcpyHostToDevice, e->copy));
-    CU(cudaEventRecord(e->copied, e->copy));
-    CU(cudaStreamWaitEvent(e->frames, e->copied, 0));
-    const uint32_t nwin = (uint32_t)((kFrameHead + t.span + kFrameWindow - 1) / kFrameWindow);
+    const uint32_t n_new = t.mode == 2 ? t.inflated : (uint32_t)t.span;
+    k_frame_tail<<<1, 256, 0, e->frames>>>(prev ? prev->dev.bytes : nullptr, prev ? prev->d_frame : nullptr, d.bytes, s.d_frame, n_new, t.skip);
+    if (t.mode == 2) {
+        // compressed bytes + block table over PCIe, inflate on the device into the stream region of the buffer
+        CU(cudaMemcpyAsync(s.d_cin, t.h2d_src, t.span, cudaMemcpyHostToDevice, e->copy));
+        CU(cudaMemcpyAsync(s.d_blocks, s.h_blocks, (size_t)t.n_blocks * sizeof(InflateBlock), cudaMemcpyHostToDevice, e->copy));
+        CU(cudaEventRecord(e->copied, e->copy));
+        CU(cudaStreamWaitEvent(e->frames, e->copied, 0));
+        CU(cudaMemsetAsync(s.d_ictl, 0, 8, e->frames));
+        if (t.n_blocks) {
+            const int grid = (int)std::min<uint64_t>(((uint64_t)t.n_blocks + kInflateWarps - 1) / kInflateWarps, (uint64_t)e->n_sm * e->inflate_bps);
+            ProfScope prof(e, 8, e->frames);
+            k_inflate<<<grid, kInflateWarps * 32, 0, e->frames>>>(s.d_cin, s.d_blocks, t.n_blocks, d.bytes + kFrameHead, s.d_ictl);
+            e->launches += 1;
+        }
+    } else {
+        CU(cudaMemcpyAsync(d.bytes + kFrameHead, t.h2d_src, t.span, cudaMemcpyHostToDevice, e->copy));
+        CU(cudaEventRecord(e->copied, e->copy));
+        CU(cudaStreamWaitEvent(e->frames, e->copied, 0));
+    }
+    ProfScope prof_frame(e, 9, e->frames);
+    const uint32_t nwin = (uint32_t)((kFrameHead + (uint64_t)n_new + kFrameWindow - 1) / kFrameWindow);
     const uint32_t nblk = (nwin + kFrameThreads - 1) / kFrameThreads;
     const uint32_t rec_cap = (uint32_t)e->max_records_per_slot;
     k_frame_speculate<<<nblk, kFrameThreads, 0, e->frames>>>(d.bytes, s.d_frame, std::max(1, e->cfg.n_ref), nwin, s.d_ws, s.d_we, s.d_wc);
@@ -1065,7 +1103,7 @@ static int stream_stage_a(bqc_engine* e, const bqc_engine::Task& t) {
         k_frame_relax<<<nblk, kFrameThreads, 0, e->frames>>>(d.bytes, s.d_frame, nwin, s.d_ws2, s.d_we2, s.d_wc2, s.d_ws, s.d_we, s.d_wc);
     }
     k_frame_blocksum<<<nblk, kFrameThreads, 0, e->frames>>>(nwin, s.d_wc, s.d_bsum);
-    k_frame_verify<<<1, 1024, 0, e->frames>>>(s.d_frame, nwin, nblk, s.d_ws, s.d_we, s.d_bsum, s.d_bbase, d.offsets, rec_cap, e->force_bad_frames ? 1u : 0u);
+    k_frame_verify<<<1, 1024, 0, e->frames>>>(s.d_frame, nwin, nblk, s.d_ws, s.d_we, s.d_bsum, s.d_bbase, d.offsets, rec_cap, e->force_bad_frames ? 1u : 0u, t.mode == 2 ? s.d_ictl : nullptr);
     k_frame_repair<<<1, 32, 0, e->frames>>>(d.bytes, s.d_frame, e->cfg.n_ref, e->d_main_chrom, d.offsets, s.d_meta, rec_cap);
     k_frame_emit<<<nblk, kFrameThreads, 0, e->frames>>>(d.bytes, s.d_frame, e->cfg.n_ref, e->d_main_chrom, nwin, s.d_ws, s.d_wc, s.d_bbase, d.offsets, s.d_meta);
     e->launches += 10;
@@ -1085,6 +1123,13 @@ static int stream_stage_b(bqc_engine* e, const bqc_engine::Task& t) {
     CU(cudaEventSynchronize(s.framed));
     auto t_b1 = std::chrono::steady_clock::now();
     const FrameResult fr = *s.h_frame;
+    if (fr.inflate_bad) {
+        e->host_error.code = BQC_ERR_BAD_RECORD;
+        e->host_error.record = e->records_seen;
+        snprintf(e->host_error.message, sizeof(e->host_error.message), "ERROR: Could not read record from BAM File (BGZF block %u of the submission does not inflate)", fr.inflate_bad - 1);
+        set_error(e, "%s", e->host_error.message);
+        return BQC_ERR_BAD_RECORD;
+    }
     if (fr.tail_overflow) {
         e->host_error.code = fr.tail_overflow == 2 ? BQC_ERR_ARG : BQC_ERR_BAD_RECORD;
         e->host_error.record = e->records_seen + fr.n_records;
@@ -1150,7 +1195,7 @@ static void commit_loop(bqc_engine* e) {
             // keep up to two stream buffers in the copy + framing stage so that the H2D copy of the next buffer
             // overlaps the anchor pass and the launches of this one
             // (tasks complete in submission order: a host-framed task waits for the stream tasks before it)
-            const bool take_new = !e->cq.empty() && (e->cq.front().mode == 1 ? e->ingest.size() < 2 : e->ingest.empty());
+            const bool take_new = !e->cq.empty() && (e->cq.front().mode != 0 ? e->ingest.size() < 2 : e->ingest.empty());
             if (take_new) {
                 t = e->cq.front();
                 e->cq.pop_front();
@@ -1174,7 +1219,7 @@ static void commit_loop(bqc_engine* e) {
         }
         {
             std::lock_guard<std::mutex> g(e->cm);
-            if (have_new && t.mode == 1 && !finished_slot) e->ingest.push_back(t);
+            if (have_new && t.mode != 0 && !finished_slot) e->ingest.push_back(t);
             if (finished_slot) {
                 e->slots[t.slot].queued = false;
                 e->slots[t.slot].in_flight = rc == 0;
@@ -1326,6 +1371,104 @@ extern "C" int bqc_submit(bqc_engine* e, const void* data, size_t n_bytes, const
 
 extern "C" int bqc_submit_stream(bqc_engine* e, const void* data, size_t n_bytes, int last) {
     return submit_common(e, data, n_bytes, nullptr, 0, true, last != 0);
+}
+
+// Index the BGZF blocks at the front of in[0..n): block table entries relative to `in`, until a limit is reached or
+// the next block is incomplete.  Returns the bytes consumed; bad = malformed block header.
+static uint64_t index_bgzf(const uint8_t* in, uint64_t n, InflateBlock* blocks, uint64_t max_blocks, uint64_t max_out, uint64_t max_in, uint32_t& n_blocks, uint64_t& inflated, bool& bad) {
+    uint64_t p = 0, o = 0;
+    n_blocks = 0;
+    bad = false;
+    while (p + 18 <= n && n_blocks < max_blocks) {
+        if (in[p] != 0x1f || in[p + 1] != 0x8b || in[p + 2] != 8 || !(in[p + 3] & 4)) { bad = true; break; }
+        const uint32_t xlen = in[p + 10] | (in[p + 11] << 8);
+        if (p + 12 + xlen > n) break;
+        uint64_t x = p + 12, xend = x + xlen;
+        int bsize = -1;
+        while (x + 4 <= xend) {  // extra subfields; BC carries the block size (SAM/BAM specification 4.1)
+            const uint32_t slen = in[x + 2] | (in[x + 3] << 8);
+            if (in[x] == 'B' && in[x + 1] == 'C' && slen == 2 && x + 6 <= xend) bsize = in[x + 4] | (in[x + 5] << 8);
+            x += 4 + slen;
+        }
+        if (bsize < 0) { bad = true; break; }
+        const uint64_t blen = (uint64_t)bsize + 1;
+        if (p + blen > n) break;
+        if (blen < 12ull + xlen + 8) { bad = true; break; }
+        if (p + blen > max_in) break;
+        const uint32_t isize = rd32(in + p + blen - 4);
+        if (isize > 65536u) { bad = true; break; }
+        if (o + isize > max_out) break;
+        InflateBlock b;
+        b.cbeg = (uint32_t)(p + 12 + xlen);
+        b.clen = (uint32_t)(blen - 12 - xlen - 8);
+        b.obeg = (uint32_t)o;
+        b.isize = isize;
+        blocks[n_blocks++] = b;
+        o += isize;
+        p += blen;
+    }
+    inflated = o;
+    return p;
+}
+
+extern "C" int bqc_submit_bgzf(bqc_engine* e, const void* data, size_t n_bytes, size_t skip_bytes, int last) {
+    if (e->finished) { set_error(e, "bqc_submit_bgzf after bqc_finish (call bqc_reset)"); return BQC_ERR_ARG; }
+    if (e->async_rc) return e->async_rc;
+    CU(cudaSetDevice(e->cfg.device));
+    const uint8_t* src = (const uint8_t*)data;
+    const bool on_device = e->device_framing && e->n_lanes == 1;
+    size_t p = 0;
+    bool any = false;
+    while (p < n_bytes || (last && !any)) {
+        Slot& s = e->slots[e->next_slot];
+        int rc = ensure_slot(e, s);
+        if (rc) return rc;
+        rc = wait_slot(e, s);
+        if (rc) return rc;
+        uint32_t nb = 0;
+        uint64_t inflated = 0;
+        bool bad = false;
+        const uint64_t used = index_bgzf(src + p, n_bytes - p, s.h_blocks, e->blocks_per_slot, e->staging_bytes, e->staging_bytes, nb, inflated, bad);
+        if (bad || (used == 0 && p < n_bytes)) {
+            e->host_error.code = BQC_ERR_BAD_RECORD;
+            e->host_error.record = e->records_seen;
+            snprintf(e->host_error.message, sizeof(e->host_error.message), "ERROR: Could not read record from BAM File (malformed or truncated BGZF block)");
+            set_error(e, "%s", e->host_error.message);
+            return BQC_ERR_BAD_RECORD;
+        }
+        const bool final_chunk = last && p + used >= n_bytes;
+        if (skip_bytes > inflated) { set_error(e, "bqc_submit_bgzf: skip_bytes lies beyond the first %llu inflated bytes", (unsigned long long)inflated); return BQC_ERR_ARG; }
+        if (on_device) {
+            bqc_engine::Task t;
+            t.slot = e->next_slot;
+            t.n_records = 0;
+            t.max_lseq = 0;
+            t.mode = 2;
+            t.must_align = final_chunk;
+            t.span = (size_t)used;
+            t.n_blocks = nb;
+            t.inflated = (uint32_t)inflated;
+            t.skip = (uint32_t)skip_bytes;
+            t.h2d_src = used ? h2d_source(e, s, src + p, (size_t)used) : s.pinned + kFrameHead;
+            enqueue_task(e, s, t);
+        } else {
+            // several read groups / BQC_HOST_FRAMING=1: zlib on the host threads, then the host-framed stream path
+            uint8_t* buf = s.pinned + kFrameHead;
+            if (inflated && bqc_bgzf_inflate(src + p, used, buf, e->staging_bytes, e->host_threads) != inflated) {
+                e->host_error.code = BQC_ERR_BAD_RECORD;
+                e->host_error.record = e->records_seen;
+                snprintf(e->host_error.message, sizeof(e->host_error.message), "ERROR: Could not read record from BAM File (BGZF block does not inflate)");
+                set_error(e, "%s", e->host_error.message);
+                return BQC_ERR_BAD_RECORD;
+            }
+            rc = submit_common(e, buf + skip_bytes, (size_t)(inflated - skip_bytes), nullptr, 0, true, final_chunk);
+            if (rc) return rc;
+        }
+        skip_bytes = 0;
+        p += (size_t)used;
+        any = true;
+    }
+    return 0;
 }
 
 extern "C" uint64_t bqc_frames_repaired(bqc_engine* e) { drain_commits(e); return e->frames_repaired; }

@@ -113,6 +113,7 @@ extern "C" void bqc_free_bam_header(bqc_bam_header* h) {
 // BGZF
 // ------------------------------------------------------------------------------------------------
 struct BgzfBlock {
+    uint64_t bbeg;   // start of the block (gzip member header)
     uint64_t cbeg;   // start of the raw deflate payload
     uint32_t clen;   // payload length
     uint32_t isize;  // inflated size
@@ -147,6 +148,7 @@ static uint64_t bgzf_index(const uint8_t* in, uint64_t n, std::vector<BgzfBlock>
         BgzfBlock b;
         memcpy(&b.isize, in + p + blen - 4, 4);
         if (o + b.isize > max_out) break;
+        b.bbeg = p;
         b.cbeg = p + 12 + xlen;
         b.clen = (uint32_t)(blen - 12 - xlen - 8);
         b.obeg = o;
@@ -584,15 +586,15 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
 
     // ---- stream the inflated bytes through the pinned staging buffers; the engine frames the records --------
     int rc = 0;
+    auto report_submit_error = [&]() -> int {
+        bqc_error_info ei;
+        bqc_get_error(eng, &ei);
+        if (ei.code == BQC_ERR_BAD_RECORD) std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
+        else std::cerr << "ERROR: " << bqc_last_error(eng) << std::endl;
+        return 1;
+    };
     auto submit_chunk = [&](uint8_t* buf, size_t filled, bool last) -> int {
-        if (bqc_submit_stream(eng, buf, filled, last ? 1 : 0)) {
-            bqc_error_info ei;
-            bqc_get_error(eng, &ei);
-            if (ei.code == BQC_ERR_BAD_RECORD) std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
-            else std::cerr << "ERROR: " << bqc_last_error(eng) << std::endl;
-            return 1;
-        }
-        return 0;
+        return bqc_submit_stream(eng, buf, filled, last ? 1 : 0) ? report_submit_error() : 0;
     };
     if (raw) {
         size_t p = hdr_bytes;
@@ -609,35 +611,15 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
             rc = submit_chunk(buf, take, p >= file.size());
         }
     } else {
-        // the tail of the header prefix that already holds records
-        std::vector<uint8_t> pending(head.begin() + hdr_bytes, head.end());
-        size_t bi = next_block;
-        bool first = true;
-        while ((bi < blocks.size() || first) && !rc) {
-            void* pin;
-            size_t cap;
-            if (bqc_acquire_staging(eng, &pin, &cap)) { rc = 1; break; }
-            uint8_t* buf = (uint8_t*)pin;
-            size_t filled = 0;
-            if (first) {
-                memcpy(buf, pending.data(), pending.size());
-                filled = pending.size();
-                first = false;
-            }
-            std::vector<BgzfBlock> part;
-            uint64_t o = filled;
-            while (bi < blocks.size() && o + blocks[bi].isize <= cap) {
-                BgzfBlock b = blocks[bi++];
-                b.obeg = o;
-                o += b.isize;
-                part.push_back(b);
-            }
-            if (!part.empty() && !inflate_blocks(file.data(), part, buf, c.threads)) {
-                std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
-                rc = 1;
-                break;
-            }
-            rc = submit_chunk(buf, (size_t)o, bi >= blocks.size());
+        // the compressed blocks go to the device as they are (inflated and framed there); the first block that
+        // holds records may start with the end of the header
+        size_t k = 0;
+        while (k < blocks.size() && blocks[k].obeg + blocks[k].isize <= hdr_bytes) ++k;
+        if (k < blocks.size()) {
+            const size_t skip = hdr_bytes - (size_t)blocks[k].obeg;
+            if (bqc_submit_bgzf(eng, file.data() + blocks[k].bbeg, file.size() - (size_t)blocks[k].bbeg, skip, 1)) rc = report_submit_error();
+        } else {
+            rc = submit_chunk(nullptr, 0, true);
         }
     }
     if (!rc) {

@@ -37,7 +37,8 @@ struct FrameResult {
     uint32_t tail_overflow;  // 1: the partial record at the end does not fit the head room of the next buffer; 2: more records than the offset arrays hold
     uint32_t skip_emit;  // k_frame_emit has nothing to do (repaired, or overflow)
     uint32_t repaired;   // the speculation failed verification (1 + first inconsistent window) and k_frame_repair framed the buffer
-    uint32_t pad[3];
+    uint32_t inflate_bad; // device inflate: 1 + index of the first BGZF block of this buffer that failed (0 = none)
+    uint32_t pad[2];
 };
 
 struct FrameMeta { int32_t rid; uint32_t pos; };  // rid < 0: the record does not take part in the coverage statistic
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame_blocksum(uint32_t nwin,
 // one CTA of 1024 threads
 __global__ void __launch_bounds__(1024) k_frame_verify(FrameResult* fr, uint32_t nwin, uint32_t nblk, const uint32_t* __restrict__ ws, const uint32_t* __restrict__ we,
                                                        const uint32_t* __restrict__ block_sum, uint32_t* __restrict__ block_base, uint32_t* __restrict__ offsets, uint32_t rec_cap,
-                                                       uint32_t force_bad) {
+                                                       uint32_t force_bad, const uint32_t* __restrict__ inflate_ctl) {
     __shared__ uint32_t s_bad, s_end, s_carry;
     __shared__ uint32_t wsum[32];
     if (threadIdx.x == 0) { s_bad = 0xFFFFFFFFu; s_end = 0; s_carry = 0; }
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(1024) k_frame_verify(FrameResult* fr, uint32_t
     if (threadIdx.x == 0) {
         const uint32_t end = s_end ? s_end : min(start, total);  // no record at all: everything is tail
         const bool bad = s_bad != 0xFFFFFFFFu || force_bad;
+        fr->inflate_bad = (inflate_ctl && inflate_ctl[1]) ? (0xFFFFFFFFu - inflate_ctl[1]) + 1u : 0u;
         fr->n_records = s_carry;
         fr->bad = bad ? (s_bad == 0xFFFFFFFFu ? 1u : s_bad + 1u) : 0u;
         fr->end = end;
@@ -295,7 +297,9 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame_emit(const uint8_t* __r
 
 // Prepare the frame header of the next buffer: carry the partial record [end, total) of the previous buffer (if
 // any) in front of kFrameHead and set start/total.  One CTA.
-__global__ void __launch_bounds__(256) k_frame_tail(const uint8_t* __restrict__ prev_bytes, const FrameResult* __restrict__ prev, uint8_t* __restrict__ bytes, FrameResult* fr, uint32_t n_new) {
+// `skip`: bytes at the front of the new data that are not records (the BAM header in the first buffer of a file).
+__global__ void __launch_bounds__(256) k_frame_tail(const uint8_t* __restrict__ prev_bytes, const FrameResult* __restrict__ prev, uint8_t* __restrict__ bytes, FrameResult* fr, uint32_t n_new,
+                                                    uint32_t skip) {
     uint32_t tail = 0;
     if (prev) {
         tail = prev->total - prev->end;
@@ -308,12 +312,13 @@ __global__ void __launch_bounds__(256) k_frame_tail(const uint8_t* __restrict__ 
         fr->n_records = 0;
         fr->max_lseq = 0;
         fr->bad = 0;
-        fr->start = kFrameHead - tail;
+        fr->start = kFrameHead - tail + skip;
         fr->end = 0;
         fr->total = kFrameHead + n_new;
         fr->tail_overflow = 0;
         fr->skip_emit = 0;
         fr->repaired = 0;
+        fr->inflate_bad = 0;
     }
 }
 

@@ -129,6 +129,11 @@ class Engine:
         n = a.size if n_bytes is None else n_bytes
         self._check(self.lib.bqc_submit_stream(self.handle, a.ctypes.data if n else None, n, 1 if last else 0))
 
+    def submit_bgzf(self, data, skip=0, last=False):
+        """Whole BGZF blocks (compressed .bam bytes); inflated and framed on the device."""
+        a = _as_u8(data)
+        self._check(self.lib.bqc_submit_bgzf(self.handle, a.ctypes.data if a.size else None, a.size, skip, 1 if last else 0))
+
     @property
     def frames_repaired(self):
         return int(self.lib.bqc_frames_repaired(self.handle))
@@ -170,11 +175,12 @@ class Engine:
 
     def profile_read(self):
         """{family: (milliseconds, launch groups)} since the previous read (CUDA events on the compute stream)."""
-        ms = (ctypes.c_double * 8)()
-        n = (ctypes.c_uint64 * 8)()
+        ms = (ctypes.c_double * 12)()
+        n = (ctypes.c_uint64 * 12)()
         self._check(self.lib.bqc_profile_read(self.handle, ms, n))
-        names = ["k_stats", "k_eightmer", "k_sketch", "k_cov", "merge", "host_framing", "host_scan_pass1", "host_scan_pass2"]
-        return {names[i]: (float(ms[i]), int(n[i])) for i in range(8)}
+        names = ["k_stats", "k_eightmer", "k_sketch", "k_cov", "merge", "host_framing", "host_scan_pass1", "host_scan_pass2",
+                 "k_inflate", "k_frame", "_10", "_11"]
+        return {names[i]: (float(ms[i]), int(n[i])) for i in range(12)}
 
     # ---- multi-GPU merge ----------------------------------------------------------------------------
     def counters_len(self):

@@ -92,6 +92,13 @@ int bqc_submit(bqc_engine* e, const void* data, size_t n_bytes, const uint64_t* 
  * the reference's "Could not read record" error (BQC_ERR_BAD_RECORD).  With several read groups, or with
  * BQC_HOST_FRAMING=1 in the environment, the host framer is used instead (same results). */
 int bqc_submit_stream(bqc_engine* e, const void* data, size_t n_bytes, int last);
+/* Submit whole BGZF blocks (the compressed bytes of a .bam file) -- SURVEY section 8f rank 1: the blocks are copied
+ * to the device as they are, inflated there (one warp per block, kernel_inflate.cuh) and the inflated stream then
+ * takes the bqc_submit_stream path on the device.  data must start at a block boundary and hold whole blocks; any
+ * size (the call splits it to the staging capacity).  skip_bytes: inflated bytes at the front that are not records
+ * (the BAM header, for the first call of a file).  With several read groups or BQC_HOST_FRAMING=1 the blocks are
+ * inflated with zlib on the host threads instead (same results). */
+int bqc_submit_bgzf(bqc_engine* e, const void* data, size_t n_bytes, size_t skip_bytes, int last);
 /* Number of stream buffers whose speculative framing failed verification and were re-framed sequentially. */
 uint64_t bqc_frames_repaired(bqc_engine* e);
 /* Records submitted so far (waits for the submissions in flight to be framed). */
@@ -114,9 +121,10 @@ int bqc_get_error(bqc_engine* e, bqc_error_info* out); /* sticky device/host err
 
 /* Optional device timing of each kernel family with CUDA events on the compute stream.
  * bqc_profile_read: milliseconds and launch-group counts accumulated since the previous read, per family:
- * 0 k_stats, 1 k_eightmer, 2 k_sketch, 3 coverage flush, 4 merge/export. */
+ * 0 k_stats, 1 k_eightmer, 2 k_sketch, 3 coverage scatter + flush, 4 merge/export, 5-7 host framing / pre-pass /
+ * anchor pass (wall clock), 8 k_inflate, 9 framing kernels. */
 void bqc_profile_enable(bqc_engine* e, int on);
-int bqc_profile_read(bqc_engine* e, double ms_out[8], uint64_t n_out[8]);
+int bqc_profile_read(bqc_engine* e, double ms_out[12], uint64_t n_out[12]);
 
 /* End of input: flush the last two coverage windows (src/bamqualcheck.cpp:447-453).  After this the
  * device tables are final for this GPU.  Idempotent until the next bqc_reset. */

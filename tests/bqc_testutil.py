@@ -186,3 +186,21 @@ def run_cli(args):
     """The product CLI (bamqc_b200/bin/bamqualcheck)."""
     exe = os.path.join(ROOT, "bamqc_b200", "bin", "bamqualcheck")
     return subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True)
+
+
+def bgzf_block_starts(comp):
+    """Offsets of the BGZF blocks in a compressed byte array (BSIZE from the BC extra field, SAM/BAM spec 4.1)."""
+    b = bytes(comp)
+    out, p = [], 0
+    while p + 18 <= len(b):
+        assert b[p:p + 4] == b"\x1f\x8b\x08\x04"
+        xlen = struct.unpack_from("<H", b, p + 10)[0]
+        x, bsize = p + 12, None
+        while x + 4 <= p + 12 + xlen:
+            slen = struct.unpack_from("<H", b, x + 2)[0]
+            if b[x:x + 2] == b"BC" and slen == 2:
+                bsize = struct.unpack_from("<H", b, x + 4)[0]
+            x += 4 + slen
+        out.append(p)
+        p += bsize + 1
+    return out

@@ -140,3 +140,89 @@ def test_stream_truncated_record_is_an_error(tmp_path):
         assert ei.value.code == 4
     finally:
         eng.close()
+
+
+# ---- device-side BGZF inflate (kernel_inflate.cuh) --------------------------------------------------------------
+def _bgzf_roundtrip(tmp_path, lib_, level, pieces=1, with_header=False, engine_kwargs=None, monkey_env=None):
+    """Records -> BGZF (zlib at `level`) -> bqc_submit_bgzf -> .bamqc identical to the oracle's."""
+    from bamqc_b200 import Engine, synth
+    genome = util.small_genome()
+    records, offsets = synth.generate(genome, lib_)
+    n_bytes = int(offsets[-1])
+    fasta, bam = tmp_path / "ref.fa", tmp_path / "in.ubam"
+    genome.write_fasta(fasta)
+    synth.write_bam(bam, genome, lib_, records, n_bytes)
+    r = util.run_oracle(bam, fasta, tmp_path / "oracle.bamqc", chroms="chr1,chr2")
+    assert r.returncode == 0, r.stderr
+    payload = records[:n_bytes]
+    skip = 0
+    if with_header:  # the inflated stream starts with a BAM header that is not block aligned
+        raw = np.fromfile(bam, dtype=np.uint8)
+        skip = raw.size - n_bytes
+        payload = raw
+    comp = synth.bgzf_compress(payload, level=level)
+    eng = Engine(lane_ids=synth.lane_ids(lib_), ref_names=genome.names, chroms="chr1,chr2", **(engine_kwargs or {}))
+    try:
+        for rid, (p, n) in enumerate(zip(genome.packed, genome.lengths)):
+            eng.set_reference(rid, p, n)
+        # cut the compressed bytes at BGZF block boundaries into `pieces` submissions
+        starts = util.bgzf_block_starts(comp)
+        cuts = [starts[len(starts) * i // pieces] for i in range(pieces)] + [comp.size]
+        for i in range(pieces):
+            eng.submit_bgzf(comp[cuts[i]:cuts[i + 1]], skip=skip if i == 0 else 0, last=i == pieces - 1)
+        eng.finish()
+        assert eng.records_seen == len(offsets) - 1
+        eng.write_bamqc("S1", tmp_path / "gpu.bamqc")
+        diffs = util.diff_bamqc(tmp_path / "oracle.bamqc", tmp_path / "gpu.bamqc")
+        assert not diffs, "\n".join(diffs)
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+def test_device_inflate_levels(tmp_path, level):
+    """Stored blocks (level 0), fast and best dynamic-Huffman streams."""
+    from bamqc_b200 import synth
+    _bgzf_roundtrip(tmp_path, synth.Library(seed=31 + level, n_pairs=6000), level)
+
+
+def test_device_inflate_header_skip_and_pieces(tmp_path):
+    from bamqc_b200 import synth
+    _bgzf_roundtrip(tmp_path, synth.Library(seed=41, n_pairs=9000).stress(), 6, pieces=5, with_header=True)
+
+
+def test_device_inflate_small_staging_splits_submission(tmp_path):
+    from bamqc_b200 import synth
+    _bgzf_roundtrip(tmp_path, synth.Library(seed=42, n_pairs=5000), 6, engine_kwargs=dict(staging_bytes=1 << 18))
+
+
+def test_device_inflate_tiny_input_fixed_huffman(tmp_path):
+    """A few records: zlib emits fixed-Huffman blocks for tiny inputs."""
+    from bamqc_b200 import synth
+    _bgzf_roundtrip(tmp_path, synth.Library(seed=43, n_pairs=3), 6)
+    _bgzf_roundtrip(tmp_path, synth.Library(seed=44, n_pairs=40), 9)
+
+
+def test_device_inflate_corrupt_block_is_an_error(tmp_path):
+    from bamqc_b200 import Engine, synth
+    from bamqc_b200.engine import BamQCError
+    genome = util.small_genome()
+    lib_ = synth.Library(seed=45, n_pairs=3000)
+    records, offsets = synth.generate(genome, lib_)
+    comp = synth.bgzf_compress(records[:int(offsets[-1])], level=6).copy()
+    starts = util.bgzf_block_starts(comp)
+    comp[starts[2] + 40:starts[2] + 60] ^= 0x5A  # damage the deflate payload of the third block
+    eng = Engine(lane_ids=synth.lane_ids(lib_), ref_names=genome.names, chroms="chr1,chr2")
+    try:
+        with pytest.raises(BamQCError) as ei:
+            eng.submit_bgzf(comp, last=True)
+            eng.finish()
+        assert ei.value.code == 4
+    finally:
+        eng.close()
+
+
+def test_bgzf_host_inflate_switch(tmp_path, monkeypatch):
+    from bamqc_b200 import synth
+    monkeypatch.setenv("BQC_HOST_FRAMING", "1")
+    _bgzf_roundtrip(tmp_path, synth.Library(seed=46, n_pairs=4000), 6, pieces=3, with_header=True)
