@@ -4,7 +4,7 @@
 //
 // The record chain p -> p + 4 + block_size is a dependent load per record, so it is cut into windows that are
 // framed concurrently from SPECULATED starts and then VERIFIED:
-//   k_frame_speculate  one thread per 16 KiB window: the first position whose next six hops all look like BAM
+//   k_frame_speculate  one thread per 4 KiB window: the first position whose next six hops all look like BAM
 //                      records (same plausibility test as the host framer) is taken as the window's start; the
 //                      chain is walked to the first record that starts beyond the window (count, exit);
 //   k_frame_relax      a few rounds in which a window that its predecessor's chain enters somewhere else than at
@@ -22,7 +22,7 @@
 
 namespace bqc {
 
-static const uint32_t kFrameWindow = 16384;   // bytes per speculation window
+static const uint32_t kFrameWindow = 4096;    // bytes per speculation window
 static const uint32_t kFrameThreads = 128;    // windows per CTA
 static const uint32_t kFrameHops = 6;
 static const uint32_t kFrameHead = 1u << 20;  // room in front of a device buffer for the carried partial record

@@ -23,16 +23,23 @@ struct InflateBlock {   // one BGZF block, filled by the host from the block hea
     uint32_t isize;     // inflated size (BGZF trailer)
 };
 
-static const uint32_t kInflateWarps = 8;          // warps per CTA
+static const uint32_t kInflateWarps = 6;          // warps per CTA (6.5 KB of tables per warp)
 static const uint32_t kLitBits = 10, kDistBits = 8, kClBits = 7;
 
+// Table entries are packed so that one shared-memory load yields everything a symbol needs:
+//   bits 0-3 code length (0 = the code is longer than the primary index: canonical search), bits 4-7 number of
+//   extra bits, bits 8-9 kind (0 literal, 1 length / distance, 2 end of block, 3 invalid symbol), bits 16-31 value
+//   (literal byte, length base, distance base; the symbol itself for the code-length alphabet).
+static const uint32_t kKindBase = 1u << 8, kKindEob = 2u << 8, kKindInvalid = 3u << 8;
+
 struct alignas(16) InflateTabs {                   // per warp, shared memory
-    uint16_t lit[1u << kLitBits];                  // (code length << 9) | symbol; 0 = longer than kLitBits
-    uint16_t dist[1u << kDistBits];                // (code length << 5) | symbol
-    uint16_t cl[1u << kClBits];                    // code-length alphabet
+    uint32_t lit[1u << kLitBits];
+    uint32_t dist[1u << kDistBits];
+    uint32_t cl[1u << kClBits];
     uint16_t lit_sorted[288], dist_sorted[32], cl_sorted[20];   // symbols ordered by (length, symbol)
     uint16_t lit_count[16], dist_count[16], cl_count[16];       // symbols per code length
     uint16_t first[16], off0[16], offs[16];        // builder scratch: first canonical code / sorted offset per length
+    uint16_t slow_first[4], slow_index[4];         // state of the canonical search after the primary bits: [0] lit [1] dist [2] cl
     uint8_t lens[320];                             // code lengths of the literal/length + distance alphabets
     uint8_t cl_lens[32];                           // code lengths of the code-length alphabet
 };
@@ -43,17 +50,47 @@ __constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49
 __constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
+// packed entry of a symbol (without the code length)
+__device__ __forceinline__ uint32_t inflate_lit_entry(uint32_t s) {
+    if (s < 256u) return s << 16;
+    if (s == 256u) return kKindEob;
+    if (s > 285u) return kKindInvalid;
+    return kKindBase | ((uint32_t)c_len_extra[s - 257u] << 4) | ((uint32_t)c_len_base[s - 257u] << 16);
+}
+__device__ __forceinline__ uint32_t inflate_dist_entry(uint32_t s) {
+    if (s > 29u) return kKindInvalid;
+    return kKindBase | ((uint32_t)c_dist_extra[s] << 4) | ((uint32_t)c_dist_base[s] << 16);
+}
+__device__ __forceinline__ uint32_t inflate_cl_entry(uint32_t s) { return s << 16; }
+
 struct BitReader {  // LSB-first bit stream (RFC 1951 section 3.1.1); identical in every lane
     const uint8_t* in;
-    uint32_t pos;     // next byte to load
+    uint32_t pos;         // bytes folded into buf so far
     uint64_t buf;
-    uint32_t cnt;     // valid bits in buf
-    __device__ __forceinline__ void init(const uint8_t* p) { in = p; pos = 0; buf = 0; cnt = 0; }
+    uint32_t cnt;         // valid bits in buf
+    // input words are fetched one refill ahead through aligned 32-bit loads: w0 = aligned word under pos, wn = the
+    // one after it (already in flight), sh = byte misalignment of the payload
+    const uint32_t* wp;
+    uint32_t w0, wn, sh;
+    __device__ __forceinline__ void seek(uint32_t p) {
+        pos = p;
+        buf = 0;
+        cnt = 0;
+        const uintptr_t a = (uintptr_t)(in + p);
+        wp = (const uint32_t*)(a & ~(uintptr_t)3);
+        sh = (uint32_t)(a & 3) * 8;
+        w0 = __ldg(wp);
+        wn = __ldg(++wp);
+    }
+    __device__ __forceinline__ void init(const uint8_t* p) { in = p; seek(0); }
     __device__ __forceinline__ void refill() {  // afterwards cnt >= 32
         if (cnt < 32u) {
-            buf |= (uint64_t)ldu32(in + pos) << cnt;
+            const uint32_t v = sh ? __funnelshift_r(w0, wn, sh) : w0;
+            buf |= (uint64_t)v << cnt;
             pos += 4;
             cnt += 32;
+            w0 = wn;
+            wn = __ldg(++wp);
         }
     }
     __device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t)buf & ((1u << n) - 1u); }
@@ -62,13 +99,14 @@ struct BitReader {  // LSB-first bit stream (RFC 1951 section 3.1.1); identical 
     __device__ __forceinline__ uint32_t bytes_used() const { return pos - (cnt >> 3); }  // bytes consumed (partial byte counts)
 };
 
-// Build the decoding tables of one alphabet from lens[0..n): count[], sorted[] and the primary table (PB index
-// bits, entry = length << SB | symbol).  Returns false for an over-subscribed code.  Called by all lanes.
-template <uint32_t PB, uint32_t SB>
-__device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* lens, uint32_t n, uint16_t* count, uint16_t* sorted, uint16_t* tab, uint32_t lane) {
+// Build the decoding tables of one alphabet from lens[0..n): count[], sorted[], the primary table (PB index bits)
+// and the entry state of the canonical search for longer codes.  WHICH: 0 literal/length, 1 distance, 2 code
+// lengths.  Returns false for an over-subscribed code.  Called by all lanes.
+template <uint32_t PB, uint32_t WHICH>
+__device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* lens, uint32_t n, uint16_t* count, uint16_t* sorted, uint32_t* tab, uint32_t lane) {
     __syncwarp();
     if (lane < 8) reinterpret_cast<uint32_t*>(count)[lane] = 0;
-    for (uint32_t i = lane; i < (1u << PB) / 2; i += 32) reinterpret_cast<uint32_t*>(tab)[i] = 0;
+    for (uint32_t i = lane; i < (1u << PB); i += 32) tab[i] = 0;
     __syncwarp();
     for (uint32_t s = lane; s < n; s += 32) {  // 16-bit counters updated through their 32-bit word
         const uint32_t l = lens[s];
@@ -87,6 +125,7 @@ __device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* len
             T.offs[l] = (uint16_t)off;
             code += c;
             off += c;
+            if (l == PB) { T.slow_first[WHICH] = (uint16_t)(code << 1); T.slow_index[WHICH] = (uint16_t)off; }
         }
         T.offs[0] = (uint16_t)bad;
         T.off0[0] = (uint16_t)off;  // number of coded symbols
@@ -105,7 +144,7 @@ __device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* len
         if (l <= PB) {
             const uint32_t code = (uint32_t)T.first[l] + (i - (uint32_t)T.off0[l]);
             const uint32_t r = __brev(code) >> (32u - l);   // Huffman codes are packed starting from their MSB
-            const uint16_t entry = (uint16_t)((l << SB) | s);
+            const uint32_t entry = l | (WHICH == 0 ? inflate_lit_entry(s) : WHICH == 1 ? inflate_dist_entry(s) : inflate_cl_entry(s));
             for (uint32_t k = r; k < (1u << PB); k += (1u << l)) tab[k] = entry;
         }
     }
@@ -113,33 +152,28 @@ __device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* len
     return true;
 }
 
-// canonical decode, one bit at a time (codes longer than the primary table); needs >= 15 bits in the buffer
-__device__ __forceinline__ int inflate_decode_slow(BitReader& br, const uint16_t* count, const uint16_t* sorted) {
-    uint32_t bits = (uint32_t)br.buf;
-    int code = 0, first = 0, index = 0;
-    for (uint32_t len = 1; len < 16; ++len) {
+// Codes longer than the primary index: canonical search one bit at a time, entered with the state it has after
+// PB bits (no shorter code matched, or the primary entry would exist).  Needs >= 15 bits in the buffer.  Returns
+// the packed entry with the full code length, or 0 if no code matches.
+template <uint32_t PB, uint32_t WHICH>
+__device__ __noinline__ uint32_t inflate_decode_slow(const InflateTabs& T, uint64_t buf, const uint16_t* count, const uint16_t* sorted) {
+    uint32_t bits = (uint32_t)(buf >> PB);
+    int code = (int)((__brev((uint32_t)buf) >> (32u - PB)) << 1);
+    int first = T.slow_first[WHICH], index = T.slow_index[WHICH];
+    for (uint32_t len = PB + 1; len < 16; ++len) {
         code |= (int)(bits & 1u);
         bits >>= 1;
         const int c = count[len];
         if (code - c < first) {
-            br.drop(len);
-            return sorted[index + (code - first)];
+            const uint32_t s = sorted[index + (code - first)];
+            return len | (WHICH == 0 ? inflate_lit_entry(s) : WHICH == 1 ? inflate_dist_entry(s) : inflate_cl_entry(s));
         }
         index += c;
         first += c;
         first <<= 1;
         code <<= 1;
     }
-    return -1;
-}
-template <uint32_t PB, uint32_t SB>
-__device__ __forceinline__ int inflate_decode(BitReader& br, const uint16_t* tab, const uint16_t* count, const uint16_t* sorted) {
-    const uint32_t e = tab[br.peek(PB)];
-    if (e) {
-        br.drop(e >> SB);
-        return (int)(e & ((1u << SB) - 1u));
-    }
-    return inflate_decode_slow(br, count, sorted);
+    return 0;
 }
 
 // ctl[0] = ticket, ctl[1] = 1 + index of the first BGZF block that failed to inflate (0 = none; atomicMin on the
@@ -162,6 +196,8 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
         br.init(cin + blk.cbeg);
         bool ok = true;
         uint32_t last = 0;
+        uint32_t pend = kNone;     // deferred store of the last step of the previous match (per lane): offset in o
+        uint32_t pend_val = 0;
         while (ok && !last) {
             br.refill();
             last = br.take(1);
@@ -176,9 +212,7 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
                 if (len != (~nlen & 0xFFFFu) || pos + len > isize || p + len > blk.clen) { ok = false; break; }
                 for (uint32_t j = lane; j < len; j += 32) o[pos + j] = ldg8(br.in + p + j);
                 pos += len;
-                br.pos = p + len;
-                br.buf = 0;
-                br.cnt = 0;
+                br.seek(p + len);
                 continue;
             }
             if (type == 3u) { ok = false; break; }
@@ -199,13 +233,15 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
                     const uint32_t v = br.take(3);
                     if (lane == 0) T.cl_lens[c_cl_order[i]] = (uint8_t)v;
                 }
-                if (!inflate_build<kClBits, 5>(T, T.cl_lens, 19, T.cl_count, T.cl_sorted, T.cl, lane)) { ok = false; break; }
+                if (!inflate_build<kClBits, 2>(T, T.cl_lens, 19, T.cl_count, T.cl_sorted, T.cl, lane)) { ok = false; break; }
                 const uint32_t total = nlit + ndist;
                 uint32_t i = 0;
                 while (i < total) {
                     br.refill();
-                    const int sym = inflate_decode<kClBits, 5>(br, T.cl, T.cl_count, T.cl_sorted);
-                    if (sym < 0) { ok = false; break; }
+                    uint32_t ce = T.cl[br.peek(kClBits)];
+                    if (!ce) { ok = false; break; }  // code-length codes are at most 7 bits: every valid code is in the table
+                    br.drop(ce & 15u);
+                    const int sym = (int)(ce >> 16);
                     if (sym < 16) {
                         if (lane == 0) T.lens[i] = (uint8_t)sym;
                         ++i;
@@ -227,40 +263,57 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
                 if (!ok) break;
                 if (T.lens[256] == 0) { ok = false; break; }  // no end-of-block code
             }
-            if (!inflate_build<kLitBits, 9>(T, T.lens, nlit, T.lit_count, T.lit_sorted, T.lit, lane)) { ok = false; break; }
-            if (!inflate_build<kDistBits, 5>(T, T.lens + nlit, ndist, T.dist_count, T.dist_sorted, T.dist, lane)) { ok = false; break; }
+            if (!inflate_build<kLitBits, 0>(T, T.lens, nlit, T.lit_count, T.lit_sorted, T.lit, lane)) { ok = false; break; }
+            if (!inflate_build<kDistBits, 1>(T, T.lens + nlit, ndist, T.dist_count, T.dist_sorted, T.dist, lane)) { ok = false; break; }
             // ---- symbols of this block ------------------------------------------------------------------
             for (;;) {
                 br.refill();
-                int sym = inflate_decode<kLitBits, 9>(br, T.lit, T.lit_count, T.lit_sorted);
-                if (sym < 0) { ok = false; break; }
-                if (sym < 256) {
+                uint32_t e = T.lit[br.peek(kLitBits)];
+                if (!(e & 15u)) {
+                    e = inflate_decode_slow<kLitBits, 0>(T, br.buf, T.lit_count, T.lit_sorted);
+                    if (!e) { ok = false; break; }
+                }
+                br.drop(e & 15u);
+                if (!(e & 0x300u)) {  // literal
                     if (pos >= isize) { ok = false; break; }
-                    if (lane == 0) o[pos] = (uint8_t)sym;
+                    if (lane == 0) o[pos] = (uint8_t)(e >> 16);
                     ++pos;
                     continue;
                 }
-                if (sym == 256) break;
-                sym -= 257;
-                if (sym >= 29) { ok = false; break; }
-                const uint32_t len = c_len_base[sym] + br.take(c_len_extra[sym]);
-                br.refill();
-                const int dsym = inflate_decode<kDistBits, 5>(br, T.dist, T.dist_count, T.dist_sorted);
-                if (dsym < 0 || dsym >= 30) { ok = false; break; }
-                const uint32_t dist = c_dist_base[dsym] + br.take(c_dist_extra[dsym]);
-                if (dist > pos || pos + len > isize) { ok = false; break; }
-                __syncwarp();  // the bytes the match refers to were stored by other lanes
-                const uint8_t* src = o + pos - dist;
-                if (dist >= len) {
-                    for (uint32_t j = lane; j < len; j += 32) o[pos + j] = src[j];
-                } else {       // overlapping match: byte j repeats with period dist
-                    for (uint32_t j = lane; j < len; j += 32) o[pos + j] = src[j % dist];
+                if (e & 0x200u) {     // end of block, or a symbol that must not occur
+                    if (e & 0x100u) ok = false;
+                    break;
                 }
-                __syncwarp();
+                const uint32_t len = (e >> 16) + br.take((e >> 4) & 15u);
+                br.refill();
+                uint32_t d = T.dist[br.peek(kDistBits)];
+                if (!(d & 15u)) {
+                    d = inflate_decode_slow<kDistBits, 1>(T, br.buf, T.dist_count, T.dist_sorted);
+                    if (!d) { ok = false; break; }
+                }
+                br.drop(d & 15u);
+                if (d & 0x200u) { ok = false; break; }
+                const uint32_t dist = (d >> 16) + br.take((d >> 4) & 15u);
+                if (dist > pos || pos + len > isize) { ok = false; break; }
+                // The copy is software-pipelined: the last 32-byte step of a match is loaded now and stored when the
+                // next match arrives (or at the end of the BGZF block), so the L2 round trip of the load overlaps
+                // the decoding of the following symbols instead of stalling the warp at the store.
+                if (pend != kNone) { o[pend] = (uint8_t)pend_val; pend = kNone; }
+                __syncwarp();  // the bytes the match refers to were stored by other lanes
+                const uint32_t sp = pos - dist;
+                uint32_t j = lane;
+                if (dist >= len) {
+                    for (; j + 32 < len + lane; j += 32) o[pos + j] = o[sp + j];   // all but the last step (uniform trip count)
+                    if (j < len) { pend_val = o[sp + j]; pend = pos + j; }
+                } else {       // overlapping match: byte j repeats with period dist
+                    for (; j + 32 < len + lane; j += 32) o[pos + j] = o[sp + j % dist];
+                    if (j < len) { pend_val = o[sp + j % dist]; pend = pos + j; }
+                }
                 pos += len;
             }
             if (br.bytes_used() > blk.clen + 8u) ok = false;  // ran past the payload
         }
+        if (pend != kNone) o[pend] = (uint8_t)pend_val;
         if (ok && (pos != isize || br.bytes_used() > blk.clen)) ok = false;
         if (!ok && lane == 0) atomicMax(ctl + 1, 0xFFFFFFFFu - b);  // largest complement = smallest index
         __syncwarp();

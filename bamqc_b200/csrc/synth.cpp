@@ -12,6 +12,8 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <thread>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -492,16 +494,39 @@ static size_t bgzfBlock(const uint8_t* in, size_t n, int level, uint8_t* out) {
 }
 
 uint64_t bqc_synth_bgzf_compress(const uint8_t* in, uint64_t n, int level, uint8_t* out, uint64_t cap) {
+    // blocks are independent: compressed by all host threads in groups, concatenated in order
     const size_t chunk = 0xff00;
-    std::vector<uint8_t> tmp(chunk + 1024);
+    const uint64_t nblk = (n + chunk - 1) / chunk;
+    const unsigned T = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::thread::hardware_concurrency(), nblk / 8));
+    const uint64_t group = 256;  // blocks per work item
+    const uint64_t ngroups = (nblk + group - 1) / group;
+    std::vector<std::vector<uint8_t>> parts((size_t)ngroups);
+    std::atomic<uint64_t> next(0);
+    auto work = [&]() {
+        std::vector<uint8_t> tmp(chunk + 1024);
+        for (;;) {
+            const uint64_t g = next.fetch_add(1);
+            if (g >= ngroups) break;
+            std::vector<uint8_t>& dst = parts[(size_t)g];
+            for (uint64_t b = g * group; b < std::min(nblk, (g + 1) * group); ++b) {
+                const uint64_t p = b * chunk;
+                const size_t m = (size_t)std::min<uint64_t>(chunk, n - p);
+                const size_t len = bgzfBlock(in + p, m, level, tmp.data());
+                dst.insert(dst.end(), tmp.begin(), tmp.begin() + len);
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
     uint64_t o = 0;
-    for (uint64_t p = 0; p < n; p += chunk) {
-        size_t m = (size_t)std::min<uint64_t>(chunk, n - p);
-        size_t b = bgzfBlock(in + p, m, level, tmp.data());
-        if (o + b > cap) return 0;
-        memcpy(out + o, tmp.data(), b);
-        o += b;
+    for (auto& part : parts) {
+        if (o + part.size() > cap) return 0;
+        memcpy(out + o, part.data(), part.size());
+        o += part.size();
     }
+    std::vector<uint8_t> tmp(1024);
     size_t b = bgzfBlock(in, 0, level, tmp.data());  // EOF block
     if (o + b > cap) return 0;
     memcpy(out + o, tmp.data(), b);
