@@ -226,6 +226,7 @@ struct bqc_engine {
     bool cstop = false, cbusy = false;
     int async_rc = 0;
     int tune_stats_bps = 0, tune_sketch_threads = 1024;  // BQC_STATS_BPS / BQC_SKETCH_THREADS (tuning knobs)
+    int tune_cov_bps = 8;                                // BQC_COV_BPS: coverage CTAs per SM (upper bound)
     std::vector<CovState> cov;
     uint64_t records_seen = 0, launches = 0, frames_repaired = 0;
     bool finished = false;
@@ -449,6 +450,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     e->blocks_per_slot = e->staging_bytes / 4096 + 4096;   // BGZF blocks per submission (larger inputs are split)
     e->ring_log2 = cfg->cov_ring_log2 ? cfg->cov_ring_log2 : 28;
     if (const char* v = getenv("BQC_STATS_BPS")) e->tune_stats_bps = atoi(v);
+    if (const char* v = getenv("BQC_COV_BPS")) e->tune_cov_bps = std::max(1, std::min(8, atoi(v)));
     if (const char* v = getenv("BQC_HOST_FRAMING")) e->device_framing = atoi(v) == 0;
     if (const char* v = getenv("BQC_TRACE")) e->trace = atoi(v) != 0;
     if (const char* v = getenv("BQC_FRAME_FORCE_REPAIR")) e->force_bad_frames = atoi(v) != 0;
@@ -500,12 +502,13 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
             CU(cudaEventCreateWithFlags(&s.aux_done, cudaEventDisableTiming));
         }
         // opt in to large dynamic shared memory
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->inflate_bps, k_inflate, (int)kInflateWarps * 32, 0));
+        CU(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kInflateStreams * sizeof(InflateTabs))));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->inflate_bps, k_inflate, (int)kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs)));
         if (e->inflate_bps < 1) e->inflate_bps = 1;
         CU(cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(k_eightmer, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CU(cudaFuncSetAttribute(k_sketch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-        CU(cudaFuncSetAttribute(k_sketch32, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024 + (int)sizeof(HashPairTable)));
+        CU(cudaFuncSetAttribute(k_sketch32, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024 + (int)sizeof(HashPairTable) + (int)(kSketchThreads / 32 * kSketchQueue * 8)));
         return 0;
     }();
     if (rc) { g_last_error = e->last_error; bqc_destroy(e); return rc; }
@@ -868,7 +871,9 @@ static int launch_cov_flush(bqc_engine* e, uint32_t lane, uint64_t from_abs, uin
     uint32_t start = (uint32_t)(from_abs & mask);
     uint64_t ntiles = (len + 31 + kCovTile - 1) / kCovTile;  // tiles are aligned to 32-entry granules
     if (ntiles + 1 > e->cov_sums_cap) { set_error(e, "coverage flush larger than the ring"); return BQC_ERR_ARG; }
-    int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)e->n_sm * (2048 / kCovThreads));
+    // a small grid: the flush is bound by the look-back latency, not by throughput, and a full-occupancy grid would
+    // evict the table kernels it is meant to overlap with
+    int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)e->n_sm * e->tune_cov_bps);
     unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
     ProfScope prof(e, 3, e->covs);
     // tile states + ticket live in one buffer: [0] = ticket, [1..] = states
@@ -938,7 +943,7 @@ static int launch_cov(bqc_engine* e, const DeviceBatch& d, const BatchLaunch& BL
                 B.cycb = BL.cycb;
                 B.first_record = d.first_record + sg.r0;
                 B.ring_base = (uint32_t)((sg.base_window[lane] * 1000) & (ring_size - 1));
-                int grid = (int)std::min<uint64_t>((ns + 255) / 256, (uint64_t)e->n_sm * 8);
+                int grid = (int)std::min<uint64_t>((ns + 255) / 256, (uint64_t)e->n_sm * e->tune_cov_bps);
                 ProfScope prof(e, 3, e->covs);
                 k_cov_scatter<<<grid, 256, 0, e->covs>>>(BL.E, B, lane);
                 e->launches += 1;
@@ -969,8 +974,8 @@ static int launch_tables(bqc_engine* e, const DeviceBatch& d, const BatchLaunch&
         B.ring_base = 0;
         int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * BL.bps);
         { ProfScope prof(e, 0); k_stats<<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane); }
-        int g8 = (int)std::min<uint64_t>(2 * ((n + kEightThreads - 1) / kEightThreads), (uint64_t)(e->n_sm & ~1));
-        if (g8 < 2) g8 = 2;
+        int g8 = (int)std::min<uint64_t>((n + kEightThreads - 1) / kEightThreads, (uint64_t)e->n_sm);
+        if (g8 < 1) g8 = 1;
         { ProfScope prof(e, 1); k_eightmer<<<g8, kEightThreads, 32768 * 4, e->compute>>>(E, B, lane); }
         e->launches += 2;
         for (uint32_t qi = 0; qi < e->qlist.size(); ++qi)
@@ -982,7 +987,7 @@ static int launch_tables(bqc_engine* e, const DeviceBatch& d, const BatchLaunch&
                 int gs = (int)std::min<uint64_t>((n + kSketchThreads - 1) / kSketchThreads, (uint64_t)e->n_sm);
                 ProfScope prof(e, 2);
                 if (SP.k == 32u && e->L.f2size <= 32768u)
-                    k_sketch32<<<gs, e->tune_sketch_threads, e->L.f2size * 4 + sizeof(HashPairTable), e->compute>>>(E, B, lane, SP, e->d_hash + ki);
+                    k_sketch32<<<gs, e->tune_sketch_threads, e->L.f2size * 4 + sizeof(HashPairTable) + kSketchThreads / 32 * kSketchQueue * 8, e->compute>>>(E, B, lane, SP, e->d_hash + ki);
                 else if (e->L.f2size <= 32768u)
                     k_sketch<true><<<gs, kSketchThreads, e->L.f2size * 4, e->compute>>>(E, B, lane, SP, e->d_hash + ki);
                 else
@@ -1083,9 +1088,9 @@ static int stream_stage_a(bqc_engine* e, const bqc_engine::Task& t) {
         CU(cudaStreamWaitEvent(e->frames, e->copied, 0));
         CU(cudaMemsetAsync(s.d_ictl, 0, 8, e->frames));
         if (t.n_blocks) {
-            const int grid = (int)std::min<uint64_t>(((uint64_t)t.n_blocks + kInflateWarps - 1) / kInflateWarps, (uint64_t)e->n_sm * e->inflate_bps);
+            const int grid = (int)std::min<uint64_t>(((uint64_t)t.n_blocks + kInflateStreams - 1) / kInflateStreams, (uint64_t)e->n_sm * e->inflate_bps);
             ProfScope prof(e, 8, e->frames);
-            k_inflate<<<grid, kInflateWarps * 32, 0, e->frames>>>(s.d_cin, s.d_blocks, t.n_blocks, d.bytes + kFrameHead, s.d_ictl);
+            k_inflate<<<grid, kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs), e->frames>>>(s.d_cin, s.d_blocks, t.n_blocks, d.bytes + kFrameHead, s.d_ictl);
             e->launches += 1;
         }
     } else {

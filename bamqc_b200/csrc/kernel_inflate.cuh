@@ -23,7 +23,13 @@ struct InflateBlock {   // one BGZF block, filled by the host from the block hea
     uint32_t isize;     // inflated size (BGZF trailer)
 };
 
-static const uint32_t kInflateWarps = 6;          // warps per CTA (6.5 KB of tables per warp)
+// Lanes that inflate one BGZF block together.  Sub-warp groups (8 lanes per block, four blocks per warp, the
+// instructions of a step shared by the groups whose symbols take the same path) were measured: 32 GB/s against
+// 38 GB/s for a whole warp per block -- the tables of four blocks per warp leave 12 warps per SM, too few to hide
+// the latency of the dependent decode chain -- so a block gets a full warp.
+static const uint32_t kGroup = 32;
+static const uint32_t kInflateWarps = 6;          // warps per CTA
+static const uint32_t kInflateStreams = kInflateWarps * 32 / kGroup;   // BGZF blocks in flight per CTA
 static const uint32_t kLitBits = 10, kDistBits = 8, kClBits = 7;
 
 // Table entries are packed so that one shared-memory load yields everything a symbol needs:
@@ -32,7 +38,7 @@ static const uint32_t kLitBits = 10, kDistBits = 8, kClBits = 7;
 //   (literal byte, length base, distance base; the symbol itself for the code-length alphabet).
 static const uint32_t kKindBase = 1u << 8, kKindEob = 2u << 8, kKindInvalid = 3u << 8;
 
-struct alignas(16) InflateTabs {                   // per warp, shared memory
+struct alignas(16) InflateTabs {                   // per group, shared memory
     uint32_t lit[1u << kLitBits];
     uint32_t dist[1u << kDistBits];
     uint32_t cl[1u << kClBits];
@@ -103,16 +109,16 @@ struct BitReader {  // LSB-first bit stream (RFC 1951 section 3.1.1); identical 
 // and the entry state of the canonical search for longer codes.  WHICH: 0 literal/length, 1 distance, 2 code
 // lengths.  Returns false for an over-subscribed code.  Called by all lanes.
 template <uint32_t PB, uint32_t WHICH>
-__device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* lens, uint32_t n, uint16_t* count, uint16_t* sorted, uint32_t* tab, uint32_t lane) {
-    __syncwarp();
-    if (lane < 8) reinterpret_cast<uint32_t*>(count)[lane] = 0;
-    for (uint32_t i = lane; i < (1u << PB); i += 32) tab[i] = 0;
-    __syncwarp();
-    for (uint32_t s = lane; s < n; s += 32) {  // 16-bit counters updated through their 32-bit word
+__device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* lens, uint32_t n, uint16_t* count, uint16_t* sorted, uint32_t* tab, uint32_t lane, uint32_t gmask) {
+    __syncwarp(gmask);
+    for (uint32_t i = lane; i < 8; i += kGroup) reinterpret_cast<uint32_t*>(count)[i] = 0;
+    for (uint32_t i = lane; i < (1u << PB); i += kGroup) tab[i] = 0;
+    __syncwarp(gmask);
+    for (uint32_t s = lane; s < n; s += kGroup) {  // 16-bit counters updated through their 32-bit word
         const uint32_t l = lens[s];
         atomicAdd(reinterpret_cast<uint32_t*>(count) + (l >> 1), 1u << (16 * (l & 1)));
     }
-    __syncwarp();
+    __syncwarp(gmask);
     if (lane == 0) {
         uint32_t code = 0, off = 0, left = 1, bad = 0;
         for (uint32_t l = 1; l < 16; ++l) {
@@ -135,10 +141,10 @@ __device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* len
                 if (l) sorted[T.offs[l]++] = (uint16_t)s;
             }
     }
-    __syncwarp();
+    __syncwarp(gmask);
     if (T.offs[0]) return false;
     const uint32_t total = T.off0[0];
-    for (uint32_t i = lane; i < total; i += 32) {
+    for (uint32_t i = lane; i < total; i += kGroup) {
         const uint32_t s = sorted[i];
         const uint32_t l = lens[s];
         if (l <= PB) {
@@ -148,7 +154,7 @@ __device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* len
             for (uint32_t k = r; k < (1u << PB); k += (1u << l)) tab[k] = entry;
         }
     }
-    __syncwarp();
+    __syncwarp(gmask);
     return true;
 }
 
@@ -180,13 +186,18 @@ __device__ __noinline__ uint32_t inflate_decode_slow(const InflateTabs& T, uint6
 // bitwise complement so that a zeroed word means "none")
 __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* __restrict__ cin, const InflateBlock* __restrict__ blocks, uint32_t n_blocks,
                                                                  uint8_t* out, uint32_t* ctl) {
-    __shared__ InflateTabs tabs[kInflateWarps];
-    const uint32_t lane = threadIdx.x & 31u;
-    InflateTabs& T = tabs[threadIdx.x >> 5];
+    extern __shared__ __align__(16) uint8_t inflate_smem[];
+    InflateTabs* tabs = reinterpret_cast<InflateTabs*>(inflate_smem);
+    // kGroup lanes work on one BGZF block; the groups of a warp run the same code on different blocks, so the
+    // instructions of a step are issued once for all groups whose symbols take the same path (literal / match)
+    const uint32_t lane = threadIdx.x & (kGroup - 1u);                       // lane within the group
+    const uint32_t gbase = (threadIdx.x & 31u) & ~(kGroup - 1u);              // first lane of the group in its warp
+    const uint32_t gmask = (kGroup == 32u ? 0xFFFFFFFFu : ((1u << kGroup) - 1u) << gbase);
+    InflateTabs& T = tabs[threadIdx.x / kGroup];
     for (;;) {
         uint32_t b = 0;
         if (lane == 0) b = atomicAdd(ctl, 1u);
-        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        b = __shfl_sync(gmask, b, gbase);
         if (b >= n_blocks) break;
         const InflateBlock blk = blocks[b];
         uint8_t* o = out + blk.obeg;
@@ -210,7 +221,7 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
                 const uint32_t nlen = br.take(16);
                 const uint32_t p = br.bytes_used();
                 if (len != (~nlen & 0xFFFFu) || pos + len > isize || p + len > blk.clen) { ok = false; break; }
-                for (uint32_t j = lane; j < len; j += 32) o[pos + j] = ldg8(br.in + p + j);
+                for (uint32_t j = lane; j < len; j += kGroup) o[pos + j] = ldg8(br.in + p + j);
                 pos += len;
                 br.seek(p + len);
                 continue;
@@ -218,22 +229,22 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
             if (type == 3u) { ok = false; break; }
             uint32_t nlit = 288, ndist = 30;
             if (type == 1u) {  // fixed codes (3.2.6)
-                for (uint32_t s = lane; s < 288; s += 32) T.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
-                if (lane < 30) T.lens[288 + lane] = 5;
+                for (uint32_t s = lane; s < 288; s += kGroup) T.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
+                for (uint32_t s = lane; s < 30; s += kGroup) T.lens[288 + s] = 5;
             } else {           // dynamic codes (3.2.7)
                 br.refill();
                 nlit = br.take(5) + 257;
                 ndist = br.take(5) + 1;
                 const uint32_t ncl = br.take(4) + 4;
                 if (nlit > 286 || ndist > 30) { ok = false; break; }
-                if (lane < 19) T.cl_lens[lane] = 0;
-                __syncwarp();
+                for (uint32_t s = lane; s < 19; s += kGroup) T.cl_lens[s] = 0;
+                __syncwarp(gmask);
                 for (uint32_t i = 0; i < ncl; ++i) {
                     br.refill();
                     const uint32_t v = br.take(3);
                     if (lane == 0) T.cl_lens[c_cl_order[i]] = (uint8_t)v;
                 }
-                if (!inflate_build<kClBits, 2>(T, T.cl_lens, 19, T.cl_count, T.cl_sorted, T.cl, lane)) { ok = false; break; }
+                if (!inflate_build<kClBits, 2>(T, T.cl_lens, 19, T.cl_count, T.cl_sorted, T.cl, lane, gmask)) { ok = false; break; }
                 const uint32_t total = nlit + ndist;
                 uint32_t i = 0;
                 while (i < total) {
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
                     if (sym < 16) {
                         if (lane == 0) T.lens[i] = (uint8_t)sym;
                         ++i;
-                        __syncwarp();
+                        __syncwarp(gmask);
                         continue;
                     }
                     uint32_t val = 0, rep;
@@ -256,15 +267,15 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
                     } else if (sym == 17) rep = 3 + br.take(3);
                     else rep = 11 + br.take(7);
                     if (i + rep > total) { ok = false; break; }
-                    for (uint32_t j = lane; j < rep; j += 32) T.lens[i + j] = (uint8_t)val;
+                    for (uint32_t j = lane; j < rep; j += kGroup) T.lens[i + j] = (uint8_t)val;
                     i += rep;
-                    __syncwarp();
+                    __syncwarp(gmask);
                 }
                 if (!ok) break;
                 if (T.lens[256] == 0) { ok = false; break; }  // no end-of-block code
             }
-            if (!inflate_build<kLitBits, 0>(T, T.lens, nlit, T.lit_count, T.lit_sorted, T.lit, lane)) { ok = false; break; }
-            if (!inflate_build<kDistBits, 1>(T, T.lens + nlit, ndist, T.dist_count, T.dist_sorted, T.dist, lane)) { ok = false; break; }
+            if (!inflate_build<kLitBits, 0>(T, T.lens, nlit, T.lit_count, T.lit_sorted, T.lit, lane, gmask)) { ok = false; break; }
+            if (!inflate_build<kDistBits, 1>(T, T.lens + nlit, ndist, T.dist_count, T.dist_sorted, T.dist, lane, gmask)) { ok = false; break; }
             // ---- symbols of this block ------------------------------------------------------------------
             for (;;) {
                 br.refill();
@@ -295,18 +306,18 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
                 if (d & 0x200u) { ok = false; break; }
                 const uint32_t dist = (d >> 16) + br.take((d >> 4) & 15u);
                 if (dist > pos || pos + len > isize) { ok = false; break; }
-                // The copy is software-pipelined: the last 32-byte step of a match is loaded now and stored when the
+                // The copy is software-pipelined: the last step of a match is loaded now and stored when the
                 // next match arrives (or at the end of the BGZF block), so the L2 round trip of the load overlaps
                 // the decoding of the following symbols instead of stalling the warp at the store.
                 if (pend != kNone) { o[pend] = (uint8_t)pend_val; pend = kNone; }
-                __syncwarp();  // the bytes the match refers to were stored by other lanes
+                __syncwarp(gmask);  // the bytes the match refers to were stored by other lanes
                 const uint32_t sp = pos - dist;
                 uint32_t j = lane;
                 if (dist >= len) {
-                    for (; j + 32 < len + lane; j += 32) o[pos + j] = o[sp + j];   // all but the last step (uniform trip count)
+                    for (; j + kGroup < len + lane; j += kGroup) o[pos + j] = o[sp + j];   // all but the last step (uniform trip count)
                     if (j < len) { pend_val = o[sp + j]; pend = pos + j; }
                 } else {       // overlapping match: byte j repeats with period dist
-                    for (; j + 32 < len + lane; j += 32) o[pos + j] = o[sp + j % dist];
+                    for (; j + kGroup < len + lane; j += kGroup) o[pos + j] = o[sp + j % dist];
                     if (j < len) { pend_val = o[sp + j % dist]; pend = pos + j; }
                 }
                 pos += len;
@@ -316,7 +327,7 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
         if (pend != kNone) o[pend] = (uint8_t)pend_val;
         if (ok && (pos != isize || br.bytes_used() > blk.clen)) ok = false;
         if (!ok && lane == 0) atomicMax(ctl + 1, 0xFFFFFFFFu - b);  // largest complement = smallest index
-        __syncwarp();
+        __syncwarp(gmask);
     }
 }
 

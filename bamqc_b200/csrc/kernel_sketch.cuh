@@ -17,10 +17,34 @@ struct HashPairTable {  // [strand][in 0..15][out 0..16] -> {h.lo, h.hi, t.lo, t
     ulonglong2 t[2][16][17];
 };
 
+// Valid k-mer hashes are rare on low-quality stretches (one base under the cutoff silences the next k windows), so
+// probing the sketch straight from the per-base loop would run the ~70 instructions of a probe for a handful of
+// active lanes.  Instead each lane appends its hash to a per-warp queue in shared memory (ballot + rank) and the
+// warp probes 32 queued hashes at a time with every lane busy.  The order of the updates does not matter: F2 and
+// sumCount are sums, the sketch counters saturate at 15.
+static const uint32_t kSketchQueue = 64;  // entries per warp (at most 31 waiting + 32 new)
+
+struct SketchProbe {  // one in-flight probe per lane: the word was loaded, the 4-bit increment is still to be done
+    uint32_t* wp;
+    uint32_t sh, old;
+    bool pend;
+    __device__ __forceinline__ void finish() {
+        if (pend) {
+            while (((old >> sh) & 15u) != 15u) {  // 4-bit saturating increment
+                const uint32_t assumed = old;
+                old = atomicCAS(wp, assumed, assumed + (1u << sh));
+                if (old == assumed) break;
+            }
+            pend = false;
+        }
+    }
+};
+
 __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, BatchView B, uint32_t lane, SketchParams SP, const HashTables* __restrict__ HT) {
-    extern __shared__ uint32_t sm[];                 // F2 table (f2size u32) followed by the pair table
+    extern __shared__ uint32_t sm[];                 // F2 table (f2size u32), the pair table, the per-warp hash queues
     const Layout& L = E.L;
     HashPairTable* PT = reinterpret_cast<HashPairTable*>(sm + L.f2size);
+    uint64_t* queue = reinterpret_cast<uint64_t*>(PT + 1) + (threadIdx.x >> 5) * kSketchQueue;
     for (uint32_t i = threadIdx.x; i < L.f2size; i += blockDim.x) sm[i] = 0;
     for (uint32_t i = threadIdx.x; i < 2 * 16 * 17; i += blockDim.x) {
         const uint32_t s = i / (16 * 17), in = (i / 17) % 16, out = i % 17;
@@ -37,8 +61,24 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, Ba
     const uint64_t idx_mask = (uint64_t)L.sk_size * 16ull - 1ull;
     const uint32_t f2mask = L.f2size - 1u;
     const int32_t q_thresh = SP.q_thresh;
-    unsigned long long my_count = 0;
+    unsigned long long warp_count = 0;               // k-mers hashed by this warp (same value in every lane)
     const uint32_t lane_id = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane_id) - 1u;
+    uint32_t qn = 0;                                 // queued hashes of this warp (uniform)
+    SketchProbe probe = {nullptr, 0u, 0u, false};
+
+    // StreamCounter::operator() (src/kmerstream/StreamCounter.hpp:67-93) for one hash per participating lane
+    auto probe_issue = [&](uint64_t hv) {
+        probe.finish();
+        atomicAdd(sm + ((uint32_t)hv & f2mask), 1u);
+        uint32_t w = hv ? (uint32_t)(__ffsll((long long)hv) - 1) : 63u;  // bitScanForward, 63 for 0
+        if (w > 31u) w = 31u;
+        const uint64_t index = (hv >> (w + 1u)) & idx_mask;
+        probe.wp = sk + w * words_per_level + (uint32_t)(index >> 3);
+        probe.sh = ((uint32_t)index & 7u) * 4u;
+        probe.old = __ldcg(probe.wp);   // tested one drain later: the L2 latency overlaps the hashing in between
+        probe.pend = true;
+    };
 
     for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < B.n_records; r0 += gridDim.x * blockDim.x) {
         const uint32_t rec = r0 + lane_id;
@@ -60,9 +100,6 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, Ba
         uint64_t seq_cur = ldu64(seqp), q_lo = ldu64(qualp), q_hi = ldu64(qualp + 8);
         uint64_t hist1 = 0, hist2 = 0;
         uint32_t run = 0;
-        bool pend = false;
-        uint32_t* pwp = nullptr;
-        uint32_t psh = 0, pold = 0;
         const uint32_t nchunks = (maxL + 15u) >> 4;
         for (uint32_t c = 0; c < nchunks; ++c) {
             // prefetch the next chunk of both streams (reads past a short record stay inside the padded batch)
@@ -72,6 +109,7 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, Ba
 #pragma unroll
             for (uint32_t j = 0; j < 16; ++j) {
                 const uint32_t i = c * 16 + j;
+                bool emit = false;
                 if (i < Ls) {
                     const uint32_t nin = (uint32_t)(seq_cur >> (4 * (j ^ 1))) & 15u;
                     const uint32_t nout = has_out ? ((uint32_t)(hist2 >> (4 * (j ^ 1))) & 15u) : 16u;
@@ -88,28 +126,21 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, Ba
                     thi = (xh >> 1) | (xl << 63);
                     const bool valid = (nin != 15u) && ((int8_t)(q + 33u) >= (int8_t)q_thresh);
                     run = valid ? run + 1u : 0u;
-                    if (pend) {  // finish the probe issued for the previous k-mer
-                        while (((pold >> psh) & 15u) != 15u) {
-                            const uint32_t assumed = pold;
-                            pold = atomicCAS(pwp, assumed, assumed + (1u << psh));
-                            if (pold == assumed) break;
-                        }
-                        pend = false;
-                    }
-                    if (run >= 32u) {
-                        const uint64_t hv = hlo ^ tlo;
-                        ++my_count;
-                        atomicAdd(sm + ((uint32_t)hv & f2mask), 1u);
-                        uint32_t w = hv ? (uint32_t)(__ffsll((long long)hv) - 1) : 63u;
-                        if (w > 31u) w = 31u;
-                        const uint64_t index = (hv >> (w + 1u)) & idx_mask;
-                        pwp = sk + w * words_per_level + (uint32_t)(index >> 3);
-                        psh = ((uint32_t)index & 7u) * 4u;
-                        pold = __ldcg(pwp);
-                        pend = true;
+                    emit = run >= 32u;
+                }
+                const uint32_t em = __ballot_sync(0xFFFFFFFFu, emit);
+                if (em) {  // warp-uniform
+                    if (emit) queue[qn + __popc(em & lt_mask)] = hlo ^ tlo;
+                    const uint32_t n = __popc(em);
+                    qn += n;
+                    warp_count += n;
+                    if (qn >= 32u) {
+                        __syncwarp();
+                        qn -= 32u;
+                        probe_issue(queue[qn + lane_id]);
+                        __syncwarp();
                     }
                 }
-                __syncwarp();
             }
             hist2 = hist1;
             hist1 = seq_cur;
@@ -117,17 +148,11 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, Ba
             q_lo = q_lo_next;
             q_hi = q_hi_next;
         }
-        if (pend) {
-            while (((pold >> psh) & 15u) != 15u) {
-                const uint32_t assumed = pold;
-                pold = atomicCAS(pwp, assumed, assumed + (1u << psh));
-                if (pold == assumed) break;
-            }
-        }
-        __syncwarp();
     }
-    for (int o = 16; o > 0; o >>= 1) my_count += __shfl_xor_sync(0xFFFFFFFFu, my_count, o);
-    if ((threadIdx.x & 31u) == 0 && my_count) atomicAdd((unsigned long long*)G, my_count);
+    __syncwarp();
+    if (lane_id < qn) probe_issue(queue[lane_id]);  // what is left in the queue
+    probe.finish();
+    if (lane_id == 0 && warp_count) atomicAdd((unsigned long long*)G, warp_count);
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < L.f2size; i += blockDim.x) {
         uint32_t v = sm[i];

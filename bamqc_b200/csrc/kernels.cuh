@@ -251,20 +251,23 @@ namespace bqc {
 
 // ------------------------------------------------------------------------------------------------
 // k_eightmer: OverallNumbers::count8mers (src/OverallNumbers.hpp:137-168)
-// CTA b owns half (b & 1) of the 65536-bin table in shared memory and walks record slab (b >> 1).
+// The whole 65536-bin table of a CTA lives in shared memory as 16-bit counters, two per 32-bit word (128 KB), so
+// every record is read once.  Overflow is exact: an increment is a 32-bit atomicAdd whose return value shows a
+// field that was 0xFFFF; the wrap is credited to the 64-bit global bin at once (+65536) and, for the low field,
+// the carry that leaked into the neighbouring high field is taken back from ITS global bin (-1 mod 2^64).  The
+// final flush adds the 16-bit residues.  All of it is commutative modular arithmetic, so the sums are exact.
 // ------------------------------------------------------------------------------------------------
 static const uint32_t kEightThreads = 1024;
 __global__ void __launch_bounds__(kEightThreads, 1) k_eightmer(EngineView E, BatchView B, uint32_t lane) {
-    extern __shared__ uint32_t sm[];  // 32768 bins
+    extern __shared__ uint32_t sm[];  // 32768 words = 65536 x u16
     for (uint32_t i = threadIdx.x; i < 32768u; i += blockDim.x) sm[i] = 0;
     __syncthreads();
-    const uint32_t half = blockIdx.x & 1u;
-    const uint32_t slab = blockIdx.x >> 1, nslab = gridDim.x >> 1;
+    unsigned long long* g = (unsigned long long*)(E.counters + (uint64_t)lane * E.L.lane_stride + E.L.o_eightmer);
     // 2-bit codes per BAM nibble: forward C(2)->1 G(4)->2 T(8)->3 else 0; reverse-complement view
     // A(1)->3 C(2)->2 G(4)->1 else 0  (char->Dna conversion of the complemented char, R5/R7)
     const uint32_t LUTF = (1u << (2 * 2)) | (2u << (2 * 4)) | (3u << (2 * 8));
     const uint32_t LUTR = (3u << (2 * 1)) | (2u << (2 * 2)) | (1u << (2 * 4));
-    for (uint32_t rec = slab * blockDim.x + threadIdx.x; rec < B.n_records; rec += nslab * blockDim.x) {
+    for (uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x; rec < B.n_records; rec += gridDim.x * blockDim.x) {
         if (B.rec_lane && B.rec_lane[rec] != lane) continue;
         const uint32_t off = B.offsets[rec];
         RecHdr h;
@@ -274,22 +277,35 @@ __global__ void __launch_bounds__(kEightThreads, 1) k_eightmer(EngineView E, Bat
         if (Ls < 8u) continue;
         const bool rc = (h.flag & 0x10u) != 0;
         const uint8_t* seqp = h.p + h.o_seq;
+        const uint32_t lut = rc ? LUTR : LUTF;
         uint32_t code = 0, since_n = 0;
         uint64_t seqw = 0;
         for (uint32_t i = 0; i < Ls; ++i) {
-            if ((i & 15u) == 0) seqw = ldu64(seqp + (i >> 1));
-            uint32_t nb = nib_of(seqw, i & 15u);
+            if ((i & 15u) == 0) seqw = NibStream::swap_nibbles(ldu64(seqp + (i >> 1)));  // next base in the low nibble
+            const uint32_t nb = (uint32_t)seqw & 15u;
+            seqw >>= 4;
             since_n = (nb == 15u) ? 0u : since_n + 1u;
-            if (!rc) code = ((code << 2) | ((LUTF >> (2 * nb)) & 3u)) & 0xFFFFu;
-            else code = (code >> 2) | (((LUTR >> (2 * nb)) & 3u) << 14);
-            if (i >= 7u && since_n >= 8u && (code >> 15) == half) atomicAdd(sm + (code & 32767u), 1u);
+            const uint32_t c2 = (lut >> (2 * nb)) & 3u;
+            // forward reads roll the code left; reverse reads roll the reverse-complement code from the other end
+            code = rc ? ((code >> 2) | (c2 << 14)) : (((code << 2) | c2) & 0xFFFFu);
+            if (i >= 7u && since_n >= 8u) {
+                const uint32_t sh = (code & 1u) << 4;
+                const uint32_t old = atomicAdd(sm + (code >> 1), 1u << sh);
+                if (((old >> sh) & 0xFFFFu) == 0xFFFFu) {  // this increment wrapped the 16-bit field
+                    atomicAdd(g + code, 65536ULL);
+                    if (sh == 0u) {                       // the carry went into the high field (bin code + 1)
+                        atomicAdd(g + code + 1u, ~0ULL);
+                        if (old == 0xFFFFFFFFu) atomicAdd(g + code + 1u, 65536ULL);  // and wrapped that one too
+                    }
+                }
+            }
         }
     }
     __syncthreads();
-    uint64_t* g = E.counters + (uint64_t)lane * E.L.lane_stride + E.L.o_eightmer + half * 32768u;
     for (uint32_t i = threadIdx.x; i < 32768u; i += blockDim.x) {
-        uint32_t v = sm[i];
-        if (v) atomicAdd((unsigned long long*)(g + i), (unsigned long long)v);
+        const uint32_t v = sm[i];
+        if (v & 0xFFFFu) atomicAdd(g + 2u * i, (unsigned long long)(v & 0xFFFFu));
+        if (v >> 16) atomicAdd(g + 2u * i + 1u, (unsigned long long)(v >> 16));
     }
 }
 
@@ -456,16 +472,16 @@ __global__ void __launch_bounds__(256) k_cov_scatter(EngineView E, BatchView B, 
     }
 }
 
-// Window flush = one pass over the ring range: single-pass prefix sum with decoupled look-back
-// (tile aggregate / inclusive-prefix flags), fused with the min(depth,100) histogram and the re-zeroing of
-// the ring.  A byte map marks the 32-entry granules that received events; untouched granules are neither
-// read nor written (their depth is the running prefix), so sparse coverage costs traffic proportional to the
-// reads, dense coverage 8 bytes per genome position.  16-byte vector accesses, streaming cache hints.
-static const uint32_t kCovThreads = 256;                // small CTAs: the look-back of one tile stalls only 8 warps
-static const uint32_t kCovTile = kCovThreads * 8;     // ring entries per tile (8 per thread)
+// Window flush = one pass over the ring range: single-pass prefix sum with decoupled look-back (tile aggregate /
+// inclusive-prefix flags), fused with the min(depth,100) histogram and the re-zeroing of the ring.  One thread owns
+// one 32-entry granule (= one byte of the touch map written by the scatter kernel): an untouched granule is neither
+// read nor written (its 32 positions have the running depth), a touched one is read with eight 16-byte loads.  The
+// pass is bound by the latency of the look-back chain per tile, so tiles are large (8192 positions).
+static const uint32_t kCovThreads = 256;
+static const uint32_t kCovTile = kCovThreads * 32;   // ring entries per tile
 static const uint32_t kTileAggregate = 1u, kTileInclusive = 2u;
-// [start, start+len) is the range to flush (ring indices, multiples of 8); tiles are aligned to 32 entries in
-// ring index space: lead = start & 31 entries of the first granule lie before the range.
+// [start, start+len) is the range to flush (ring indices, multiples of 8); tiles are aligned to granules in ring
+// index space: lead = start & 31 entries of the first granule lie before the range.
 __global__ void __launch_bounds__(kCovThreads) k_cov_flush(uint32_t* ring, uint8_t* touch, uint32_t ring_mask, uint32_t start, uint64_t len, uint32_t* carry,
                                                            unsigned long long* tile_state, uint32_t* ticket, unsigned long long* poscov) {
     __shared__ uint32_t hist[128];
@@ -482,23 +498,26 @@ __global__ void __launch_bounds__(kCovThreads) k_cov_flush(uint32_t* ring, uint8
         __syncthreads();
         const uint64_t tile = s_tile;
         if (tile >= ntiles) break;
-        const uint64_t i0 = tile * kCovTile + 8ull * threadIdx.x;    // entry index relative to astart
-        const bool inside = i0 >= lead && i0 < alen;                   // range ends are multiples of 8: all or nothing
-        const uint32_t ridx = (astart + (uint32_t)i0) & ring_mask;
+        const uint64_t g0 = tile * kCovTile + 32ull * threadIdx.x;   // first entry of this thread's granule, relative to astart
+        // part of the granule inside the range, as entry offsets [ka, kb) within the granule (multiples of 8)
+        const uint32_t ka = g0 < lead ? min(32u, (uint32_t)(lead - g0)) : 0u;
+        const uint32_t kb = g0 >= alen ? 0u : (uint32_t)min((uint64_t)32, alen - g0);
+        const bool inside = ka < kb;
+        const uint32_t ridx = (astart + (uint32_t)g0) & ring_mask;
         const uint32_t gidx = ridx >> 5;
         const bool touched = inside && touch[gidx] != 0;
-        uint32_t v[8];
-        if (touched) {
-            uint4 a = __ldcs(reinterpret_cast<const uint4*>(ring + ridx));
-            uint4 b = __ldcs(reinterpret_cast<const uint4*>(ring + ridx + 4));
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
-#pragma unroll
-            for (uint32_t j = 0; j < 8; ++j) v[j] = 0u;
-        }
+        uint32_t v[32];
         uint32_t acc = 0;
+        if (touched) {
+            const uint4* src = reinterpret_cast<const uint4*>(ring + ridx);
 #pragma unroll
-        for (uint32_t j = 0; j < 8; ++j) acc += v[j];
+            for (uint32_t q = 0; q < 8; ++q) {
+                uint4 a = make_uint4(0, 0, 0, 0);
+                if (4 * q >= ka && 4 * q < kb) a = __ldcs(src + q);   // streamed once: do not keep in L2
+                v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+                acc += a.x + a.y + a.z + a.w;
+            }
+        }
         uint32_t incl = acc;
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -552,23 +571,29 @@ __global__ void __launch_bounds__(kCovThreads) k_cov_flush(uint32_t* ring, uint8
         uint32_t depth = s_prefix + wsum[threadIdx.x >> 5] + (incl - acc);
         if (inside) {
             if (touched) {
-                uint32_t zeros = 0;
+                // the depth changes only at events: one histogram update per run of equal depth
+                uint32_t runlen = 0;
 #pragma unroll
-                for (uint32_t j = 0; j < 8; ++j) {
-                    depth += v[j];
-                    if (depth == 0) ++zeros;
-                    else atomicAdd(hist + min(depth, 100u), 1u);
+                for (uint32_t k = 0; k < 32; ++k) {
+                    if (k >= ka && k < kb) {
+                        if (v[k] != 0u) {
+                            if (runlen) atomicAdd(hist + min(depth, 100u), runlen);
+                            runlen = 0;
+                            depth += v[k];
+                        }
+                        ++runlen;
+                    }
                 }
-                if (zeros) atomicAdd(hist, zeros);
-                __stcs(reinterpret_cast<uint4*>(ring + ridx), make_uint4(0, 0, 0, 0));
-                __stcs(reinterpret_cast<uint4*>(ring + ridx + 4), make_uint4(0, 0, 0, 0));
+                if (runlen) atomicAdd(hist + min(depth, 100u), runlen);
+                uint4* dst = reinterpret_cast<uint4*>(ring + ridx);
+#pragma unroll
+                for (uint32_t q = 0; q < 8; ++q)
+                    if (4 * q >= ka && 4 * q < kb) __stcs(dst + q, make_uint4(0, 0, 0, 0));
+                if (kb == 32u) touch[gidx] = 0;   // the rest of a granule cut by the end of the range is flushed later
             } else {
-                atomicAdd(hist + min(depth, 100u), 8u);  // no events in this granule: constant depth
+                atomicAdd(hist + min(depth, 100u), kb - ka);  // no events in this granule: constant depth
             }
         }
-        // clear the map byte once the granule's last entry has been flushed (4 threads share a granule; entries
-        // of the granule that precede the range were flushed by the previous call)
-        if ((threadIdx.x & 3u) == 3u && inside && touch[gidx]) touch[gidx] = 0;
         __syncthreads();
     }
     if (threadIdx.x < 101 && hist[threadIdx.x]) atomicAdd(poscov + threadIdx.x, (unsigned long long)hist[threadIdx.x]);

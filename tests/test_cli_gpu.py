@@ -144,3 +144,21 @@ def test_multi_batch_streaming_with_small_staging(tmp_path):
     eng.close()
     diffs = util.diff_bamqc(tmp_path / "o.bamqc", tmp_path / "g.bamqc")
     assert not diffs, "\n".join(diffs)
+
+
+def test_homopolymer_reads_overflow_the_16_bit_eightmer_counters(tmp_path):
+    """k_eightmer keeps 16-bit counters in shared memory: poly-A / poly-T / poly-C reads push single bins far past
+    65535 inside one CTA (wrap of a low field with its carry into the neighbour, wrap of a high field), and the
+    low-quality stretches exercise the queued sketch probes."""
+    recs = []
+    pos = 100
+    for i in range(1800):
+        base = "ATC"[i % 3]
+        pos += 7
+        qual = [37] * 150
+        if i % 5 == 0:
+            qual[40] = 2
+        flag = 0x1 | 0x2 | (0x10 if i % 4 == 1 else 0x20) | (0x40 if i % 2 == 0 else 0x80)
+        recs.append(util.bam_record(name=f"h{i}", flag=flag, rid=0, pos=pos, mapq=60, cigar=((150, "M"),), seq=base * 150, qual=qual,
+                                    nrid=0, npos=pos + 200, tlen=350 if i % 2 == 0 else -350))
+    _against_oracle(tmp_path, util.bam_stream(recs))
