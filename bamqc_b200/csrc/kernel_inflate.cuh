@@ -286,9 +286,24 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
                 }
                 br.drop(e & 15u);
                 if (!(e & 0x300u)) {  // literal
-                    if (pos >= isize) { ok = false; break; }
-                    if (lane == 0) o[pos] = (uint8_t)(e >> 16);
-                    ++pos;
+                    // Literals come in runs: after a refill the buffer holds >= 32 bits, enough for two more codes of
+                    // the primary table, so up to three literals are taken per refill / loop trip.
+                    uint32_t b0 = e >> 16, nl = 1;
+                    uint32_t e2 = T.lit[br.peek(kLitBits)];
+                    if ((e2 & 15u) && !(e2 & 0x300u)) {
+                        br.drop(e2 & 15u);
+                        b0 |= (e2 >> 16) << 8;
+                        nl = 2;
+                        e2 = T.lit[br.peek(kLitBits)];
+                        if ((e2 & 15u) && (e2 & 15u) <= br.cnt && !(e2 & 0x300u)) {  // (the first code may have been a long one)
+                            br.drop(e2 & 15u);
+                            b0 |= (e2 >> 16) << 16;
+                            nl = 3;
+                        }
+                    }
+                    if (pos + nl > isize) { ok = false; break; }
+                    if (lane < nl) o[pos + lane] = (uint8_t)(b0 >> (8 * lane));
+                    pos += nl;
                     continue;
                 }
                 if (e & 0x200u) {     // end of block, or a symbol that must not occur
@@ -303,22 +318,28 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
                     if (!d) { ok = false; break; }
                 }
                 br.drop(d & 15u);
-                if (d & 0x200u) { ok = false; break; }
                 const uint32_t dist = (d >> 16) + br.take((d >> 4) & 15u);
-                if (dist > pos || pos + len > isize) { ok = false; break; }
+                if ((d & 0x200u) || dist > pos || pos + len > isize) { ok = false; break; }
                 // The copy is software-pipelined: the last step of a match is loaded now and stored when the
                 // next match arrives (or at the end of the BGZF block), so the L2 round trip of the load overlaps
                 // the decoding of the following symbols instead of stalling the warp at the store.
                 if (pend != kNone) { o[pend] = (uint8_t)pend_val; pend = kNone; }
                 __syncwarp(gmask);  // the bytes the match refers to were stored by other lanes
                 const uint32_t sp = pos - dist;
-                uint32_t j = lane;
-                if (dist >= len) {
-                    for (; j + kGroup < len + lane; j += kGroup) o[pos + j] = o[sp + j];   // all but the last step (uniform trip count)
-                    if (j < len) { pend_val = o[sp + j]; pend = pos + j; }
-                } else {       // overlapping match: byte j repeats with period dist
-                    for (; j + kGroup < len + lane; j += kGroup) o[pos + j] = o[sp + j % dist];
-                    if (j < len) { pend_val = o[sp + j % dist]; pend = pos + j; }
+                if (len <= kGroup) {   // the common case: one step, no loop
+                    // an overlapping match repeats with period dist: lane j reads byte j mod dist (j < 32)
+                    uint32_t m = lane;
+                    if (dist < len) m = dist == 1u ? 0u : lane % dist;
+                    if (lane < len) { pend_val = o[sp + m]; pend = pos + lane; }
+                } else {
+                    uint32_t j = lane;
+                    if (dist >= len) {
+                        for (; j + kGroup < len + lane; j += kGroup) o[pos + j] = o[sp + j];   // all but the last step (uniform trip count)
+                        if (j < len) { pend_val = o[sp + j]; pend = pos + j; }
+                    } else {
+                        for (; j + kGroup < len + lane; j += kGroup) o[pos + j] = o[sp + j % dist];
+                        if (j < len) { pend_val = o[sp + j % dist]; pend = pos + j; }
+                    }
                 }
                 pos += len;
             }
