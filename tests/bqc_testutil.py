@@ -204,3 +204,64 @@ def bgzf_block_starts(comp):
         out.append(p)
         p += bsize + 1
     return out
+
+
+def bam_records_to_sam(stream_bytes):
+    """SAM text (header + alignment lines) of an uncompressed BAM byte stream (SAM/BAM specification 4.2)."""
+    b = bytes(stream_bytes)
+    assert b[:4] == b"BAM\1"
+    l_text = struct.unpack_from("<i", b, 4)[0]
+    text = b[8:8 + l_text].decode()
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<i", b, p)[0]
+    p += 4
+    names = []
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<i", b, p)[0]
+        names.append(b[p + 4:p + 4 + l_name - 1].decode())
+        p += 4 + l_name + 4
+    lines = []
+    while p + 4 <= len(b):
+        bs = struct.unpack_from("<i", b, p)[0]
+        r = b[p + 4:p + 4 + bs]
+        p += 4 + bs
+        rid, pos, l_name, mapq, _bin, n_cig, flag, l_seq, nrid, npos, tlen = struct.unpack_from("<iiBBHHHiiii", r, 0)
+        q = 32
+        name = r[q:q + l_name - 1].decode()
+        q += l_name
+        cig = ""
+        for _ in range(n_cig):
+            c = struct.unpack_from("<I", r, q)[0]
+            cig += "%d%s" % (c >> 4, CIGAR_OPS[c & 15])
+            q += 4
+        seq = "".join(NT16[(r[q + i // 2] >> (4 if i % 2 == 0 else 0)) & 15] for i in range(l_seq))
+        q += (l_seq + 1) // 2
+        qual = "".join(chr(33 + x) for x in r[q:q + l_seq])
+        q += l_seq
+        tags = []
+        while q + 3 <= len(r):
+            key, ty = r[q:q + 2].decode(), chr(r[q + 2])
+            q += 3
+            if ty == "A":
+                tags.append(f"{key}:A:{chr(r[q])}"); q += 1
+            elif ty in "cCsSiI":
+                fmt = {"c": "b", "C": "B", "s": "h", "S": "H", "i": "i", "I": "I"}[ty]
+                v = struct.unpack_from("<" + fmt, r, q)[0]
+                tags.append(f"{key}:i:{v}"); q += struct.calcsize(fmt)
+            elif ty == "f":
+                tags.append(f"{key}:f:{struct.unpack_from('<f', r, q)[0]!r}"); q += 4
+            elif ty in "ZH":
+                e = r.index(b"\0", q)
+                tags.append(f"{key}:{ty}:{r[q:e].decode()}"); q = e + 1
+            elif ty == "B":
+                sub = chr(r[q]); cnt = struct.unpack_from("<i", r, q + 1)[0]
+                fmt = {"c": "b", "C": "B", "s": "h", "S": "H", "i": "i", "I": "I", "f": "f"}[sub]
+                vals = struct.unpack_from("<%d%s" % (cnt, fmt), r, q + 5)
+                tags.append(f"{key}:B:{sub}," + ",".join(repr(v) for v in vals)); q += 5 + cnt * struct.calcsize(fmt)
+            else:
+                raise ValueError(ty)
+        rn = names[rid] if rid >= 0 else "*"
+        nn = "*" if nrid < 0 else ("=" if nrid == rid else names[nrid])
+        lines.append("\t".join([name, str(flag), rn, str(pos + 1), str(mapq), cig or "*", nn, str(npos + 1), str(tlen), seq or "*",
+                                qual or "*"] + tags))
+    return text + "\n".join(lines) + ("\n" if lines else "")

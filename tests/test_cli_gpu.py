@@ -162,3 +162,35 @@ def test_homopolymer_reads_overflow_the_16_bit_eightmer_counters(tmp_path):
         recs.append(util.bam_record(name=f"h{i}", flag=flag, rid=0, pos=pos, mapq=60, cigar=((150, "M"),), seq=base * 150, qual=qual,
                                     nrid=0, npos=pos + 200, tlen=350 if i % 2 == 0 else -350))
     _against_oracle(tmp_path, util.bam_stream(recs))
+
+
+def test_sam_on_stdin_gives_the_same_bamqc_as_the_bam_file(tmp_path):
+    """`bamqualcheck ... -` (src/bamqualcheck.cpp:252-260): the same records as SAM text on stdin."""
+    import subprocess
+    from bamqc_b200 import synth
+    genome = util.golden_genome()
+    lib_ = synth.Library(seed=51, n_pairs=3000).stress()
+    records, offsets = synth.generate(genome, lib_)
+    fasta, bam = tmp_path / "ref.fa", tmp_path / "in.ubam"
+    genome.write_fasta(fasta)
+    synth.write_bam(bam, genome, lib_, records, int(offsets[-1]))
+    g1 = util.run_cli(["-r", fasta, "-c", "chr1,chr2", "-o", tmp_path / "bam.bamqc", bam])
+    assert g1.returncode == 0, g1.stderr
+    sam = util.bam_records_to_sam(open(bam, "rb").read())
+    exe = os.path.join(util.ROOT, "bamqc_b200", "bin", "bamqualcheck")
+    g2 = subprocess.run([exe, "-r", str(fasta), "-c", "chr1,chr2", "-o", str(tmp_path / "sam.bamqc"), "-"], input=sam, capture_output=True, text=True)
+    assert g2.returncode == 0, g2.stderr
+    assert "Reading from stdin" in g2.stderr
+    diffs = util.diff_bamqc(tmp_path / "bam.bamqc", tmp_path / "sam.bamqc")
+    assert not diffs, "\n".join(diffs)
+    # the odd tag types of the hand-made records survive the text round trip too
+    recs = [util.bam_record(name=f"s{i}", flag=0x63 if i % 2 == 0 else 0x93, pos=1000 + 3 * i, npos=1200, tlen=350,
+                            tags=(("RG", "Z", "L1"), ("XB", "B", ("S", [1, 2, 3])), ("NM", "i", i % 4), ("XF", "f", 1.5), ("AS", "s", 120), ("XA", "A", "q")))
+            for i in range(50)]
+    stream = util.bam_stream(recs)
+    open(tmp_path / "h.ubam", "wb").write(stream)
+    g3 = util.run_cli(["-r", fasta, "-c", "chr1", "-o", tmp_path / "h_bam.bamqc", tmp_path / "h.ubam"])
+    g4 = subprocess.run([exe, "-r", str(fasta), "-c", "chr1", "-o", str(tmp_path / "h_sam.bamqc"), "-"], input=util.bam_records_to_sam(stream),
+                        capture_output=True, text=True)
+    assert g3.returncode == 0 and g4.returncode == 0, g3.stderr + g4.stderr
+    assert not util.diff_bamqc(tmp_path / "h_bam.bamqc", tmp_path / "h_sam.bamqc")
