@@ -194,3 +194,31 @@ def test_sam_on_stdin_gives_the_same_bamqc_as_the_bam_file(tmp_path):
                         capture_output=True, text=True)
     assert g3.returncode == 0 and g4.returncode == 0, g3.stderr + g4.stderr
     assert not util.diff_bamqc(tmp_path / "h_bam.bamqc", tmp_path / "h_sam.bamqc")
+
+
+def test_records_larger_than_a_framing_window(tmp_path):
+    """Records of 6-20 KB (long aux arrays) between ordinary ones: speculation windows of 4 KiB without any record
+    start, chains that jump over several windows, through the raw-stream and the BGZF paths of the CLI."""
+    rng = random.Random(5)
+    recs = []
+    pos = 300
+    for i in range(600):
+        pos += rng.randint(1, 40)
+        big = rng.random() < 0.3
+        tags = [("RG", "Z", "L1"), ("NM", "C", rng.randint(0, 3)), ("AS", "C", 140)]
+        if big:
+            tags.insert(1, ("XK", "B", ("S", [rng.randint(0, 65535) for _ in range(rng.choice([3000, 5000, 10000]))])))
+        flag = 0x1 | 0x2 | (0x10 if i % 2 else 0x20) | (0x40 if i % 2 == 0 else 0x80)
+        recs.append(util.bam_record(name=f"b{i}", flag=flag, rid=0, pos=pos, mapq=60, nrid=0, npos=pos + 100, tlen=250 if i % 2 == 0 else -250,
+                                    tags=tuple(tags)))
+    stream = util.bam_stream(recs)
+    _against_oracle(tmp_path, stream)
+    # the same file BGZF-compressed: device inflate + device framing
+    from bamqc_b200 import synth
+    comp = synth.bgzf_compress(np.frombuffer(stream, dtype=np.uint8), level=6)
+    open(tmp_path / "in.bam", "wb").write(comp.tobytes())
+    fasta = tmp_path / "ref2.fa"
+    util.golden_genome().write_fasta(fasta)
+    g = util.run_cli(["-r", fasta, "-c", "chr1,chr2", "-o", tmp_path / "g2.bamqc", tmp_path / "in.bam"])
+    assert g.returncode == 0, g.stderr
+    assert not util.diff_bamqc(tmp_path / "g.bamqc", tmp_path / "g2.bamqc")
