@@ -446,7 +446,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     e->sketch_words_per_qk = 32ull * sksize * 2ull;
     e->staging_bytes = cfg->staging_bytes ? cfg->staging_bytes : (256ull << 20);
     if (e->staging_bytes > 0xF0000000ull) e->staging_bytes = 0xF0000000ull;
-    e->max_records_per_slot = e->staging_bytes / 40 + 16;  // a record is at least 36 bytes
+    e->max_records_per_slot = e->staging_bytes / 36 + 16;  // a record is at least 37 bytes (block_size + 32 fixed + a NUL name)
     e->blocks_per_slot = e->staging_bytes / 4096 + 4096;   // BGZF blocks per submission (larger inputs are split)
     e->ring_log2 = cfg->cov_ring_log2 ? cfg->cov_ring_log2 : 28;
     if (const char* v = getenv("BQC_STATS_BPS")) e->tune_stats_bps = atoi(v);

@@ -170,7 +170,7 @@ __device__ __noinline__ uint32_t inflate_decode_slow(const InflateTabs& T, uint6
         code |= (int)(bits & 1u);
         bits >>= 1;
         const int c = count[len];
-        if (code - c < first) {
+        if (code >= first && code - c < first) {  // (code >= first always holds for a valid code set)
             const uint32_t s = sorted[index + (code - first)];
             return len | (WHICH == 0 ? inflate_lit_entry(s) : WHICH == 1 ? inflate_dist_entry(s) : inflate_cl_entry(s));
         }
