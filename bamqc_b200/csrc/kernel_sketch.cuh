@@ -12,9 +12,22 @@
 
 namespace bqc {
 
-struct HashPairTable {  // [strand][in 0..15][out 0..16] -> {h.lo, h.hi, t.lo, t.hi}
-    ulonglong2 h[2][16][17];
-    ulonglong2 t[2][16][17];
+// Only the low 64 bits of both 128-bit states are ever used (hash = h.lo ^ ht.lo) and a base stays in the window
+// for k = 32 steps, so each state can be carried in 96 bits without changing a single hash:
+//   h  = XOR_j rotl^j(H[s_j]), j = 0..31: its low word takes at most the top 31 bits of H.hi, bits of H.lo that rotate
+//        up into hi would need 64 more steps to come back -> keep (lo, top 32 bits of hi); the 32-bit hi part simply
+//        shifts left and a base's contribution leaves it by itself after 32 steps;
+//   ht = XOR_m rotl^m(Ht[s]), m = 31..0, rotated RIGHT each step: bits come back into lo from the LOW end of hi ->
+//        keep (lo, low 32 bits of hi) with bits 0..32 of Ht.hi cleared in the table (they never reach lo in 32 steps).
+// One 32-byte row per (strand, in, out): {a_lo, b_lo, a_hi32, b_hi32} with a = H[in] ^ rotl_k(H[out]) and
+// b = rotl_k(Ht''[in]) ^ Ht''[out]; the generic k_sketch keeps the full 128-bit arithmetic of the reference.
+struct HashPairRow {
+    uint64_t a_lo, b_lo;
+    uint32_t a_hi, b_hi;
+    uint32_t pad[2];
+};
+struct HashPairTable {  // [strand][in 0..15][out 0..16]
+    HashPairRow row[2][16][17];
 };
 
 // Valid k-mer hashes are rare on low-quality stretches (one base under the cutoff silences the next k windows), so
@@ -48,11 +61,16 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, Ba
     for (uint32_t i = threadIdx.x; i < L.f2size; i += blockDim.x) sm[i] = 0;
     for (uint32_t i = threadIdx.x; i < 2 * 16 * 17; i += blockDim.x) {
         const uint32_t s = i / (16 * 17), in = (i / 17) % 16, out = i % 17;
-        // HT->t[s][which][n][0] = hi, [1] = lo; which: 0 h-in, 1 h-out, 2 t-in, 3 t-out
-        const uint64_t hlo = HT->t[s][0][in][1] ^ HT->t[s][1][out][1], hhi = HT->t[s][0][in][0] ^ HT->t[s][1][out][0];
-        const uint64_t tlo = HT->t[s][2][in][1] ^ HT->t[s][3][out][1], thi = HT->t[s][2][in][0] ^ HT->t[s][3][out][0];
-        PT->h[s][in][out] = make_ulonglong2(hlo, hhi);
-        PT->t[s][in][out] = make_ulonglong2(tlo, thi);
+        // HT->t[s][which][n][0] = hi, [1] = lo; which: 0 H[in], 1 rotl_k(H[out]), 2 rotl_k(Ht[in]), 3 Ht[out]
+        // (rotl_32 swaps and mixes the halves: rotl_32(X).lo = X.lo << 32 | X.hi >> 32, .hi = X.hi << 32 | X.lo >> 32)
+        HashPairRow r;
+        r.a_lo = HT->t[s][0][in][1] ^ HT->t[s][1][out][1];
+        r.a_hi = (uint32_t)(HT->t[s][0][in][0] >> 32);                 // top 32 bits of H[in].hi; the out term has none
+        // Ht'' = Ht with hi bits 0..32 cleared: rotl_32(Ht'')[in].lo differs from the stored rotl_32(Ht)[in].lo in bit 0
+        r.b_lo = (HT->t[s][2][in][1] & ~1ULL) ^ HT->t[s][3][out][1];
+        r.b_hi = (uint32_t)HT->t[s][2][in][0];                         // low 32 bits of rotl_32(Ht[in]).hi = Ht[in].lo >> 32
+        r.pad[0] = r.pad[1] = 0;
+        PT->row[s][in][out] = r;
     }
     __syncthreads();
     uint64_t* G = E.counters + (uint64_t)lane * L.lane_stride + L.o_qk + (uint64_t)SP.qk * L.qk_stride;
@@ -94,9 +112,9 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, Ba
         const uint32_t s = act ? ((h.flag >> 4) & 1u) : 0u;
         const uint8_t* seqp = act ? h.p + h.o_seq : B.bytes;
         const uint8_t* qualp = act ? h.p + h.o_qual : B.bytes;
-        const ulonglong2* rowh = &PT->h[s][0][0];
-        const ulonglong2* rowt = &PT->t[s][0][0];
-        uint64_t hlo = 0, hhi = 0, tlo = 0, thi = 0;
+        const HashPairRow* rows = &PT->row[s][0][0];
+        uint64_t hlo = 0, tlo = 0;
+        uint32_t hhi = 0, thi = 0;   // top 32 bits of h.hi, low 32 bits of ht.hi
         uint64_t seq_cur = ldu64(seqp), q_lo = ldu64(qualp), q_hi = ldu64(qualp + 8);
         uint64_t hist1 = 0, hist2 = 0;
         uint32_t run = 0;
@@ -115,15 +133,16 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, Ba
                     const uint32_t nout = has_out ? ((uint32_t)(hist2 >> (4 * (j ^ 1))) & 15u) : 16u;
                     const uint32_t q = (uint32_t)((j < 8 ? q_lo : q_hi) >> (8 * (j & 7))) & 255u;
                     const uint32_t ridx = nin * 17u + nout;
-                    const ulonglong2 a = rowh[ridx], b = rowt[ridx];
+                    const ulonglong2 ab = *reinterpret_cast<const ulonglong2*>(rows + ridx);        // a_lo, b_lo
+                    const uint2 abh = *reinterpret_cast<const uint2*>(&rows[ridx].a_hi);            // a_hi32, b_hi32
                     // h = rotl1(h) ^ H[in] ^ rotl_k(H[out])
-                    const uint64_t nh = (hhi << 1) | (hlo >> 63);
-                    hlo = ((hlo << 1) | (hhi >> 63)) ^ a.x;
-                    hhi = nh ^ a.y;
+                    hlo = ((hlo << 1) | (uint64_t)(hhi >> 31)) ^ ab.x;
+                    hhi = (hhi << 1) ^ abh.x;
                     // ht = rotr1(ht ^ rotl_k(Ht[in]) ^ Ht[out])
-                    const uint64_t xl = tlo ^ b.x, xh = thi ^ b.y;
-                    tlo = (xl >> 1) | (xh << 63);
-                    thi = (xh >> 1) | (xl << 63);
+                    const uint64_t xl = tlo ^ ab.y;
+                    const uint32_t xh = thi ^ abh.y;
+                    tlo = (xl >> 1) | ((uint64_t)xh << 63);
+                    thi = xh >> 1;
                     const bool valid = (nin != 15u) && ((int8_t)(q + 33u) >= (int8_t)q_thresh);
                     run = valid ? run + 1u : 0u;
                     emit = run >= 32u;
