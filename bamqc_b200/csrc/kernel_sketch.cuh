@@ -38,17 +38,16 @@ struct HashPairTable {  // [strand][in 0..15][out 0..16]
 static const uint32_t kSketchQueue = 64;  // entries per warp (at most 31 waiting + 32 new)
 
 struct SketchProbe {  // one in-flight probe per lane: the word was loaded, the 4-bit increment is still to be done
-    uint32_t* wp;
+    uint32_t word;       // index of the sketch word (kNone: nothing pending)
     uint32_t sh, old;
-    bool pend;
-    __device__ __forceinline__ void finish() {
-        if (pend) {
+    __device__ __forceinline__ void finish(uint32_t* sk) {
+        if (word != kNone) {
             while (((old >> sh) & 15u) != 15u) {  // 4-bit saturating increment
                 const uint32_t assumed = old;
-                old = atomicCAS(wp, assumed, assumed + (1u << sh));
+                old = atomicCAS(sk + word, assumed, assumed + (1u << sh));
                 if (old == assumed) break;
             }
-            pend = false;
+            word = kNone;
         }
     }
 };
@@ -79,23 +78,22 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, Ba
     const uint64_t idx_mask = (uint64_t)L.sk_size * 16ull - 1ull;
     const uint32_t f2mask = L.f2size - 1u;
     const int32_t q_thresh = SP.q_thresh;
-    unsigned long long warp_count = 0;               // k-mers hashed by this warp (same value in every lane)
+    uint32_t warp_count = 0;                         // k-mers hashed by this warp (same value in every lane; < 2^32 per launch)
     const uint32_t lane_id = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane_id) - 1u;
     uint32_t qn = 0;                                 // queued hashes of this warp (uniform)
-    SketchProbe probe = {nullptr, 0u, 0u, false};
+    SketchProbe probe = {kNone, 0u, 0u};
 
     // StreamCounter::operator() (src/kmerstream/StreamCounter.hpp:67-93) for one hash per participating lane
     auto probe_issue = [&](uint64_t hv) {
-        probe.finish();
+        probe.finish(sk);
         atomicAdd(sm + ((uint32_t)hv & f2mask), 1u);
         uint32_t w = hv ? (uint32_t)(__ffsll((long long)hv) - 1) : 63u;  // bitScanForward, 63 for 0
         if (w > 31u) w = 31u;
         const uint64_t index = (hv >> (w + 1u)) & idx_mask;
-        probe.wp = sk + w * words_per_level + (uint32_t)(index >> 3);
+        probe.word = w * words_per_level + (uint32_t)(index >> 3);
         probe.sh = ((uint32_t)index & 7u) * 4u;
-        probe.old = __ldcg(probe.wp);   // tested one drain later: the L2 latency overlaps the hashing in between
-        probe.pend = true;
+        probe.old = __ldcg(sk + probe.word);   // tested one drain later: the L2 latency overlaps the hashing in between
     };
 
     for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < B.n_records; r0 += gridDim.x * blockDim.x) {
@@ -170,8 +168,8 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, Ba
     }
     __syncwarp();
     if (lane_id < qn) probe_issue(queue[lane_id]);  // what is left in the queue
-    probe.finish();
-    if (lane_id == 0 && warp_count) atomicAdd((unsigned long long*)G, warp_count);
+    probe.finish(sk);
+    if (lane_id == 0 && warp_count) atomicAdd((unsigned long long*)G, (unsigned long long)warp_count);
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < L.f2size; i += blockDim.x) {
         uint32_t v = sm[i];
