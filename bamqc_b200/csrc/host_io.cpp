@@ -3,6 +3,10 @@
 // loading (replaces the streaming cursor of src/TripletCounting.hpp:60-104), the `.bamqc` writer
 // (src/bamqualcheck.cpp:156-233) and the `bamqualcheck` command line (src/CommandLineParser.hpp:43-149).
 // Everything here talks to the GPU engine only through include/bamqc_b200.h.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -211,55 +215,127 @@ struct bqc_fasta {
     std::vector<int64_t> lengths;
 };
 
+// FASTA -> 2 bits per base on all host threads (a human reference is 3 GB of text; one byte at a time on one thread it
+// took longer than the whole statistics pass of a 30x genome on the GPU).  The file is read once, records are found
+// with memchr, and every record's sequence bytes are cut into chunks: pass 1 counts the bases of each chunk (white
+// space skipped), a prefix sum gives the chunk's first base index, pass 2 packs.  Two chunks can share an output
+// byte at their boundary, so the first and last byte of a chunk are merged with atomic ORs.
+struct FastaLut {  // per byte: 0..3 = 2-bit code, 4 = white space (not a base)
+    uint8_t v[256];
+    FastaLut() {
+        for (int i = 0; i < 256; ++i) v[i] = 0;  // Dna5 -> Dna keeps the low two bits: N (4) -> A (0), SURVEY R6
+        v['C'] = v['c'] = 1;
+        v['G'] = v['g'] = 2;
+        v['T'] = v['t'] = 3;
+        v['\n'] = v['\r'] = v[' '] = v['\t'] = 4;
+    }
+};
+static const FastaLut kFastaLut;
+
 extern "C" bqc_fasta* bqc_fasta_open(const char* path) {
-    FILE* f = fopen(path, "rb");
-    if (!f) return nullptr;
-    bqc_fasta* fa = new bqc_fasta();
-    std::vector<char> buf(1 << 22);
-    bool in_header = false, at_line_start = true;
-    std::string hdr;
-    std::vector<uint8_t>* cur = nullptr;
-    int64_t len = 0;
-    auto finish_header = [&]() {
-        std::string s = hdr.substr(0, hdr.find(' '));
-        s = s.substr(0, s.find('\t'));  // src/TripletCounting.hpp:99-102
-        while (!s.empty() && (s.back() == '\r' || s.back() == '\n')) s.pop_back();
-        if (cur) fa->lengths.back() = len;
-        fa->names.push_back(s);
-        fa->packed.emplace_back();
-        fa->lengths.push_back(0);
-        cur = &fa->packed.back();
-        len = 0;
-    };
-    size_t got;
-    while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) {
-        for (size_t i = 0; i < got; ++i) {
-            char c = buf[i];
-            if (in_header) {
-                if (c == '\n') { in_header = false; at_line_start = true; finish_header(); }
-                else hdr.push_back(c);
-                continue;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return nullptr;
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return nullptr; }
+    const size_t n = (size_t)st.st_size;
+    const char* d = nullptr;
+    void* map = nullptr;
+    std::vector<char> fallback;
+    if (n) {
+        map = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        if (map == MAP_FAILED) {  // e.g. a pipe or an odd file system: read it
+            map = nullptr;
+            fallback.resize(n);
+            size_t got = 0;
+            while (got < n) {
+                const ssize_t r = read(fd, fallback.data() + got, n - got);
+                if (r <= 0) break;
+                got += (size_t)r;
             }
-            if (c == '\n') { at_line_start = true; continue; }
-            if (at_line_start && c == '>') { in_header = true; hdr.clear(); at_line_start = false; continue; }
-            at_line_start = false;
-            if (!cur || c == '\r' || c == ' ' || c == '\t') continue;
-            uint8_t code;
-            switch (c) {  // Dna5 -> Dna keeps the low two bits: N (4) -> A (0), SURVEY R6
-                case 'C': case 'c': code = 1; break;
-                case 'G': case 'g': code = 2; break;
-                case 'T': case 't': code = 3; break;
-                default: code = 0; break;
-            }
-            if ((len & 3) == 0) cur->push_back(0);
-            cur->back() |= (uint8_t)(code << ((len & 3) * 2));
-            ++len;
+            if (got != n) { close(fd); return nullptr; }
+            d = fallback.data();
+        } else {
+            d = (const char*)map;
         }
     }
-    if (in_header) finish_header();
-    if (cur) fa->lengths.back() = len;
-    fclose(f);
-    for (auto& p : fa->packed) p.resize(p.size() + 16, 0);
+    close(fd);
+    bqc_fasta* fa = new bqc_fasta();
+    // records: '>' at the start of a line opens a header line; the sequence runs to the next such '>'.  '>' is rare
+    // inside sequence text, so the scan is a memchr for '>' plus a look at the byte before it.
+    struct Rec { size_t seq_beg, seq_end; };
+    std::vector<Rec> recs;
+    size_t p = 0;
+    while (p < n) {
+        const char* q = (const char*)memchr(d + p, '>', n - p);
+        if (!q) break;
+        const size_t at = (size_t)(q - d);
+        if (at > 0 && d[at - 1] != '\n') { p = at + 1; continue; }  // not at a line start: an ordinary character
+        const char* eol = (const char*)memchr(d + at, '\n', n - at);
+        const size_t hend = eol ? (size_t)(eol - d) : n;
+        std::string hdr(d + at + 1, d + hend);
+        std::string name = hdr.substr(0, hdr.find(' '));
+        name = name.substr(0, name.find('\t'));  // src/TripletCounting.hpp:99-102
+        while (!name.empty() && (name.back() == '\r' || name.back() == '\n')) name.pop_back();
+        if (!recs.empty()) recs.back().seq_end = at;
+        fa->names.push_back(name);
+        recs.push_back({std::min(n, hend + 1), n});
+        p = std::min(n, hend + 1);
+    }
+    const unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    const uint8_t* lut = kFastaLut.v;
+    fa->packed.resize(recs.size());
+    fa->lengths.assign(recs.size(), 0);
+    for (size_t r = 0; r < recs.size(); ++r) {
+        const size_t beg = recs[r].seq_beg, end = recs[r].seq_end;
+        const size_t span = end > beg ? end - beg : 0;
+        const unsigned parts = (unsigned)std::max<size_t>(1, std::min<size_t>(T, span >> 20));
+        std::vector<size_t> count(parts + 1, 0);
+        auto bounds = [&](unsigned t) { return beg + span * t / parts; };
+        auto pass1 = [&](unsigned t) {
+            size_t c = 0;
+            for (size_t i = bounds(t), e = bounds(t + 1); i < e; ++i) c += lut[(unsigned char)d[i]] != 4;
+            count[t + 1] = c;
+        };
+        {
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < parts; ++t) th.emplace_back(pass1, t);
+            pass1(0);
+            for (auto& x : th) x.join();
+        }
+        for (unsigned t = 0; t < parts; ++t) count[t + 1] += count[t];
+        const size_t len = count[parts];
+        std::vector<uint8_t>& out = fa->packed[r];
+        out.assign((len + 3) / 4 + 16, 0);
+        fa->lengths[r] = (int64_t)len;
+        auto pass2 = [&](unsigned t) {
+            size_t k = count[t];
+            const size_t k_end = count[t + 1];
+            if (k == k_end) return;
+            const size_t first_byte = k >> 2, last_byte = (k_end - 1) >> 2;
+            uint8_t acc = 0;
+            size_t cur_byte = first_byte;
+            auto store = [&](size_t byte, uint8_t v) {
+                if (byte == first_byte || byte == last_byte) __atomic_fetch_or(&out[byte], v, __ATOMIC_RELAXED);  // may be shared with a neighbour chunk
+                else out[byte] = v;
+            };
+            for (size_t i = bounds(t), e = bounds(t + 1); i < e; ++i) {
+                const uint8_t code = lut[(unsigned char)d[i]];
+                if (code == 4) continue;
+                const size_t byte = k >> 2;
+                if (byte != cur_byte) { store(cur_byte, acc); acc = 0; cur_byte = byte; }
+                acc |= (uint8_t)(code << ((k & 3) * 2));
+                ++k;
+            }
+            store(cur_byte, acc);
+        };
+        {
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < parts; ++t) th.emplace_back(pass2, t);
+            pass2(0);
+            for (auto& x : th) x.join();
+        }
+    }
+    if (map) munmap(map, n);
     return fa;
 }
 extern "C" int64_t bqc_fasta_contig(bqc_fasta* f, const char* name, const uint8_t** packed) {

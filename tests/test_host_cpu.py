@@ -134,3 +134,66 @@ def test_shard_regions_have_reanchoring_gaps():
                     assert lo - prev_end[c] >= 5000  # > 2*vsize + read span: the next shard always re-anchors
                 prev_end[c] = hi
         assert all(prev_end[c] == lengths[c] for c in range(len(lengths)))
+
+
+def test_fasta_packer_matches_a_bytewise_restatement(tmp_path):
+    """bqc_fasta_open packs on all host threads (chunks of one record share boundary bytes): same result as the
+    byte-at-a-time rule -- '>' only at a line start opens a record, the name ends at the first blank/tab, every other
+    non-white character is a base, C/G/T (either case) are 1/2/3 and everything else (A, N, IUPAC, '>') is 0."""
+    import ctypes
+    import random
+    from bamqc_b200 import _lib
+    L = _lib.load_library()
+    rng = random.Random(11)
+
+    def seq(n, alphabet="ACGTacgtNnRY"):
+        return "".join(rng.choice(alphabet) for _ in range(n))
+
+    big = seq(2_500_003, "ACGT")  # several chunks per record
+    parts = ["junk before the first header\nACGT\n", ">chr1 description here\n"]
+    for i in range(0, len(big), 61):
+        parts.append(big[i:i + 61] + ("\r\n" if i % 7 == 0 else "\n"))
+    parts += [">chr2\tother\n", seq(70) + "\n", "AC>GT  \t" + seq(13) + "\n\n", seq(5), "\n>empty\n>last no newline\n" + seq(1_200_001, "ACGTN")]
+    text = "".join(parts)
+    path = tmp_path / "odd.fa"
+    path.write_bytes(text.encode())
+    # byte-wise restatement
+    want, cur, hdr, in_hdr, line_start = [], None, "", False, True
+    for c in text:
+        if in_hdr:
+            if c == "\n":
+                in_hdr, line_start = False, True
+                name = hdr.split(" ")[0].split("\t")[0].rstrip("\r\n")
+                cur = [name, []]
+                want.append(cur)
+            else:
+                hdr += c
+            continue
+        if c == "\n":
+            line_start = True
+            continue
+        if line_start and c == ">":
+            in_hdr, hdr, line_start = True, "", False
+            continue
+        line_start = False
+        if cur is None or c in "\r \t":
+            continue
+        cur[1].append({"C": 1, "c": 1, "G": 2, "g": 2, "T": 3, "t": 3}.get(c, 0))
+    if in_hdr:
+        want.append([hdr.split(" ")[0].split("\t")[0].rstrip("\r\n"), []])
+    fa = L.bqc_fasta_open(str(path).encode())
+    assert fa
+    try:
+        for name, codes in want:
+            ptr = ctypes.c_void_p()
+            n = L.bqc_fasta_contig(fa, name.encode(), ctypes.byref(ptr))
+            assert n == len(codes), (name, n, len(codes))
+            if n:
+                got = np.frombuffer((ctypes.c_uint8 * ((n + 3) // 4)).from_address(ptr.value), dtype=np.uint8)
+                exp = np.zeros((n + 3) // 4 * 4, dtype=np.uint8)
+                exp[:n] = codes
+                exp = exp.reshape(-1, 4)
+                packed = exp[:, 0] | (exp[:, 1] << 2) | (exp[:, 2] << 4) | (exp[:, 3] << 6)
+                assert np.array_equal(got, packed), name
+    finally:
+        L.bqc_fasta_close(fa)
