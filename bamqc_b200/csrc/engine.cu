@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -154,6 +155,9 @@ struct Slot {  // one half of the staging double buffer
     ScanMeta* d_meta = nullptr;
     uint32_t *d_ws = nullptr, *d_we = nullptr, *d_wc = nullptr, *d_ws2 = nullptr, *d_we2 = nullptr, *d_wc2 = nullptr, *d_bsum = nullptr, *d_bbase = nullptr;
     cudaEvent_t framed = nullptr, aux_done = nullptr;
+    cudaEvent_t tables_go = nullptr;   // compute-stream position before this buffer's table kernels (coverage waits for it)
+    cudaEvent_t cov_end = nullptr;     // this buffer's coverage kernels are done (recorded by the anchor thread)
+    bool cov_pending = false;          // cov_end has been recorded for the buffer in flight
     // device inflate (kernel_inflate.cuh)
     uint8_t* d_cin = nullptr;          // compressed BGZF bytes of the submission
     InflateBlock* h_blocks = nullptr;  // pinned
@@ -214,6 +218,12 @@ struct bqc_engine {
         bool must_align;   // the bytes must end on a record boundary (whole-record submissions, last stream chunk)
     };
     std::deque<Task> ingest;       // stream tasks whose H2D copy + framing kernels are enqueued, not yet launched
+    // the anchor thread takes the sequential coverage recurrence (host_scan_pass2, ~4 ms per 256 MB buffer) and the
+    // coverage launches of device-framed buffers off the commit thread, which then only enqueues copies and kernels
+    std::thread anchor_thread;
+    std::deque<Task> aq;
+    std::condition_variable acv;
+    bool abusy = false;
     int last_stream_slot = -1;     // slot of the previous stream submission (source of the carried partial record)
     bool device_framing = true;    // BQC_HOST_FRAMING=1 turns it off (A/B tests)
     bool trace = false;            // BQC_TRACE=1: per-buffer timings of the commit thread on stderr
@@ -228,7 +238,8 @@ struct bqc_engine {
     int tune_stats_bps = 0, tune_sketch_threads = 1024;  // BQC_STATS_BPS / BQC_SKETCH_THREADS (tuning knobs)
     int tune_cov_bps = 8;                                // BQC_COV_BPS: coverage CTAs per SM (upper bound)
     std::vector<CovState> cov;
-    uint64_t records_seen = 0, launches = 0, frames_repaired = 0;
+    uint64_t records_seen = 0, frames_repaired = 0;
+    std::atomic<uint64_t> launches{0};   // kernels launched (commit thread, anchor thread, caller)
     bool finished = false;
     std::string last_error;
     bqc_error_info host_error = {0, 0, {0}};
@@ -237,6 +248,7 @@ struct bqc_engine {
     // optional per-kernel-family timing (CUDA events on the compute stream)
     bool profiling = false;
     struct ProfEv { int family; cudaEvent_t a, b; };
+    std::mutex prof_m;             // ProfScope is used from the commit and the anchor thread
     std::vector<ProfEv> prof_pending;
     std::vector<cudaEvent_t> prof_pool;
     double prof_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -318,10 +330,12 @@ static void free_device_batch(DeviceBatch& d) {
 extern "C" void bqc_destroy(bqc_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
-    if (e->commit_thread.joinable()) {
+    if (e->commit_thread.joinable() || e->anchor_thread.joinable()) {
         { std::lock_guard<std::mutex> g(e->cm); e->cstop = true; }
         e->ccv.notify_all();
-        e->commit_thread.join();
+        if (e->commit_thread.joinable()) e->commit_thread.join();
+        e->acv.notify_all();
+        if (e->anchor_thread.joinable()) e->anchor_thread.join();
     }
     if (e->compute) cudaStreamSynchronize(e->compute);
     if (e->copy) cudaStreamSynchronize(e->copy);
@@ -342,6 +356,8 @@ extern "C" void bqc_destroy(bqc_engine* e) {
         if (s.done) cudaEventDestroy(s.done);
         if (s.framed) cudaEventDestroy(s.framed);
         if (s.aux_done) cudaEventDestroy(s.aux_done);
+        if (s.tables_go) cudaEventDestroy(s.tables_go);
+        if (s.cov_end) cudaEventDestroy(s.cov_end);
     }
     for (auto p : e->ref_bufs) cudaFree(p);
     cudaFree(e->d_counters);
@@ -403,7 +419,7 @@ extern "C" int bqc_reset(bqc_engine* e) {
     e->finished = false;
     e->have_results = false;
     e->host_error.code = 0;
-    for (auto& s : e->slots) s.in_flight = false;
+    for (auto& s : e->slots) { s.in_flight = false; s.cov_pending = false; }
     return 0;
 }
 
@@ -500,6 +516,8 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
             CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s.framed, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s.aux_done, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s.tables_go, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s.cov_end, cudaEventDisableTiming));
         }
         // opt in to large dynamic shared memory
         CU(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kInflateStreams * sizeof(InflateTabs))));
@@ -830,13 +848,17 @@ struct ProfScope {  // records an event pair around the launches of one kernel f
         if (!on) return;
         auto get = [&]() { cudaEvent_t x; if (e->prof_pool.empty()) cudaEventCreate(&x); else { x = e->prof_pool.back(); e->prof_pool.pop_back(); } return x; };
         ev.family = family;
-        ev.a = get();
-        ev.b = get();
+        {
+            std::lock_guard<std::mutex> g(e->prof_m);
+            ev.a = get();
+            ev.b = get();
+        }
         cudaEventRecord(ev.a, st);
     }
     ~ProfScope() {
         if (!on) return;
         cudaEventRecord(ev.b, st);
+        std::lock_guard<std::mutex> g(e->prof_m);
         e->prof_pending.push_back(ev);
     }
 };
@@ -1166,26 +1188,67 @@ static int stream_stage_b(bqc_engine* e, const bqc_engine::Task& t) {
         int rc = batch_launch_setup(e, d, BL);
         if (rc) return rc;
         CU(cudaStreamWaitEvent(e->compute, s.framed, 0));
-        CU(cudaEventRecord(e->cov_go, e->compute));  // coverage of this batch does not overtake the previous batch's tables
+        CU(cudaEventRecord(s.tables_go, e->compute));  // coverage of this batch does not overtake the previous batch's tables
         rc = launch_tables(e, d, BL);
         if (rc) return rc;
-        auto t_b2 = std::chrono::steady_clock::now();
-        CU(cudaEventSynchronize(s.aux_done));
-        auto t_b3 = std::chrono::steady_clock::now();
-        host_scan_pass2(e, s.h_meta, n, s.h_cov, nullptr, d.segs);
         if (e->trace) {
             auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-            fprintf(stderr, "[bqc trace] slot %d: repaired %u, wait framed %.2f ms, launch tables %.2f ms, wait meta %.2f ms, pass2 %.2f ms, n=%llu segs=%zu\n", t.slot, fr.repaired, ms(t_b0, t_b1), ms(t_b1, t_b2), ms(t_b2, t_b3),
-                    ms(t_b3, std::chrono::steady_clock::now()), (unsigned long long)n, d.segs.size());
+            fprintf(stderr, "[bqc trace] slot %d: repaired %u, wait framed %.2f ms, launch tables %.2f ms, n=%llu\n", t.slot, fr.repaired, ms(t_b0, t_b1),
+                    ms(t_b1, std::chrono::steady_clock::now()), (unsigned long long)n);
         }
-        d.cov_src = s.h_cov;
-        CU(cudaStreamWaitEvent(e->covs, e->cov_go, 0));
-        rc = launch_cov(e, d, BL);
-        if (rc) return rc;
-        CU(cudaStreamWaitEvent(e->compute, e->cov_done, 0));
     }
     CU(cudaEventRecord(s.done, e->compute));
     return 0;
+}
+
+// anchor thread: the sequential coverage recurrence over the (rid, pos) pairs of a device-framed buffer, then its
+// coverage kernels (own stream; they wait for the data and for the position of the compute stream before this buffer)
+static int anchor_stage(bqc_engine* e, const bqc_engine::Task& t) {
+    Slot& s = e->slots[t.slot];
+    DeviceBatch& d = s.dev;
+    const uint64_t n = d.n_records;
+    auto t0 = std::chrono::steady_clock::now();
+    CU(cudaEventSynchronize(s.aux_done));
+    auto t1 = std::chrono::steady_clock::now();
+    host_scan_pass2(e, s.h_meta, n, s.h_cov, nullptr, d.segs);
+    if (e->trace) {
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[bqc trace] slot %d (anchor): wait pairs %.2f ms, pass2 %.2f ms, segs=%zu\n", t.slot, ms(t0, t1), ms(t1, std::chrono::steady_clock::now()), d.segs.size());
+    }
+    d.cov_src = s.h_cov;
+    BatchLaunch BL;
+    int rc = batch_launch_setup(e, d, BL);
+    if (rc) return rc;
+    CU(cudaStreamWaitEvent(e->covs, s.tables_go, 0));
+    rc = launch_cov(e, d, BL);
+    if (rc) return rc;
+    CU(cudaEventRecord(s.cov_end, e->covs));
+    s.cov_pending = true;
+    return 0;
+}
+
+static void anchor_loop(bqc_engine* e) {
+    cudaSetDevice(e->cfg.device);
+    for (;;) {
+        bqc_engine::Task t;
+        {
+            std::unique_lock<std::mutex> g(e->cm);
+            e->acv.wait(g, [&] { return e->cstop || !e->aq.empty(); });
+            if (e->aq.empty()) return;
+            t = e->aq.front();
+            e->aq.pop_front();
+            e->abusy = true;
+        }
+        int rc = e->async_rc ? e->async_rc : anchor_stage(e, t);
+        {
+            std::lock_guard<std::mutex> g(e->cm);
+            e->slots[t.slot].queued = false;
+            e->slots[t.slot].in_flight = rc == 0;
+            e->abusy = false;
+            if (rc && !e->async_rc) e->async_rc = rc;
+        }
+        e->ccv_idle.notify_all();
+    }
 }
 
 static void commit_loop(bqc_engine* e) {
@@ -1215,12 +1278,26 @@ static void commit_loop(bqc_engine* e) {
         int rc = e->async_rc;
         bool finished_slot = false;
         if (have_new) {
-            if (t.mode == 0) { if (!rc) rc = commit_task(e, t); finished_slot = true; }
+            if (t.mode == 0) {
+                {   // the host-framed path runs the recurrence here: wait until the anchor thread has caught up
+                    std::unique_lock<std::mutex> g(e->cm);
+                    e->ccv_idle.wait(g, [&] { return e->aq.empty() && !e->abusy; });
+                }
+                if (!rc) rc = commit_task(e, t);
+                finished_slot = true;
+            }
             else if (!rc) { rc = stream_stage_a(e, t); if (rc) finished_slot = true; }
             else finished_slot = true;
         } else if (have_old) {
             if (!rc) rc = stream_stage_b(e, t);
             finished_slot = true;
+            if (!rc && e->slots[t.slot].dev.n_records) {  // the anchor thread finishes the slot
+                finished_slot = false;
+                std::lock_guard<std::mutex> g(e->cm);
+                if (!e->anchor_thread.joinable()) e->anchor_thread = std::thread(anchor_loop, e);
+                e->aq.push_back(t);
+                e->acv.notify_all();
+            }
         }
         {
             std::lock_guard<std::mutex> g(e->cm);
@@ -1239,7 +1316,7 @@ static void commit_loop(bqc_engine* e) {
 // wait until the commit thread has enqueued everything handed to it; returns its sticky error
 static int drain_commits(bqc_engine* e) {
     std::unique_lock<std::mutex> g(e->cm);
-    e->ccv_idle.wait(g, [&] { return e->cq.empty() && e->ingest.empty() && !e->cbusy; });
+    e->ccv_idle.wait(g, [&] { return e->cq.empty() && e->ingest.empty() && !e->cbusy && e->aq.empty() && !e->abusy; });
     return e->async_rc;
 }
 
@@ -1250,6 +1327,7 @@ static int wait_slot(bqc_engine* e, Slot& s) {
     }
     if (s.in_flight) {
         CU(cudaEventSynchronize(s.done));
+        if (s.cov_pending) { CU(cudaEventSynchronize(s.cov_end)); s.cov_pending = false; }
         s.in_flight = false;
     }
     return 0;
