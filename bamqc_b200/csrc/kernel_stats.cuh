@@ -33,6 +33,13 @@ struct NibStream {
     }
 };
 
+__device__ __forceinline__ void red_shared_inc(uint32_t saddr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory");
+}
+__device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView B, uint32_t lane) {
     extern __shared__ uint32_t sm[];
     const StatsSmem S = stats_smem_layout(B.cycb, E.insert_smem);
@@ -111,10 +118,14 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
         __syncwarp();
         // ---------------------------------------------------------------- phase B: triplet walk (:195-236)
         if (do_trip) {
+            // The reference's loop visits the read positions of every match-like CIGAR run; the test at a position
+            // only looks at read bases p-1..p+1, QUAL[p] and reference bases c-1..c+1 with c - p constant inside a
+            // run.  Runs are enumerated exactly like the loop does (:201-212); inside a run the tests are evaluated
+            // 14 positions at a time on a 16-nibble window (swar.h), leaving one predicated shared atomic per position.
             const uint32_t* __restrict__ ref = E.ref[h.rid];
             const uint64_t reflen = E.ref_len[h.rid];
             const uint32_t refmax = (uint32_t)((reflen + 15) / 16) + 3u;  // last allocated word (reads that overhang the contig)
-            uint32_t* tri = sm + S.tri + ((rc ? 2u : 0u) + (isfirst ? 0u : 1u)) * 4u;
+            const uint32_t tri_s = (uint32_t)__cvta_generic_to_shared(sm + S.tri + ((rc ? 2u : 0u) + (isfirst ? 0u : 1u)) * 4u);
             const uint8_t* seqp = h.p + h.o_seq;
             const uint8_t* qualp = h.p + h.o_qual;
             uint32_t it = 0;
@@ -122,12 +133,8 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
             uint32_t chromPos = (uint32_t)h.pos + 1u;
             uint32_t readPos = 1;
             const uint32_t last = Ls - 1;
-            bool reload = true, ok = true;
-            NibStream ns;                             // positioned on readPos + 1
-            uint32_t nprev = 0, ncur = 0, rprev = 0, rcur = 0;
-            uint64_t qw = 0;                          // QUAL chunk, current byte in the low 8 bits
-            uint32_t rw = 0;                          // reference chunk (16 bases), next base in the low 2 bits
-            for (; readPos < last; ++readPos, ++chromPos, --cc) {
+            bool ok = true;
+            while (readPos < last) {
                 if (cc == 0) {
                     do {
                         ++it;
@@ -139,40 +146,41 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
                         else cc = n;
                     } while (cc == 0);
                     if (!ok || readPos >= last) break;
-                    reload = true;
                 }
-                if (reload) {  // (re)position the three streams: read bases, qualities, reference bases
-                    ns.seek(seqp, readPos - 1);
-                    nprev = ns.get(readPos - 1);
-                    ncur = ns.get(readPos);
-                    qw = ldu64(qualp + (readPos & ~7u)) >> (8 * (readPos & 7u));
-                    const uint32_t cp = chromPos - 1;
-                    rw = __ldg(ref + min(cp >> 4, refmax)) >> (2 * (cp & 15u));
-                    rprev = rw & 3u;
-                    rw >>= 2;
-                    if (((cp + 1) & 15u) == 0) rw = __ldg(ref + min((cp + 1) >> 4, refmax));
-                    rcur = rw & 3u;
-                    rw >>= 2;
-                    reload = false;
-                } else if ((readPos & 7u) == 0) {
-                    qw = ldu64(qualp + readPos);
+                const uint32_t run = min(cc, last - readPos);
+                // positions [readPos, end) of this run lie inside the contig: chromPos + 2 <= reflen (:217-224)
+                const int64_t lim = (int64_t)reflen - 1 - (int64_t)chromPos + (int64_t)readPos;  // first p that fails
+                uint32_t end = readPos + run;
+                if (lim < (int64_t)end) end = lim > (int64_t)readPos ? (uint32_t)lim : readPos;
+                const uint32_t delta = chromPos - readPos;
+                for (uint32_t p = readPos; p < end;) {
+                    const uint32_t g = (p - 1u) & ~1u;                       // window = read positions g..g+15
+                    const uint64_t R = swar_swap_nibbles(ldu64(seqp + (g >> 1)));
+                    const uint64_t q0 = ldu64(qualp + g), q1 = ldu64(qualp + g + 8);
+                    const int32_t cg = (int32_t)(delta + g);                 // reference position of window base 0 (>= -1)
+                    const uint32_t cgc = cg < 0 ? 0u : (uint32_t)cg;
+                    const uint32_t wi = cgc >> 4;
+                    uint32_t F = __funnelshift_r(__ldg(ref + min(wi, refmax)), __ldg(ref + min(wi + 1u, refmax)), 2u * (cgc & 15u));
+                    if (cg < 0) F <<= 2;
+                    uint64_t T4, C4;
+                    swar_triplet_masks(R, F, T4, C4);
+                    const uint32_t jlo = p - g, jhi = min(end - g, 15u);      // centres jlo..jhi-1 of the window
+                    C4 &= ((1ULL << (4u * jhi)) - 1ULL) & ~((1ULL << (4u * jlo)) - 1ULL);
+                    const uint32_t qk[4] = {swar_q20((uint32_t)q0), swar_q20((uint32_t)(q0 >> 32)), swar_q20((uint32_t)q1), swar_q20((uint32_t)(q1 >> 32))};
+                    const uint32_t c_lo = (uint32_t)C4, c_hi = (uint32_t)(C4 >> 32), t_lo = (uint32_t)T4, t_hi = (uint32_t)(T4 >> 32);
+#pragma unroll
+                    for (uint32_t j = 1; j < 15; ++j) {
+                        const uint32_t cw = j < 8 ? c_lo : c_hi, tw = j < 8 ? t_lo : t_hi;
+                        const uint32_t cnt = (cw >> (4u * (j & 7u))) & (qk[j >> 2] >> (8u * (j & 3u) + 7u)) & 1u;
+                        const uint32_t ctx = (F >> (2u * (j - 1u))) & 63u;
+                        const uint32_t base = (tw >> (4u * (j & 7u))) & 3u;
+                        red_shared_add(tri_s + (ctx * 16u + base) * 4u, cnt);  // adds 0 where the position does not count: no branch
+                    }
+                    p = g + jhi;
                 }
-                if (((chromPos + 1) & 15u) == 0) rw = __ldg(ref + min((chromPos + 1) >> 4, refmax));
-                const uint32_t nnext = ns.get(readPos + 1);
-                const uint32_t rnext = rw & 3u;
-                rw >>= 2;
-                const uint32_t q = (uint32_t)qw & 255u;
-                qw >>= 8;
-                // quality >= '5' as signed chars, base and both flanks A/C/G/T, flanks equal to the reference
-                // context (char compare), context inside the contig
-                const uint32_t base = (uint32_t)(LUT_FWD >> (4 * ncur)) & 7u;
-                bool cnt = (int8_t)(q + 33u) >= (int8_t)53 && base != 4u && nprev == (1u << rprev) && nnext == (1u << rnext) &&
-                           (uint64_t)chromPos + 2 <= reflen;
-                if (cnt) atomicAdd(tri + ((rprev << 4) + (rcur << 2) + rnext) * 16u + base, 1u);
-                nprev = ncur;
-                ncur = nnext;
-                rprev = rcur;
-                rcur = rnext;
+                readPos += run;
+                chromPos += run;
+                cc -= run;
             }
         }
         __syncwarp();
@@ -181,28 +189,60 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
         const uint32_t maxL = __reduce_max_sync(0xFFFFFFFFu, myL);
         uint32_t cntN = 0, cntGC = 0, sumQ = 0;
         {
-            uint32_t* pc = sm + S.pc + mate * PC_ROWS * cycb;
+            // Eight bases per step.  Reverse reads are brought into cycle order first: __brev of the nibble word
+            // reverses the base order AND the bits of every nibble, which is the complement for the one-hot codes
+            // (R7); the quality bytes are byte-reversed.  Per word: Dna5 ordinals, N / GC counts and the quality
+            // sum come from swar.h; per base one increment of dnacount[d][cycle] and one add to qualcount[cycle].
+            const uint32_t rowb = cycb * 4u;
+            const uint32_t pc_s = (uint32_t)__cvta_generic_to_shared(sm + S.pc + mate * PC_ROWS * cycb);
             const uint8_t* seqp = live ? h.p + h.o_seq : B.bytes;
             const uint8_t* qualp = live ? h.p + h.o_qual : B.bytes;
-            const uint64_t lut = rc ? LUT_REV : LUT_FWD;
-            uint32_t cyc = rc ? Ls - 1u : 0u;
-            const uint32_t step = rc ? 0xFFFFFFFFu : 1u;
-            uint64_t seqw = 0, qualw = 0;
-            for (uint32_t i = 0; i < maxL; ++i) {
+            for (uint32_t i = 0; i < maxL; i += 8u) {
                 if (i < myL) {
-                    if ((i & 15u) == 0) seqw = NibStream::swap_nibbles(ldu64(seqp + (i >> 1)));
-                    if ((i & 7u) == 0) qualw = ldu64(qualp + i);
-                    const uint32_t nb = (uint32_t)seqw & 15u;
-                    seqw >>= 4;
-                    const uint32_t q = (uint32_t)qualw & 255u;
-                    qualw >>= 8;
-                    const uint32_t d = (uint32_t)(lut >> (4 * nb)) & 7u;
-                    atomicAdd(pc + d * cycb + cyc, 1u);
-                    atomicAdd(pc + PC_QUAL * cycb + cyc, q);
-                    cntN += (nb + 1u) >> 4;
-                    cntGC += (0x14u >> nb) & 1u;
-                    sumQ += q;
-                    cyc += step;
+                    const uint32_t v = min(8u, myL - i);                 // bases of this step
+                    uint32_t W = swar_swap_nibbles32(ldu32(seqp + (i >> 1)));
+                    uint64_t Q = ldu64(qualp + i);
+                    uint32_t qlo = (uint32_t)Q, qhi = (uint32_t)(Q >> 32);
+                    uint32_t ca = pc_s + 4u * i;                         // dnacount row 0 at the cycle of window base 0
+                    uint32_t jlo = 0, jhi = v;
+                    if (rc) {
+                        W = __brev(W);
+                        const uint32_t t = __byte_perm(qhi, 0u, 0x0123u);
+                        qhi = __byte_perm(qlo, 0u, 0x0123u);
+                        qlo = t;
+                        ca = pc_s + 4u * (Ls - 8u - i);                  // may point below the row for the last step: only j >= jlo is used
+                        jlo = 8u - v;
+                        jhi = 8u;
+                    }
+                    uint32_t pop4;
+                    const uint32_t oh = swar_onehot8(W, pop4);            // bit 4j: base j is A/C/G/T; pop4: bit count per nibble
+                    const uint32_t D = swar_dna5_8(W, oh);                // Dna5 ordinal per nibble (src/QualityCheck.hpp:135)
+                    if (v == 8u) {
+                        cntN += __popc(pop4 & 0x44444444u);               // literal N: all four bits (:137)
+                        cntGC += __popc(((W >> 1) | (W >> 2)) & oh);      // literal C or G (:141)
+                        sumQ = __dp4a(qlo, 0x01010101u, __dp4a(qhi, 0x01010101u, sumQ));
+#pragma unroll
+                        for (uint32_t j = 0; j < 8u; ++j) {
+                            const uint32_t d = (D >> (4u * j)) & 7u;
+                            const uint32_t q = ((j < 4u ? qlo : qhi) >> (8u * (j & 3u))) & 255u;
+                            red_shared_inc(ca + d * rowb + 4u * j);
+                            red_shared_add(ca + PC_QUAL * rowb + 4u * j, q);
+                        }
+                    } else {
+                        const uint32_t nm = (uint32_t)(((1ULL << (4u * jhi)) - 1ULL) & ~((1ULL << (4u * jlo)) - 1ULL));  // valid nibbles
+                        cntN += __popc(pop4 & 0x44444444u & nm);
+                        cntGC += __popc(((W >> 1) | (W >> 2)) & oh & nm);
+#pragma unroll
+                        for (uint32_t j = 0; j < 8u; ++j) {
+                            if (j >= jlo && j < jhi) {
+                                const uint32_t d = (D >> (4u * j)) & 7u;
+                                const uint32_t q = ((j < 4u ? qlo : qhi) >> (8u * (j & 3u))) & 255u;
+                                sumQ += q;
+                                red_shared_inc(ca + d * rowb + 4u * j);
+                                red_shared_add(ca + PC_QUAL * rowb + 4u * j, q);
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -289,7 +329,10 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
         flush(S.in + m * kHS, kHS, GMm + L.m_ins);
     }
     flush(S.isz, E.insert_smem, G + L.o_insert);
-    flush(S.tri, kTriplet, G + L.o_triplet);
+    for (uint32_t i = threadIdx.x; i < kTriplet; i += blockDim.x) {  // smem context order is (next, cur, prev): swar.h
+        uint32_t v = sm[S.tri + i];
+        if (v) atomicAdd((unsigned long long*)(G + L.o_triplet + triplet_ctx_to_result(i >> 4) * 16u + (i & 15u)), (unsigned long long)v);
+    }
     flush(S.sc, S_COUNT, G + L.o_scalars);
 }
 

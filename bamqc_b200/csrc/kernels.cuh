@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include "layout.h"
+#include "swar.h"
 
 namespace bqc {
 

@@ -1,0 +1,221 @@
+// swar_selftest.cpp -- CPU check of bamqc_b200/csrc/swar.h (test infrastructure; built and run by tests/test_swar_cpu.py).
+// Random reads (A/C/G/T/N and IUPAC nibbles, qualities over the whole byte range, CIGARs with I/D/N/S/H/P ops and
+// zero-length ops, reads that overhang the contig) go through
+//   (1) a per-position walk that restates src/TripletCounting.hpp:195-236, and
+//   (2) the run enumeration + 16-nibble windows used by k_stats (same statements as kernel_stats.cuh phase B),
+// and the 1024 triplet counters must be equal.  Also checks the per-cycle word forms used by k_cycles.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../bamqc_b200/csrc/swar.h"
+
+using namespace bqc;
+
+static uint64_t rng_state = 0x9E3779B97F4A7C15ULL;
+static uint64_t rnd() {
+    uint64_t z = (rng_state += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+struct Read {
+    std::vector<uint8_t> seq;   // packed 4-bit, high nibble first, padded
+    std::vector<uint8_t> qual;  // padded
+    std::vector<uint32_t> cigar;
+    uint32_t L;
+    int32_t pos;
+};
+
+static uint64_t ld64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
+static uint32_t nib(const Read& r, uint32_t i) { return (r.seq[i >> 1] >> ((i & 1) ? 0 : 4)) & 15u; }
+static uint32_t refbase(const std::vector<uint32_t>& ref, uint32_t refmax, uint32_t c) {
+    uint32_t w = c >> 4; if (w > refmax) w = refmax;
+    return (ref[w] >> (2 * (c & 15))) & 3u;
+}
+
+static void walk_naive(const Read& r, const std::vector<uint32_t>& ref, uint64_t reflen, uint32_t refmax, uint32_t* tri) {
+    uint32_t it = 0, cc = (r.cigar[0] >> 4) - 1u, chromPos = (uint32_t)r.pos + 1u, readPos = 1;
+    const uint32_t last = r.L - 1;
+    for (; readPos < last; ++readPos, ++chromPos, --cc) {
+        if (cc == 0) {
+            bool ok = true;
+            do {
+                ++it;
+                if (it >= r.cigar.size()) { ok = false; break; }
+                uint32_t c = r.cigar[it], op = c & 15u, n = c >> 4;
+                if (op == 2 || op == 3 || op == 5 || op == 6) chromPos += n;
+                else if (op == 4 || op == 1) readPos += n;
+                else cc = n;
+            } while (cc == 0);
+            if (!ok || readPos >= last) break;
+        }
+        const uint32_t q = r.qual[readPos];
+        const uint32_t np = nib(r, readPos - 1), nc = nib(r, readPos), nn = nib(r, readPos + 1);
+        const uint32_t rp = refbase(ref, refmax, chromPos - 1), rcur = refbase(ref, refmax, chromPos), rn = refbase(ref, refmax, chromPos + 1);
+        const bool onehot = nc == 1 || nc == 2 || nc == 4 || nc == 8;
+        const uint32_t base = nc == 1 ? 0 : nc == 2 ? 1 : nc == 4 ? 2 : 3;
+        if ((int8_t)(q + 33u) >= (int8_t)53 && onehot && np == (1u << rp) && nn == (1u << rn) && (uint64_t)chromPos + 2 <= reflen)
+            tri[((rp << 4) + (rcur << 2) + rn) * 16u + base]++;
+    }
+}
+
+static void walk_swar(const Read& r, const std::vector<uint32_t>& ref, uint64_t reflen, uint32_t refmax, uint32_t* tri_s) {
+    const uint8_t* seqp = r.seq.data();
+    const uint8_t* qualp = r.qual.data();
+    uint32_t it = 0, cc = (r.cigar[0] >> 4) - 1u, chromPos = (uint32_t)r.pos + 1u, readPos = 1;
+    const uint32_t last = r.L - 1;
+    bool ok = true;
+    while (readPos < last) {
+        if (cc == 0) {
+            do {
+                ++it;
+                if (it >= r.cigar.size()) { ok = false; break; }
+                uint32_t c = r.cigar[it], op = c & 15u, n = c >> 4;
+                if (op == 2 || op == 3 || op == 5 || op == 6) chromPos += n;
+                else if (op == 4 || op == 1) readPos += n;
+                else cc = n;
+            } while (cc == 0);
+            if (!ok || readPos >= last) break;
+        }
+        const uint32_t run = cc < last - readPos ? cc : last - readPos;
+        const int64_t lim = (int64_t)reflen - 1 - (int64_t)chromPos + (int64_t)readPos;
+        uint32_t end = readPos + run;
+        if (lim < (int64_t)end) end = lim > (int64_t)readPos ? (uint32_t)lim : readPos;
+        const uint32_t delta = chromPos - readPos;
+        for (uint32_t p = readPos; p < end;) {
+            const uint32_t g = (p - 1u) & ~1u;
+            const uint64_t R = swar_swap_nibbles(ld64(seqp + (g >> 1)));
+            const uint64_t q0 = ld64(qualp + g), q1 = ld64(qualp + g + 8);
+            const int32_t cg = (int32_t)(delta + g);
+            const uint32_t cgc = cg < 0 ? 0u : (uint32_t)cg;
+            const uint32_t wi = cgc >> 4;
+            const uint64_t pair = (uint64_t)ref[wi < refmax ? wi : refmax] | ((uint64_t)ref[wi + 1u < refmax ? wi + 1u : refmax] << 32);
+            uint32_t F = (uint32_t)(pair >> (2u * (cgc & 15u)));
+            if (cg < 0) F <<= 2;
+            uint64_t T4, C4;
+            swar_triplet_masks(R, F, T4, C4);
+            const uint32_t jlo = p - g, jhi = (end - g) < 15u ? (end - g) : 15u;
+            C4 &= ((1ULL << (4u * jhi)) - 1ULL) & ~((1ULL << (4u * jlo)) - 1ULL);
+            const uint32_t qk[4] = {swar_q20((uint32_t)q0), swar_q20((uint32_t)(q0 >> 32)), swar_q20((uint32_t)q1), swar_q20((uint32_t)(q1 >> 32))};
+            const uint32_t c_lo = (uint32_t)C4, c_hi = (uint32_t)(C4 >> 32), t_lo = (uint32_t)T4, t_hi = (uint32_t)(T4 >> 32);
+            for (uint32_t j = 1; j < 15; ++j) {
+                const uint32_t cw = j < 8 ? c_lo : c_hi, tw = j < 8 ? t_lo : t_hi;
+                const uint32_t cnt = (cw >> (4u * (j & 7u))) & (qk[j >> 2] >> (8u * (j & 3u) + 7u)) & 1u;
+                const uint32_t ctx = (F >> (2u * (j - 1u))) & 63u;
+                const uint32_t base = (tw >> (4u * (j & 7u))) & 3u;
+                tri_s[ctx * 16u + base] += cnt;
+            }
+            p = g + jhi;
+        }
+        readPos += run;
+        chromPos += run;
+        cc -= run;
+    }
+}
+
+static int test_triplets(int n_reads) {
+    const uint64_t reflen = 5000;
+    const uint32_t refmax = (uint32_t)((reflen + 15) / 16) + 3u;
+    std::vector<uint32_t> ref(refmax + 2);
+    for (auto& w : ref) w = (uint32_t)rnd();
+    int bad = 0;
+    for (int t = 0; t < n_reads; ++t) {
+        Read r;
+        r.L = 3 + (uint32_t)(rnd() % 260);
+        if (rnd() % 4 == 0) r.L = 150;
+        r.seq.assign(r.L / 2 + 80, 0);
+        r.qual.assign(r.L + 80, 0);
+        // position: mostly inside, sometimes overhanging the contig end, sometimes 0
+        uint32_t m = (uint32_t)(rnd() % 10);
+        r.pos = m == 0 ? 0 : m == 1 ? (int32_t)(reflen - rnd() % 200) : (int32_t)(rnd() % (reflen - 300));
+        // CIGAR
+        uint32_t nops = 1 + (rnd() % 3 == 0 ? (uint32_t)(rnd() % 5) : 0);
+        uint32_t left = r.L;
+        for (uint32_t i = 0; i < nops; ++i) {
+            static const uint32_t ops[] = {0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8};
+            uint32_t op = i == 0 && nops == 1 ? 0u : ops[rnd() % 11];
+            uint32_t n = (rnd() % 8 == 0) ? 0u : (i + 1 == nops ? left : 1 + (uint32_t)(rnd() % (left ? left : 1)));
+            if (op == 2 || op == 3 || op == 5 || op == 6) n = (uint32_t)(rnd() % 40);
+            else if (n <= left) left -= n;
+            r.cigar.push_back(n << 4 | op);
+        }
+        if (rnd() % 16 == 0) r.cigar[0] = (uint32_t)(rnd() % 3) << 4 | (uint32_t)(rnd() % 9);
+        // bases: follow the reference along a plain diagonal (so flanks match often), with noise
+        for (uint32_t i = 0; i < r.L; ++i) {
+            uint32_t c = refbase(ref, refmax, (uint32_t)r.pos + i);
+            uint32_t nb = 1u << c;
+            uint32_t e = (uint32_t)(rnd() % 100);
+            if (e < 3) nb = 1u << (rnd() % 4);
+            else if (e < 5) nb = 15;
+            else if (e < 6) nb = (uint32_t)(rnd() % 16);
+            r.seq[i >> 1] |= (uint8_t)(nb << ((i & 1) ? 0 : 4));
+            uint32_t qe = (uint32_t)(rnd() % 100);
+            r.qual[i] = qe < 70 ? 37 : qe < 80 ? 19 : qe < 85 ? 20 : qe < 88 ? 94 : qe < 90 ? 95 : (uint8_t)(rnd() % 256);
+        }
+        for (size_t i = (r.L + 1) / 2; i < r.seq.size(); ++i) r.seq[i] = (uint8_t)rnd();  // bytes after SEQ are QUAL etc.
+        for (size_t i = r.L; i < r.qual.size(); ++i) r.qual[i] = (uint8_t)rnd();
+        if (r.L & 1) r.seq[r.L >> 1] = (uint8_t)((r.seq[r.L >> 1] & 0xF0) | (rnd() & 15));
+        uint32_t a[1024] = {0}, b[1024] = {0}, bp[1024] = {0};
+        walk_naive(r, ref, reflen, refmax, a);
+        walk_swar(r, ref, reflen, refmax, b);
+        for (uint32_t i = 0; i < 1024; ++i) bp[triplet_ctx_to_result(i >> 4) * 16u + (i & 15u)] += b[i];
+        if (memcmp(a, bp, sizeof a) != 0) {
+            if (bad < 5) {
+                fprintf(stderr, "triplet mismatch: read %d L=%u pos=%d cigar:", t, r.L, r.pos);
+                for (auto c : r.cigar) fprintf(stderr, " %u%c", c >> 4, "MIDNSHP=XXXXXXXX"[c & 15]);
+                fprintf(stderr, "\n");
+            }
+            ++bad;
+        }
+    }
+    return bad;
+}
+
+static uint32_t brev32(uint32_t x) { uint32_t r = 0; for (int i = 0; i < 32; ++i) r |= ((x >> i) & 1u) << (31 - i); return r; }
+
+// the 8-base word forms of the per-cycle pass against the per-base tables of the reference semantics
+// (A/a 0, C/c 1, G/g 2, T/t 3, else 4; reverse reads see the complemented base: SURVEY Appendix F, R5/R7)
+static int test_cycles(int n) {
+    const uint64_t LUT_FWD = 0x4444444344424104ULL, LUT_REV = 0x4444444044414234ULL;
+    int bad = 0;
+    for (int t = 0; t < n; ++t) {
+        uint32_t W = 0;
+        for (int j = 0; j < 8; ++j) {
+            uint32_t e = (uint32_t)(rnd() % 10), nb = e < 7 ? 1u << (rnd() % 4) : e < 8 ? 15u : (uint32_t)(rnd() % 16);
+            W |= nb << (4 * j);
+        }
+        uint32_t pop4, oh = swar_onehot8(W, pop4), D = swar_dna5_8(W, oh);
+        uint32_t Wr = brev32(W), pop4r, ohr = swar_onehot8(Wr, pop4r), Dr = swar_dna5_8(Wr, ohr);
+        uint32_t nN = 0, nGC = 0;
+        for (int j = 0; j < 8; ++j) {
+            uint32_t nb = (W >> (4 * j)) & 15u;
+            if (((D >> (4 * j)) & 15u) != ((LUT_FWD >> (4 * nb)) & 7u)) ++bad;
+            if (((Dr >> (4 * (7 - j))) & 15u) != ((LUT_REV >> (4 * nb)) & 7u)) ++bad;
+            nN += nb == 15u;
+            nGC += nb == 2u || nb == 4u;
+        }
+        if ((uint32_t)__builtin_popcount(pop4 & 0x44444444u) != nN || (uint32_t)__builtin_popcount(pop4r & 0x44444444u) != nN) ++bad;
+        if ((uint32_t)__builtin_popcount(((W >> 1) | (W >> 2)) & oh) != nGC || (uint32_t)__builtin_popcount(((Wr >> 1) | (Wr >> 2)) & ohr) != nGC) ++bad;
+        uint32_t x = (uint32_t)rnd();
+        if (swar_swap_nibbles32(x) != (uint32_t)swar_swap_nibbles(x)) ++bad;
+        uint32_t q = swar_q20(x);
+        for (int j = 0; j < 4; ++j) {
+            uint32_t b = (x >> (8 * j)) & 255u;
+            if (((q >> (8 * j + 7)) & 1u) != (uint32_t)((int8_t)(b + 33u) >= (int8_t)53)) ++bad;
+        }
+    }
+    return bad;
+}
+
+int main(int argc, char** argv) {
+    int n = argc > 1 ? atoi(argv[1]) : 200000;
+    int bad = test_triplets(n);
+    printf("triplets: %d reads, %d mismatching\n", n, bad);
+    int bad2 = test_cycles(n);
+    printf("cycle words: %d words, %d mismatching\n", n, bad2);
+    return bad || bad2 ? 1 : 0;
+}
