@@ -235,7 +235,8 @@ struct bqc_engine {
     std::deque<Task> cq;
     bool cstop = false, cbusy = false;
     int async_rc = 0;
-    int tune_stats_bps = 0, tune_sketch_threads = 1024;  // BQC_STATS_BPS / BQC_SKETCH_THREADS (tuning knobs)
+    int tune_stats_bps = 0, tune_sketch_threads = 1024, tune_stats_stage = 0;  // BQC_STATS_STAGE=1: k_stats reads records through per-warp shared-memory staging
+    int _pad_tune = 0;   // BQC_STATS_BPS / BQC_SKETCH_THREADS (tuning knobs)
     int tune_cov_bps = 8;                                // BQC_COV_BPS: coverage CTAs per SM (upper bound)
     std::vector<CovState> cov;
     uint64_t records_seen = 0, frames_repaired = 0;
@@ -466,6 +467,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     e->blocks_per_slot = e->staging_bytes / 4096 + 4096;   // BGZF blocks per submission (larger inputs are split)
     e->ring_log2 = cfg->cov_ring_log2 ? cfg->cov_ring_log2 : 28;
     if (const char* v = getenv("BQC_STATS_BPS")) e->tune_stats_bps = atoi(v);
+    if (const char* v = getenv("BQC_STATS_STAGE")) e->tune_stats_stage = atoi(v);
     if (const char* v = getenv("BQC_COV_BPS")) e->tune_cov_bps = std::max(1, std::min(8, atoi(v)));
     if (const char* v = getenv("BQC_HOST_FRAMING")) e->device_framing = atoi(v) == 0;
     if (const char* v = getenv("BQC_TRACE")) e->trace = atoi(v) != 0;
@@ -523,7 +525,8 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         CU(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kInflateStreams * sizeof(InflateTabs))));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->inflate_bps, k_inflate, (int)kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs)));
         if (e->inflate_bps < 1) e->inflate_bps = 1;
-        CU(cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(k_stats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(k_stats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(k_eightmer, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CU(cudaFuncSetAttribute(k_sketch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CU(cudaFuncSetAttribute(k_sketch32, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024 + (int)sizeof(HashPairTable) + (int)(kSketchThreads / 32 * kSketchQueue * 8)));
@@ -937,9 +940,10 @@ static int batch_launch_setup(bqc_engine* e, const DeviceBatch& d, BatchLaunch& 
     if (cycb > e->L.cyc) cycb = e->L.cyc;  // longer reads are reported as unsupported by the kernel
     BL.cycb = cycb;
     StatsSmem S = stats_smem_layout(cycb, BL.E.insert_smem);
-    BL.stats_smem = (size_t)S.total * 4;
+    BL.stats_smem = e->tune_stats_stage ? (size_t)S.stage * 4 + (size_t)(kStatsThreads / 32) * kStatsStage : (size_t)S.total * 4;
     int bps = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats, (int)kStatsThreads, BL.stats_smem));
+    if (e->tune_stats_stage) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats<true>, (int)kStatsThreads, BL.stats_smem));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats<false>, (int)kStatsThreads, BL.stats_smem));
     if (bps < 1) { set_error(e, "k_stats does not fit: %zu bytes of shared memory", BL.stats_smem); return BQC_ERR_ARG; }
     if (e->tune_stats_bps > 0 && e->tune_stats_bps < bps) bps = e->tune_stats_bps;
     BL.bps = bps;
@@ -995,7 +999,11 @@ static int launch_tables(bqc_engine* e, const DeviceBatch& d, const BatchLaunch&
         B.first_record = d.first_record;
         B.ring_base = 0;
         int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * BL.bps);
-        { ProfScope prof(e, 0); k_stats<<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane); }
+        {
+            ProfScope prof(e, 0);
+            if (e->tune_stats_stage) k_stats<true><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
+            else k_stats<false><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
+        }
         int g8 = (int)std::min<uint64_t>((n + kEightThreads - 1) / kEightThreads, (uint64_t)e->n_sm);
         if (g8 < 1) g8 = 1;
         { ProfScope prof(e, 1); k_eightmer<<<g8, kEightThreads, 32768 * 4, e->compute>>>(E, B, lane); }

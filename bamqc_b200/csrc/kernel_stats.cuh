@@ -34,34 +34,28 @@ struct NibStream {
 };
 
 __device__ __forceinline__ void red_shared_inc(uint32_t saddr) {
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr));
 }
 __device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t v) {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v));
 }
 
-__global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView B, uint32_t lane) {
-    extern __shared__ uint32_t sm[];
-    const StatsSmem S = stats_smem_layout(B.cycb, E.insert_smem);
-    for (uint32_t i = threadIdx.x; i < S.total; i += blockDim.x) sm[i] = 0;
-    __syncthreads();
+// Phases A-D for the (up to) 32 records of one warp.  `present` lanes hold a record whose bytes start at recp (in the
+// warp's staging area: M = SMem, or in global memory: M = GMem) and span `avail` bytes.
+template <class M>
+__device__ __forceinline__ void stats_records(const EngineView& E, const BatchView& B, uint32_t lane, uint32_t* sm, const StatsSmem& S,
+                                              uint32_t rec, bool present, const uint8_t* recp, uint32_t avail) {
     const Layout& L = E.L;
     uint64_t* G = E.counters + (uint64_t)lane * L.lane_stride;
     const uint32_t cycb = B.cycb;
-    const uint32_t lane_id = threadIdx.x & 31u;
-    // Dna5 ordinal per BAM nibble, 4 bits per entry: forward view and reverse-complement view (R5, R7)
-    const uint64_t LUT_FWD = 0x4444444344424104ULL;  // nib 1->0, 2->1, 4->2, 8->3, else 4
-    const uint64_t LUT_REV = 0x4444444044414234ULL;  // nib 1->3, 2->2, 4->1, 8->0, else 4
-
-    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < B.n_records; r0 += gridDim.x * blockDim.x) {
+    {
         // ---------------------------------------------------------------- phase A
-        const uint32_t rec = r0 + lane_id;
         const uint64_t grec = B.first_record + rec;
         RecHdr h;
-        bool live = rec < B.n_records && !(B.rec_lane && B.rec_lane[rec] != lane);
+        h.p = recp;
+        bool live = present && !(B.rec_lane && B.rec_lane[rec] != lane);
         if (live) {
-            const uint32_t off = B.offsets[rec];
-            if (!decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h)) { report_error(E, grec, 4); live = false; }
+            if (!decode_hdr<M>(recp, avail, h)) { report_error(E, grec, 4); live = false; }
         }
         uint32_t flag = 0, Ls = 0, mate = 0, delc = 0, insc = 0, first_op = 0, last_op = 0;
         bool isfirst = false, rc = false, mapped = false, inmain = false, do_trip = false;
@@ -81,7 +75,7 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
             uint32_t clipped = 0;
             if (primary) {
                 for (uint32_t i = 0; i < h.ncig; ++i) {
-                    uint32_t c = ldu32(h.p + h.o_cig + 4 * i);
+                    uint32_t c = ldu32<M>(h.p + h.o_cig + 4 * i);
                     uint32_t op = c & 15u, n = c >> 4;
                     if (op == 2) delc += n;
                     else if (op == 1) insc += n;
@@ -91,7 +85,7 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
                 }
             }
             const bool do_cig = primary && hasmate && inmain && mapped;  // src/bamqualcheck.cpp:392-428
-            AuxInfo ai = aux_walk(h, [&](uint32_t nm) {
+            AuxInfo ai = aux_walk<M>(h, [&](uint32_t nm) {
                 if (do_cig) bump(sm + S.mm + mate * kHS, kHS, GM + L.m_mismatch, L.mmcap, nm - delc - insc, E, grec);
             });
             // getLane(): src/bamqualcheck.cpp:72-100, then the gate :318-335
@@ -139,7 +133,7 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
                     do {
                         ++it;
                         if (it >= h.ncig) { ok = false; break; }  // the reference reads past the CIGAR here (undefined)
-                        uint32_t c = ldu32(h.p + h.o_cig + 4 * it);
+                        uint32_t c = ldu32<M>(h.p + h.o_cig + 4 * it);
                         uint32_t op = c & 15u, n = c >> 4;
                         if (op == 2 || op == 3 || op == 5 || op == 6) chromPos += n;
                         else if (op == 4 || op == 1) readPos += n;
@@ -155,8 +149,8 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
                 const uint32_t delta = chromPos - readPos;
                 for (uint32_t p = readPos; p < end;) {
                     const uint32_t g = (p - 1u) & ~1u;                       // window = read positions g..g+15
-                    const uint64_t R = swar_swap_nibbles(ldu64(seqp + (g >> 1)));
-                    const uint64_t q0 = ldu64(qualp + g), q1 = ldu64(qualp + g + 8);
+                    const uint64_t R = swar_swap_nibbles(ldu64<M>(seqp + (g >> 1)));
+                    const uint64_t q0 = ldu64<M>(qualp + g), q1 = ldu64<M>(qualp + g + 8);
                     const int32_t cg = (int32_t)(delta + g);                 // reference position of window base 0 (>= -1)
                     const uint32_t cgc = cg < 0 ? 0u : (uint32_t)cg;
                     const uint32_t wi = cgc >> 4;
@@ -189,59 +183,57 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
         const uint32_t maxL = __reduce_max_sync(0xFFFFFFFFu, myL);
         uint32_t cntN = 0, cntGC = 0, sumQ = 0;
         {
-            // Eight bases per step.  Reverse reads are brought into cycle order first: __brev of the nibble word
-            // reverses the base order AND the bits of every nibble, which is the complement for the one-hot codes
-            // (R7); the quality bytes are byte-reversed.  Per word: Dna5 ordinals, N / GC counts and the quality
-            // sum come from swar.h; per base one increment of dnacount[d][cycle] and one add to qualcount[cycle].
-            const uint32_t rowb = cycb * 4u;
-            const uint32_t pc_s = (uint32_t)__cvta_generic_to_shared(sm + S.pc + mate * PC_ROWS * cycb);
-            const uint8_t* seqp = live ? h.p + h.o_seq : B.bytes;
-            const uint8_t* qualp = live ? h.p + h.o_qual : B.bytes;
-            for (uint32_t i = 0; i < maxL; i += 8u) {
-                if (i < myL) {
-                    const uint32_t v = min(8u, myL - i);                 // bases of this step
-                    uint32_t W = swar_swap_nibbles32(ldu32(seqp + (i >> 1)));
-                    uint64_t Q = ldu64(qualp + i);
+            // Eight CYCLES per step, for both orientations: a forward read takes stored bases 8s..8s+7, a reverse read
+            // the stored bases L-8-8s..L-1-8s (an unaligned nibble window, possibly starting before base 0 in the
+            // last step) and brings them into cycle order: __brev of the nibble word reverses the base order AND
+            // the bits of every nibble, which is the complement for the one-hot codes (R7); the quality bytes are
+            // byte-reversed.  Per word: Dna5 ordinals, N / GC counts and the quality sum come from swar.h; per base
+            // one increment of dnacount[d][cycle] and one add to qualcount[cycle].  Bases past the end of the read
+            // (last step) are sent to a dump row with quality 0, so every lane runs the same instructions.
+            // Shared-memory conflicts: the rows are padded by one word per 8 cycles (cycle c lives at c + c/8), so
+            // lanes working on different steps hit different banks, and lanes visit their steps in rotated order
+            // (lane l starts at step l mod nsteps, reverse reads half a turn further).  Before, lanes of one mate and
+            // orientation added to the same qualcount word in the same instruction (ncu: 8 wavefronts per add) and
+            // the shared atomic pipe, not instruction issue, limited the kernel.
+            const uint32_t rowp = stats_row_words(cycb), rowb = rowp * 4u;
+            const uint32_t pc_s = (uint32_t)__cvta_generic_to_shared(sm + S.pc + mate * (PC_ROWS + 1u) * rowp);
+            const uint8_t* seqp = live ? h.p + h.o_seq : recp;
+            const uint8_t* qualp = live ? h.p + h.o_qual : recp;
+            const uint32_t mysteps = (myL + 7u) >> 3;
+            const uint32_t rot = mysteps ? ((threadIdx.x & 31u) + (rc ? (mysteps >> 1) : 0u)) % mysteps : 0u;
+            for (uint32_t it = 0; it < ((maxL + 7u) >> 3); ++it) {
+                if (it < mysteps) {
+                    uint32_t step = it + rot;
+                    if (step >= mysteps) step -= mysteps;
+                    const uint32_t v = min(8u, myL - 8u * step);          // cycles of this step that exist
+                    const int32_t n0 = rc ? (int32_t)Ls - 8 - (int32_t)(8u * step) : (int32_t)(8u * step);  // first stored base
+                    const uint64_t X = swar_swap_nibbles(ldu64<M>(seqp + (n0 >> 1)));
+                    uint32_t W = (uint32_t)(X >> (4u * (uint32_t)(n0 & 1)));
+                    const uint64_t Q = ldu64<M>(qualp + n0);
                     uint32_t qlo = (uint32_t)Q, qhi = (uint32_t)(Q >> 32);
-                    uint32_t ca = pc_s + 4u * i;                         // dnacount row 0 at the cycle of window base 0
-                    uint32_t jlo = 0, jhi = v;
                     if (rc) {
                         W = __brev(W);
                         const uint32_t t = __byte_perm(qhi, 0u, 0x0123u);
                         qhi = __byte_perm(qlo, 0u, 0x0123u);
                         qlo = t;
-                        ca = pc_s + 4u * (Ls - 8u - i);                  // may point below the row for the last step: only j >= jlo is used
-                        jlo = 8u - v;
-                        jhi = 8u;
                     }
+                    const uint32_t nm = v == 8u ? 0xFFFFFFFFu : (1u << (4u * v)) - 1u;                 // nibbles that exist
+                    const uint64_t qm = v == 8u ? ~0ULL : (1ULL << (8u * v)) - 1ULL;
+                    qlo &= (uint32_t)qm;
+                    qhi &= (uint32_t)(qm >> 32);
                     uint32_t pop4;
                     const uint32_t oh = swar_onehot8(W, pop4);            // bit 4j: base j is A/C/G/T; pop4: bit count per nibble
-                    const uint32_t D = swar_dna5_8(W, oh);                // Dna5 ordinal per nibble (src/QualityCheck.hpp:135)
-                    if (v == 8u) {
-                        cntN += __popc(pop4 & 0x44444444u);               // literal N: all four bits (:137)
-                        cntGC += __popc(((W >> 1) | (W >> 2)) & oh);      // literal C or G (:141)
-                        sumQ = __dp4a(qlo, 0x01010101u, __dp4a(qhi, 0x01010101u, sumQ));
+                    const uint32_t D = (swar_dna5_8(W, oh) & nm) | (~nm & 0x88888888u);  // Dna5 ordinal per nibble (src/QualityCheck.hpp:135); 8 = dump row
+                    cntN += __popc(pop4 & 0x44444444u & nm);              // literal N: all four bits (:137)
+                    cntGC += __popc(((W >> 1) | (W >> 2)) & oh & nm);     // literal C or G (:141)
+                    sumQ = __dp4a(qlo, 0x01010101u, __dp4a(qhi, 0x01010101u, sumQ));
+                    const uint32_t ca = pc_s + 36u * step;                // row 0 at cycle 8 * step (9 words per 8 cycles)
 #pragma unroll
-                        for (uint32_t j = 0; j < 8u; ++j) {
-                            const uint32_t d = (D >> (4u * j)) & 7u;
-                            const uint32_t q = ((j < 4u ? qlo : qhi) >> (8u * (j & 3u))) & 255u;
-                            red_shared_inc(ca + d * rowb + 4u * j);
-                            red_shared_add(ca + PC_QUAL * rowb + 4u * j, q);
-                        }
-                    } else {
-                        const uint32_t nm = (uint32_t)(((1ULL << (4u * jhi)) - 1ULL) & ~((1ULL << (4u * jlo)) - 1ULL));  // valid nibbles
-                        cntN += __popc(pop4 & 0x44444444u & nm);
-                        cntGC += __popc(((W >> 1) | (W >> 2)) & oh & nm);
-#pragma unroll
-                        for (uint32_t j = 0; j < 8u; ++j) {
-                            if (j >= jlo && j < jhi) {
-                                const uint32_t d = (D >> (4u * j)) & 7u;
-                                const uint32_t q = ((j < 4u ? qlo : qhi) >> (8u * (j & 3u))) & 255u;
-                                sumQ += q;
-                                red_shared_inc(ca + d * rowb + 4u * j);
-                                red_shared_add(ca + PC_QUAL * rowb + 4u * j, q);
-                            }
-                        }
+                    for (uint32_t j = 0; j < 8u; ++j) {
+                        const uint32_t d = (D >> (4u * j)) & 15u;
+                        const uint32_t q = ((j < 4u ? qlo : qhi) >> (8u * (j & 3u))) & 255u;
+                        red_shared_inc(ca + d * rowb + 4u * j);
+                        red_shared_add(ca + PC_QUAL * rowb + 4u * j, q);
                     }
                 }
             }
@@ -279,13 +271,14 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
                         report_error(E, grec, 16);
                     } else {
                         uint32_t fo = rc ? last_op : first_op, lo = rc ? first_op : last_op;
-                        uint32_t* pc = sm + S.pc + mate * PC_ROWS * cycb;
+                        const uint32_t rowp = stats_row_words(cycb);
+                        uint32_t* pc = sm + S.pc + mate * (PC_ROWS + 1u) * rowp;
                         if ((fo & 15u) == 4u) {
                             uint32_t n = min(fo >> 4, cycb);
-                            for (uint32_t j = 0; j < n; ++j) atomicAdd(pc + PC_SC5 * cycb + j, 1u);
+                            for (uint32_t j = 0; j < n; ++j) atomicAdd(pc + PC_SC5 * rowp + j + (j >> 3), 1u);
                         } else if ((lo & 15u) == 4u) {
                             uint32_t n = lo >> 4;
-                            for (uint32_t j = (n <= Ls ? Ls - n : Ls); j < Ls; ++j) atomicAdd(pc + PC_SC3 * cycb + j, 1u);
+                            for (uint32_t j = (n <= Ls ? Ls - n : Ls); j < Ls; ++j) atomicAdd(pc + PC_SC3 * rowp + j + (j >> 3), 1u);
                         }
                         bump(sm + S.dl + mate * kHS, kHS, GM + L.m_del, L.delcap, delc, E, grec);
                         bump(sm + S.in + mate * kHS, kHS, GM + L.m_ins, L.mmcap, insc, E, grec);
@@ -305,7 +298,63 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
                 // OverallNumbers::coverage (:430-433) is handled by k_cov_scatter + k_cov_flush.
             }
         }
-        __syncwarp();
+    }
+}
+
+// 16-byte asynchronous global -> shared copy (LDGSTS, bypasses L1)
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+static const uint32_t kStatsStage = 10240;   // bytes of staging per warp: 32 standard 2x150 bp records are 9280 bytes
+static const uint32_t kStatsStageTail = 64;  // the decoders read up to a few words past the end of a record
+
+// The 32 records of a warp are one contiguous byte span of the batch.  The warp copies the span into its staging area
+// with coalesced 16-byte async copies (one round trip to HBM with ~18 copies in flight per lane) and every phase then
+// reads record bytes from shared memory; without this the kernel waited on dependent, unaligned global loads (ncu:
+// half of all stall samples).  A span larger than the stage is processed in pieces; a single record larger than the
+// stage is read straight from global memory.
+template <bool STAGE>
+__global__ void __launch_bounds__(kStatsThreads, STAGE ? 2 : 4) k_stats(EngineView E, BatchView B, uint32_t lane) {
+    extern __shared__ __align__(16) uint32_t sm[];
+    const StatsSmem S = stats_smem_layout(B.cycb, E.insert_smem);
+    for (uint32_t i = threadIdx.x; i < S.total; i += blockDim.x) sm[i] = 0;
+    __syncthreads();
+    const Layout& L = E.L;
+    uint64_t* G = E.counters + (uint64_t)lane * L.lane_stride;
+    const uint32_t cycb = B.cycb;
+    const uint32_t lane_id = threadIdx.x & 31u;
+
+    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < B.n_records; r0 += gridDim.x * blockDim.x) {
+        const uint32_t n_here = min(32u, B.n_records - r0);
+        uint32_t off = 0, end = 0;
+        if (lane_id < n_here) { off = B.offsets[r0 + lane_id]; end = B.offsets[r0 + lane_id + 1]; }
+        if (!STAGE) {
+            stats_records<GMem>(E, B, lane, sm, S, r0 + lane_id, lane_id < n_here, B.bytes + off, end - off);
+            continue;
+        }
+        uint8_t* stage = (uint8_t*)(sm + S.stage) + (threadIdx.x >> 5) * kStatsStage;
+        const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+        uint32_t sub = 0;
+        while (sub < n_here) {
+            const uint32_t lo = __shfl_sync(0xFFFFFFFFu, off, sub) & ~15u;
+            const bool fits = lane_id >= sub && lane_id < n_here && end >= lo && end - lo + kStatsStageTail <= kStatsStage;
+            const uint32_t m = __popc(__ballot_sync(0xFFFFFFFFu, fits));  // offsets ascend: the fitting lanes are sub..sub+m-1
+            if (m == 0) {
+                stats_records<GMem>(E, B, lane, sm, S, r0 + lane_id, lane_id == sub, B.bytes + off, end - off);
+                sub += 1;
+                continue;
+            }
+            const uint32_t hi = __shfl_sync(0xFFFFFFFFu, end, sub + m - 1);
+            const uint32_t nvec = (hi + 48u - lo + 15u) >> 4;
+            for (uint32_t v = lane_id; v < nvec; v += 32u) cp_async16(stage_s + 16u * v, B.bytes + lo + 16u * v);
+            cp_async_wait_all();
+            __syncwarp();
+            stats_records<SMem>(E, B, lane, sm, S, r0 + lane_id, fits, stage + (off - lo), end - off);
+            __syncwarp();  // every lane is done with the stage before it is refilled
+            sub += m;
+        }
     }
     __syncthreads();
     // ---- flush the CTA-private tables (skip zeros) ---------------------------------------------------
@@ -317,7 +366,12 @@ __global__ void __launch_bounds__(kStatsThreads) k_stats(EngineView E, BatchView
     };
     for (uint32_t m = 0; m < 2; ++m) {
         uint64_t* GMm = G + L.o_mate0 + m * L.mate_stride;
-        for (uint32_t r = 0; r < PC_ROWS; ++r) flush(S.pc + (m * PC_ROWS + r) * cycb, cycb, GMm + L.m_pc + r * pad8(L.cyc));
+        const uint32_t rowp = stats_row_words(cycb);
+        for (uint32_t r = 0; r < PC_ROWS; ++r)  // padded rows: cycle c lives at c + c/8
+            for (uint32_t c = threadIdx.x; c < cycb; c += blockDim.x) {
+                uint32_t v = sm[S.pc + (m * (PC_ROWS + 1u) + r) * rowp + c + (c >> 3)];
+                if (v) atomicAdd((unsigned long long*)(GMm + L.m_pc + r * pad8(L.cyc) + c), (unsigned long long)v);
+            }
         flush(S.rl + m * (cycb + 8), cycb + 1, GMm + L.m_readlen);
         flush(S.nc + m * (cycb + 8), cycb + 1, GMm + L.m_ncount);
         flush(S.gc + m * (cycb + 8), cycb + 1, GMm + L.m_gccount);

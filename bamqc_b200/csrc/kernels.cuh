@@ -66,22 +66,51 @@ struct HashTables {
 // ------------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ldg8(const uint8_t* p) { return __ldg(p); }
+// Where record bytes are read from: global memory through the read-only path, or a warp's staging area in shared
+// memory (k_stats copies the contiguous byte span of its 32 records there with 16-byte async copies).
+struct GMem {
+    static __device__ __forceinline__ uint32_t ld8(const uint8_t* p) { return __ldg(p); }
+    static __device__ __forceinline__ uint32_t ld32(const uint32_t* p) { return __ldg(p); }
+    static __device__ __forceinline__ uint64_t ld64(const uint64_t* p) { return __ldg(p); }
+};
+struct SMem {
+    // Explicit ld.shared: with plain dereferences the compiler folded the "two aligned loads + funnel shift" of
+    // ldu32/ldu64 back into ONE load at the unaligned address, which faults in shared memory (misaligned address).
+    static __device__ __forceinline__ uint32_t ld8(const uint8_t* p) {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+        return v;
+    }
+    static __device__ __forceinline__ uint32_t ld32(const uint32_t* p) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+        return v;
+    }
+    static __device__ __forceinline__ uint64_t ld64(const uint64_t* p) {
+        uint64_t v;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+        return v;
+    }
+};
+template <class M = GMem>
+__device__ __forceinline__ uint32_t ldg8(const uint8_t* p) { return M::ld8(p); }
+template <class M = GMem>
 __device__ __forceinline__ uint32_t ldu32(const uint8_t* p) {  // unaligned little-endian 32-bit load
     uintptr_t a = (uintptr_t)p;
     const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
     uint32_t sh = (uint32_t)(a & 3) * 8;
-    uint32_t lo = __ldg(w);
+    uint32_t lo = M::ld32(w);
     if (sh == 0) return lo;
-    return __funnelshift_r(lo, __ldg(w + 1), sh);
+    return __funnelshift_r(lo, M::ld32(w + 1), sh);
 }
+template <class M = GMem>
 __device__ __forceinline__ uint64_t ldu64(const uint8_t* p) {  // unaligned little-endian 64-bit load
     uintptr_t a = (uintptr_t)p;
     const uint64_t* w = (const uint64_t*)(a & ~(uintptr_t)7);
     uint32_t sh = (uint32_t)(a & 7) * 8;
-    uint64_t lo = __ldg(w);
+    uint64_t lo = M::ld64(w);
     if (sh == 0) return lo;
-    return (lo >> sh) | (__ldg(w + 1) << (64 - sh));
+    return (lo >> sh) | (M::ld64(w + 1) << (64 - sh));
 }
 // nibble i (0..15) of a 64-bit SEQ chunk: byte i/2, high nibble first
 __device__ __forceinline__ uint32_t nib_of(uint64_t w, uint32_t i) { return (uint32_t)(w >> (4 * (i ^ 1))) & 15u; }
@@ -100,13 +129,14 @@ struct RecHdr {
 };
 
 // BAM record fixed fields (SAM/BAM spec).  Returns false if the record is malformed.
+template <class M = GMem>
 __device__ __forceinline__ bool decode_hdr(const uint8_t* p, uint32_t avail, RecHdr& h) {
     uintptr_t a = (uintptr_t)p;
     const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
     uint32_t sh = (uint32_t)(a & 3) * 8;
     uint32_t v[10];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) v[i] = __ldg(w + i);
+    for (int i = 0; i < 10; ++i) v[i] = M::ld32(w + i);
 #define BQC_F(i) (sh ? __funnelshift_r(v[i], v[i + 1], sh) : v[i])
     h.p = p;
     h.bs = BQC_F(0);
@@ -143,6 +173,7 @@ struct AuxInfo {
     int32_t as_value;
 };
 
+template <class M = GMem>
 __device__ __forceinline__ uint32_t aux_value_size(uint32_t type, const uint8_t* p, uint32_t pos, uint32_t end) {
     // size of the value that starts at pos for a tag of `type`; 0xFFFFFFFF if malformed
     switch (type) {
@@ -151,13 +182,13 @@ __device__ __forceinline__ uint32_t aux_value_size(uint32_t type, const uint8_t*
         case 'i': case 'I': case 'f': return 4;
         case 'Z': case 'H': {
             uint32_t q = pos;
-            while (q < end && ldg8(p + q) != 0) ++q;
+            while (q < end && ldg8<M>(p + q) != 0) ++q;
             return q - pos + 1;
         }
         case 'B': {
             if (pos + 5 > end) return 0xFFFFFFFFu;
-            uint32_t sub = ldg8(p + pos);
-            uint32_t cnt = ldu32(p + pos + 1);
+            uint32_t sub = ldg8<M>(p + pos);
+            uint32_t cnt = ldu32<M>(p + pos + 1);
             uint32_t es = (sub == 'c' || sub == 'C') ? 1u : (sub == 's' || sub == 'S') ? 2u : 4u;
             return 5u + cnt * es;
         }
@@ -165,43 +196,44 @@ __device__ __forceinline__ uint32_t aux_value_size(uint32_t type, const uint8_t*
     }
 }
 // SeqAn extractTagValue into an integer (R15)
+template <class M = GMem>
 __device__ __forceinline__ bool aux_int(uint32_t type, const uint8_t* p, long long& out) {
     switch (type) {
-        case 'c': out = (int8_t)ldg8(p); return true;
-        case 'C': case 'A': out = (long long)ldg8(p); return true;
-        case 's': out = (int16_t)(ldg8(p) | (ldg8(p + 1) << 8)); return true;
-        case 'S': out = (long long)(ldg8(p) | (ldg8(p + 1) << 8)); return true;
-        case 'i': out = (int32_t)ldu32(p); return true;
-        case 'I': out = (long long)ldu32(p); return true;
-        case 'f': out = (long long)__uint_as_float(ldu32(p)); return true;
+        case 'c': out = (int8_t)ldg8<M>(p); return true;
+        case 'C': case 'A': out = (long long)ldg8<M>(p); return true;
+        case 's': out = (int16_t)(ldg8<M>(p) | (ldg8<M>(p + 1) << 8)); return true;
+        case 'S': out = (long long)(ldg8<M>(p) | (ldg8<M>(p + 1) << 8)); return true;
+        case 'i': out = (int32_t)ldu32<M>(p); return true;
+        case 'I': out = (long long)ldu32<M>(p); return true;
+        case 'f': out = (long long)__uint_as_float(ldu32<M>(p)); return true;
         default: return false;
     }
 }
 
 // One walk over the aux block: RG type (src/bamqualcheck.cpp:77-99), first AS (src/TripletCounting.hpp:
 // 113-129) and every integer-typed NM (src/QualityCheck.hpp:201-218, via on_nm).
-template <typename OnNM>
+template <class M = GMem, typename OnNM>
 __device__ __forceinline__ AuxInfo aux_walk(const RecHdr& h, OnNM on_nm) {
     AuxInfo ai = {0u, 0u, 0};
     uint32_t pos = h.o_aux;
     const uint8_t* p = h.p;
     while (pos + 3 <= h.o_end) {
-        uint32_t k0 = ldg8(p + pos), k1 = ldg8(p + pos + 1), ty = ldg8(p + pos + 2);
+        uint32_t k0 = ldg8<M>(p + pos), k1 = ldg8<M>(p + pos + 1), ty = ldg8<M>(p + pos + 2);
         pos += 3;
-        uint32_t sz = aux_value_size(ty, p, pos, h.o_end);
+        uint32_t sz = aux_value_size<M>(ty, p, pos, h.o_end);
         if (sz == 0xFFFFFFFFu) break;
         if (k0 == 'R' && k1 == 'G') {
             if (ai.rg == 0) ai.rg = (ty == 'Z') ? 1u : 2u;
         } else if (k0 == 'A' && k1 == 'S') {
             if (ai.as_state == 0) {
                 long long v;
-                if (aux_int(ty, p + pos, v)) { ai.as_state = 1; ai.as_value = (int32_t)v; }
+                if (aux_int<M>(ty, p + pos, v)) { ai.as_state = 1; ai.as_value = (int32_t)v; }
                 else ai.as_state = 2;
             }
         } else if (k0 == 'N' && k1 == 'M') {
             if (ty == 'c' || ty == 'C' || ty == 'i' || ty == 'I' || ty == 's' || ty == 'S') {
                 long long v = 0;
-                aux_int(ty, p + pos, v);
+                aux_int<M>(ty, p + pos, v);
                 on_nm((uint32_t)v);
             }
         }
@@ -218,12 +250,14 @@ static const uint32_t kHS = 32;    // smem bins of mismatch / del / ins histogra
 static const uint32_t kStatsThreads = 256;
 
 struct StatsSmem {  // word offsets into the dynamic shared array
-    uint32_t pc, rl, nc, gc, aq, cq, mq, mm, dl, in, isz, tri, sc, total;
+    uint32_t pc, rl, nc, gc, aq, cq, mq, mm, dl, in, isz, tri, sc, total, stage;
 };
+// words per per-cycle row in k_stats' shared memory: one pad word per 8 cycles (cycle c lives at c + c/8)
+__host__ __device__ inline uint32_t stats_row_words(uint32_t cycb) { return cycb + (cycb >> 3) + 1u; }
 __host__ __device__ inline StatsSmem stats_smem_layout(uint32_t cycb, uint32_t insert_smem) {
     StatsSmem s;
     uint32_t o = 0;
-    s.pc = o;  o += 2 * PC_ROWS * cycb;
+    s.pc = o;  o += 2 * (PC_ROWS + 1) * stats_row_words(cycb);  // padded per-cycle rows + one dump row per mate
     s.rl = o;  o += 2 * (cycb + 8);
     s.nc = o;  o += 2 * (cycb + 8);
     s.gc = o;  o += 2 * (cycb + 8);
@@ -237,6 +271,7 @@ __host__ __device__ inline StatsSmem stats_smem_layout(uint32_t cycb, uint32_t i
     s.tri = o; o += kTriplet;
     s.sc = o;  o += S_COUNT;
     s.total = o;
+    s.stage = (o + 3u) & ~3u;  // 16-byte aligned start of the per-warp staging areas (k_stats)
     return s;
 }
 

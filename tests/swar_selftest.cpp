@@ -211,11 +211,71 @@ static int test_cycles(int n) {
     return bad;
 }
 
+// the per-cycle pass of k_stats (kernel_stats.cuh phase C: eight cycles per step, reverse reads through an unaligned
+// nibble window + brev, padded rows, dump row) against src/QualityCheck.hpp:111-176 done base by base
+static uint32_t bperm_rev(uint32_t x) { return (x >> 24) | ((x >> 8) & 0xFF00u) | ((x << 8) & 0xFF0000u) | (x << 24); }
+static int test_cycle_pass(int n_reads) {
+    const uint64_t LUT_FWD = 0x4444444344424104ULL, LUT_REV = 0x4444444044414234ULL;
+    int bad = 0;
+    for (int t = 0; t < n_reads; ++t) {
+        const uint32_t L = 1 + (uint32_t)(rnd() % 300), cycb = (L + 7u) & ~7u, rowp = cycb + (cycb >> 3) + 1u;
+        const bool rc = rnd() & 1;
+        std::vector<uint8_t> buf(64 + L / 2 + L + 64);
+        for (auto& b : buf) b = (uint8_t)rnd();
+        uint8_t* seqp = buf.data() + 64;
+        uint8_t* qualp = seqp + (L + 1) / 2;
+        for (uint32_t i = 0; i < L; ++i) {
+            uint32_t e = (uint32_t)(rnd() % 10), nb = e < 7 ? 1u << (rnd() % 4) : e < 8 ? 15u : (uint32_t)(rnd() % 16);
+            seqp[i >> 1] = (uint8_t)((i & 1) ? (seqp[i >> 1] & 0xF0) | nb : (seqp[i >> 1] & 0x0F) | (nb << 4));
+        }
+        std::vector<uint32_t> want(6 * cycb, 0), got(9 * rowp, 0);
+        uint32_t wN = 0, wGC = 0, wQ = 0, cntN = 0, cntGC = 0, sumQ = 0;
+        for (uint32_t i = 0; i < L; ++i) {
+            const uint32_t nb = (seqp[i >> 1] >> ((i & 1) ? 0 : 4)) & 15u, q = qualp[i], cyc = rc ? L - 1 - i : i;
+            want[(uint32_t)(((rc ? LUT_REV : LUT_FWD) >> (4 * nb)) & 7u) * cycb + cyc]++;
+            want[5 * cycb + cyc] += q;
+            wN += nb == 15u; wGC += nb == 2u || nb == 4u; wQ += q;
+        }
+        const uint32_t mysteps = (L + 7u) >> 3;
+        for (uint32_t step = 0; step < mysteps; ++step) {
+            const uint32_t v = 8u < L - 8u * step ? 8u : L - 8u * step;
+            const int32_t n0 = rc ? (int32_t)L - 8 - (int32_t)(8u * step) : (int32_t)(8u * step);
+            const uint64_t X = swar_swap_nibbles(ld64(seqp + (n0 >> 1)));
+            uint32_t W = (uint32_t)(X >> (4u * (uint32_t)(n0 & 1)));
+            const uint64_t Q = ld64(qualp + n0);
+            uint32_t qlo = (uint32_t)Q, qhi = (uint32_t)(Q >> 32);
+            if (rc) { W = brev32(W); const uint32_t tq = bperm_rev(qhi); qhi = bperm_rev(qlo); qlo = tq; }
+            const uint32_t nm = v == 8u ? 0xFFFFFFFFu : (1u << (4u * v)) - 1u;
+            const uint64_t qm = v == 8u ? ~0ULL : (1ULL << (8u * v)) - 1ULL;
+            qlo &= (uint32_t)qm; qhi &= (uint32_t)(qm >> 32);
+            uint32_t pop4;
+            const uint32_t oh = swar_onehot8(W, pop4);
+            const uint32_t D = (swar_dna5_8(W, oh) & nm) | (~nm & 0x88888888u);
+            cntN += (uint32_t)__builtin_popcount(pop4 & 0x44444444u & nm);
+            cntGC += (uint32_t)__builtin_popcount(((W >> 1) | (W >> 2)) & oh & nm);
+            for (uint32_t j = 0; j < 8; ++j) {
+                const uint32_t d = (D >> (4u * j)) & 15u, q = ((j < 4u ? qlo : qhi) >> (8u * (j & 3u))) & 255u;
+                sumQ += q;
+                got[d * rowp + 9u * step + j]++;
+                got[5 * rowp + 9u * step + j] += q;
+            }
+        }
+        bool ok = cntN == wN && cntGC == wGC && sumQ == wQ;
+        for (uint32_t r = 0; r < 6 && ok; ++r)
+            for (uint32_t c = 0; c < cycb; ++c)
+                if (got[r * rowp + c + (c >> 3)] != want[r * cycb + c] + ((r < 5 && false) ? 1u : 0u)) { ok = false; break; }
+        if (!ok) { if (bad < 5) fprintf(stderr, "cycle pass mismatch: L=%u rc=%d\n", L, (int)rc); ++bad; }
+    }
+    return bad;
+}
+
 int main(int argc, char** argv) {
     int n = argc > 1 ? atoi(argv[1]) : 200000;
     int bad = test_triplets(n);
     printf("triplets: %d reads, %d mismatching\n", n, bad);
     int bad2 = test_cycles(n);
     printf("cycle words: %d words, %d mismatching\n", n, bad2);
-    return bad || bad2 ? 1 : 0;
+    int bad3 = test_cycle_pass(n / 4);
+    printf("cycle pass: %d reads, %d mismatching\n", n / 4, bad3);
+    return bad || bad2 || bad3 ? 1 : 0;
 }
