@@ -316,7 +316,7 @@ static const uint32_t kStatsStageTail = 64;  // the decoders read up to a few wo
 // half of all stall samples).  A span larger than the stage is processed in pieces; a single record larger than the
 // stage is read straight from global memory.
 template <bool STAGE>
-__global__ void __launch_bounds__(kStatsThreads, STAGE ? 2 : 4) k_stats(EngineView E, BatchView B, uint32_t lane) {
+__global__ void __launch_bounds__(kStatsThreads, STAGE ? 2 : 4) __maxnreg__(STAGE ? 96 : 64) k_stats(EngineView E, BatchView B, uint32_t lane) {
     extern __shared__ __align__(16) uint32_t sm[];
     const StatsSmem S = stats_smem_layout(B.cycb, E.insert_smem);
     for (uint32_t i = threadIdx.x; i < S.total; i += blockDim.x) sm[i] = 0;

@@ -299,10 +299,13 @@ __global__ void __launch_bounds__(kEightThreads, 1) k_eightmer(EngineView E, Bat
     for (uint32_t i = threadIdx.x; i < 32768u; i += blockDim.x) sm[i] = 0;
     __syncthreads();
     unsigned long long* g = (unsigned long long*)(E.counters + (uint64_t)lane * E.L.lane_stride + E.L.o_eightmer);
-    // 2-bit codes per BAM nibble: forward C(2)->1 G(4)->2 T(8)->3 else 0; reverse-complement view
-    // A(1)->3 C(2)->2 G(4)->1 else 0  (char->Dna conversion of the complemented char, R5/R7)
-    const uint32_t LUTF = (1u << (2 * 2)) | (2u << (2 * 4)) | (3u << (2 * 8));
-    const uint32_t LUTR = (3u << (2 * 1)) | (2u << (2 * 2)) | (1u << (2 * 4));
+    // Sixteen bases per step (swar.h): 2-bit codes of the whole chunk at once -- forward C(2)->1 G(4)->2 T(8)->3 else 0;
+    // reverse reads see the complemented base A(1)->3 C(2)->2 G(4)->1 else 0 (char->Dna conversion, R5/R7) -- packed
+    // into a 32-bit word; the 8-mer that ends at base e is a 16-bit field of (previous word : this word), taken with one
+    // funnel shift.  Forward reads pack big-endian (first base most significant, :144-156), reverse reads roll the
+    // reverse-complement code from the other end, which is the little-endian packing of the complemented codes.
+    // A window counts iff it holds no literal N (:146-166): a nibble-stride mask of "N among the last eight bases",
+    // with the distance to the last N carried between chunks (starting at 0, which also rules out the first 7 ends).
     for (uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x; rec < B.n_records; rec += gridDim.x * blockDim.x) {
         if (B.rec_lane && B.rec_lane[rec] != lane) continue;
         const uint32_t off = B.offsets[rec];
@@ -313,28 +316,62 @@ __global__ void __launch_bounds__(kEightThreads, 1) k_eightmer(EngineView E, Bat
         if (Ls < 8u) continue;
         const bool rc = (h.flag & 0x10u) != 0;
         const uint8_t* seqp = h.p + h.o_seq;
-        const uint32_t lut = rc ? LUTR : LUTF;
-        uint32_t code = 0, since_n = 0;
-        uint64_t seqw = 0;
-        for (uint32_t i = 0; i < Ls; ++i) {
-            if ((i & 15u) == 0) seqw = NibStream::swap_nibbles(ldu64(seqp + (i >> 1)));  // next base in the low nibble
-            const uint32_t nb = (uint32_t)seqw & 15u;
-            seqw >>= 4;
-            since_n = (nb == 15u) ? 0u : since_n + 1u;
-            const uint32_t c2 = (lut >> (2 * nb)) & 3u;
-            // forward reads roll the code left; reverse reads roll the reverse-complement code from the other end
-            code = rc ? ((code >> 2) | (c2 << 14)) : (((code << 2) | c2) & 0xFFFFu);
-            if (i >= 7u && since_n >= 8u) {
-                const uint32_t sh = (code & 1u) << 4;
-                const uint32_t old = atomicAdd(sm + (code >> 1), 1u << sh);
-                if (((old >> sh) & 0xFFFFu) == 0xFFFFu) {  // this increment wrapped the 16-bit field
-                    atomicAdd(g + code, 65536ULL);
-                    if (sh == 0u) {                       // the carry went into the high field (bin code + 1)
-                        atomicAdd(g + code + 1u, ~0ULL);
-                        if (old == 0xFFFFFFFFu) atomicAdd(g + code + 1u, 65536ULL);  // and wrapped that one too
+        uint32_t prev = 0;        // packed codes of the previous chunk
+        uint32_t since_n = 0;     // bases since the last N (or the start of the read) at the start of the chunk, saturating
+        const uint32_t nch = (Ls + 15u) >> 4;
+        for (uint32_t c = 0; c < nch; ++c) {
+            const uint64_t R = swar_swap_nibbles(ldu64(seqp + 8u * c));   // base j of the chunk in nibble j
+            const uint32_t rem = Ls - 16u * c;                             // bases of the read in this chunk (>= 1)
+            const uint64_t inr = rem >= 16u ? ~0ULL : (1ULL << (4u * rem)) - 1ULL;
+            const uint64_t s2 = (R & 0x5555555555555555ULL) + ((R >> 1) & 0x5555555555555555ULL);
+            const uint64_t t = (s2 & 0x3333333333333333ULL) + ((s2 >> 2) & 0x3333333333333333ULL);  // set bits per nibble
+            const uint64_t u = t ^ kNib1;
+            const uint64_t oh = ~(u | (u >> 1) | (u >> 2)) & kNib1;        // A/C/G/T
+            const uint64_t isn = (t >> 2) & kNib1 & inr;                   // literal N inside the read
+            uint64_t code = swar_code4(R);
+            if (rc) code ^= 0x3333333333333333ULL;                         // complement: 3 - c
+            code &= oh * 3ULL;                                             // everything else counts as 0 (R5)
+            // 16 codes -> 32 bits, base j at bits 2j
+            uint64_t x = (code | (code >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
+            x = (x | (x >> 4)) & 0x00FF00FF00FF00FFULL;
+            x = (x | (x >> 8)) & 0x0000FFFF0000FFFFULL;
+            const uint32_t ple = (uint32_t)x | ((uint32_t)(x >> 32) << 16);
+            uint32_t lo, hi, cur;
+            if (rc) {   // field of base e: bits 18 + 2e .. of (cur : prev)  ->  shift (cur : prev) >> 18 by 2e
+                cur = ple;
+                lo = (prev >> 18) | (cur << 14);
+                hi = cur >> 18;
+            } else {    // big-endian: base j at bits 30 - 2j; field of base e: bits 30 - 2e .. of (prev : cur)
+                const uint32_t br = __brev(ple);
+                cur = ((br & 0x55555555u) << 1) | ((br >> 1) & 0x55555555u);
+                lo = cur;
+                hi = prev;
+            }
+            // ends whose window holds an N or starts before the read / ends after it
+            uint64_t bad = isn;
+            bad |= bad << 4;
+            bad |= bad << 8;
+            bad |= bad << 16;
+            if (since_n < 7u) bad |= (1ULL << (4u * (7u - since_n))) - 1ULL;
+            bad |= ~inr;
+            since_n = isn ? (uint32_t)__clzll((long long)isn) >> 2 : min(since_n + 16u, 64u);
+            const uint32_t bad_lo = (uint32_t)bad, bad_hi = (uint32_t)(bad >> 32);
+#pragma unroll
+            for (uint32_t e = 0; e < 16u; ++e) {
+                const uint32_t code16 = __funnelshift_r(lo, hi, rc ? 2u * e : 30u - 2u * e) & 0xFFFFu;
+                if (!(((e < 8u ? bad_lo : bad_hi) >> (4u * (e & 7u))) & 1u)) {
+                    const uint32_t sh = (code16 & 1u) << 4;
+                    const uint32_t old = atomicAdd(sm + (code16 >> 1), 1u << sh);
+                    if (((old >> sh) & 0xFFFFu) == 0xFFFFu) {  // this increment wrapped the 16-bit field
+                        atomicAdd(g + code16, 65536ULL);
+                        if (sh == 0u) {                       // the carry went into the high field (bin code + 1)
+                            atomicAdd(g + code16 + 1u, ~0ULL);
+                            if (old == 0xFFFFFFFFu) atomicAdd(g + code16 + 1u, 65536ULL);  // and wrapped that one too
+                        }
                     }
                 }
             }
+            prev = cur;
         }
     }
     __syncthreads();

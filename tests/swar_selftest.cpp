@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "../bamqc_b200/csrc/swar.h"
@@ -269,6 +270,80 @@ static int test_cycle_pass(int n_reads) {
     return bad;
 }
 
+// the 16-base steps of k_eightmer (kernels.cuh) against OverallNumbers::count8mers (src/OverallNumbers.hpp:137-168)
+// done base by base on the read-oriented sequence
+static int test_eightmers(int n_reads) {
+    int bad = 0;
+    for (int t = 0; t < n_reads; ++t) {
+        const uint32_t Ls = 8 + (uint32_t)(rnd() % 200);
+        const bool rc = rnd() & 1;
+        std::vector<uint8_t> seq(Ls / 2 + 40);
+        for (auto& b : seq) b = (uint8_t)rnd();
+        std::vector<uint32_t> nibs(Ls);
+        for (uint32_t i = 0; i < Ls; ++i) {
+            uint32_t e = (uint32_t)(rnd() % 40), nb = e < 36 ? 1u << (rnd() % 4) : e < 38 ? 15u : (uint32_t)(rnd() % 16);
+            nibs[i] = nb;
+            seq[i >> 1] = (uint8_t)((i & 1) ? (seq[i >> 1] & 0xF0) | nb : (seq[i >> 1] & 0x0F) | (nb << 4));
+        }
+        std::vector<uint32_t> want, got;
+        {   // read-oriented bases: reverse reads are reverse-complemented first (nibble bit reversal)
+            std::vector<uint32_t> o(Ls);
+            for (uint32_t i = 0; i < Ls; ++i) {
+                uint32_t nb = nibs[rc ? Ls - 1 - i : i];
+                if (rc) nb = ((nb & 1) << 3) | ((nb & 2) << 1) | ((nb & 4) >> 1) | ((nb & 8) >> 3);
+                o[i] = nb;
+            }
+            for (uint32_t w = 0; w + 8 <= Ls; ++w) {
+                bool hasn = false; uint32_t code = 0;
+                for (uint32_t i = 0; i < 8; ++i) {
+                    const uint32_t nb = o[w + i];
+                    hasn |= nb == 15u;
+                    code = code * 4 + (nb == 2 ? 1 : nb == 4 ? 2 : nb == 8 ? 3 : 0);
+                }
+                if (!hasn) want.push_back(code);
+            }
+        }
+        uint32_t prev = 0, since_n = 0;
+        const uint8_t* seqp = seq.data();
+        const uint32_t nch = (Ls + 15u) >> 4;
+        for (uint32_t c = 0; c < nch; ++c) {
+            const uint64_t R = swar_swap_nibbles(ld64(seqp + 8u * c));
+            const uint32_t rem = Ls - 16u * c;
+            const uint64_t inr = rem >= 16u ? ~0ULL : (1ULL << (4u * rem)) - 1ULL;
+            const uint64_t s2 = (R & 0x5555555555555555ULL) + ((R >> 1) & 0x5555555555555555ULL);
+            const uint64_t tt = (s2 & 0x3333333333333333ULL) + ((s2 >> 2) & 0x3333333333333333ULL);
+            const uint64_t u = tt ^ kNib1;
+            const uint64_t oh = ~(u | (u >> 1) | (u >> 2)) & kNib1;
+            const uint64_t isn = (tt >> 2) & kNib1 & inr;
+            uint64_t code = swar_code4(R);
+            if (rc) code ^= 0x3333333333333333ULL;
+            code &= oh * 3ULL;
+            uint64_t x = (code | (code >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
+            x = (x | (x >> 4)) & 0x00FF00FF00FF00FFULL;
+            x = (x | (x >> 8)) & 0x0000FFFF0000FFFFULL;
+            const uint32_t ple = (uint32_t)x | ((uint32_t)(x >> 32) << 16);
+            uint32_t lo, hi, cur;
+            if (rc) { cur = ple; lo = (prev >> 18) | (cur << 14); hi = cur >> 18; }
+            else { const uint32_t br = brev32(ple); cur = ((br & 0x55555555u) << 1) | ((br >> 1) & 0x55555555u); lo = cur; hi = prev; }
+            uint64_t badm = isn;
+            badm |= badm << 4; badm |= badm << 8; badm |= badm << 16;
+            if (since_n < 7u) badm |= (1ULL << (4u * (7u - since_n))) - 1ULL;
+            badm |= ~inr;
+            since_n = isn ? (uint32_t)__builtin_clzll(isn) >> 2 : (since_n + 16u < 64u ? since_n + 16u : 64u);
+            for (uint32_t e = 0; e < 16u; ++e) {
+                const uint32_t sh = rc ? 2u * e : 30u - 2u * e;
+                const uint32_t code16 = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & 0xFFFFu;
+                if (!((badm >> (4u * e)) & 1u)) got.push_back(code16);
+            }
+            prev = cur;
+        }
+        // forward reads emit windows in read order; reverse reads emit the read-oriented windows in reverse order
+        if (rc) std::reverse(got.begin(), got.end());
+        if (got != want) { if (bad < 5) fprintf(stderr, "8-mer mismatch: L=%u rc=%d got %zu want %zu\n", Ls, (int)rc, got.size(), want.size()); ++bad; }
+    }
+    return bad;
+}
+
 int main(int argc, char** argv) {
     int n = argc > 1 ? atoi(argv[1]) : 200000;
     int bad = test_triplets(n);
@@ -277,5 +352,7 @@ int main(int argc, char** argv) {
     printf("cycle words: %d words, %d mismatching\n", n, bad2);
     int bad3 = test_cycle_pass(n / 4);
     printf("cycle pass: %d reads, %d mismatching\n", n / 4, bad3);
-    return bad || bad2 || bad3 ? 1 : 0;
+    int bad4 = test_eightmers(n / 4);
+    printf("8-mers: %d reads, %d mismatching\n", n / 4, bad4);
+    return bad || bad2 || bad3 || bad4 ? 1 : 0;
 }
