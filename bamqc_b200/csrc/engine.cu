@@ -235,7 +235,7 @@ struct bqc_engine {
     std::deque<Task> cq;
     bool cstop = false, cbusy = false;
     int async_rc = 0;
-    int tune_stats_bps = 0, tune_sketch_threads = 1024, tune_stats_stage = 0;  // BQC_STATS_STAGE=1: k_stats reads records through per-warp shared-memory staging
+    int tune_stats_bps = 0, tune_sketch_threads = 1024, tune_stats_stage = 1;  // BQC_STATS_STAGE=0: k_stats reads records straight from global memory (A/B tests)
     int _pad_tune = 0;   // BQC_STATS_BPS / BQC_SKETCH_THREADS (tuning knobs)
     int tune_cov_bps = 8;                                // BQC_COV_BPS: coverage CTAs per SM (upper bound)
     std::vector<CovState> cov;

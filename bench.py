@@ -131,43 +131,61 @@ def split_batches(offsets, max_bytes):
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled while the bench runs (NVML from a thread every ~4 ms; `nvidia-smi -lms`
+    cannot go below tens of milliseconds and missed the ~100 ms timed region).  mark() is called when the timed
+    region starts: stop() reports the samples taken from then on (all samples if there were none)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.proc = None
+        import threading
+        self.samples = []          # (time, sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self.t_mark = None
+        self._halt = threading.Event()
+        self.thread = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._halt.is_set():
+                    try:
+                        self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                    except Exception:
+                        pass
+                    self._halt.wait(0.004)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
         except Exception:
-            pass
+            self.thread = None
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if not self.proc:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        if not self.thread:
             return out
-        self.proc.terminate()
-        try:
-            text, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            return out
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in text.strip().split("\n"):
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, f[3:7]):
-                if v == "Active":
-                    reasons.add(nme)
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        self._halt.set()
+        self.thread.join(timeout=2)
+        timed = [x for x in self.samples if self.t_mark is not None and x[0] >= self.t_mark]
+        use = timed or self.samples
+        if use:
+            mask = 0
+            for x in use:
+                mask |= x[2]
+            out = {"sm_mhz": statistics.median(x[1] for x in use), "sm_max_mhz": self.max_mhz,
+                   "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(use),
+                   "sampled": "timed region" if timed else "warm-up + timed region", "how": "NVML, 4 ms period"}
         return out
 
 
@@ -363,6 +381,8 @@ def run_b200(args):
     launches0 = eng.kernel_launches
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.mark()
     ev0.record(stream)
     for _ in range(args.steps):
         step()

@@ -2,6 +2,7 @@
 Usage: python profiles/summarize.py r1   (reads gpurun_out/r1_*.ncu-rep and gpurun_out/r1_launches.csv)"""
 import collections
 import csv
+import re
 import json
 import os
 import subprocess
@@ -18,6 +19,10 @@ METRICS = [
 ] + ["smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % k for k in (
     "long_scoreboard", "short_scoreboard", "mio_throttle", "lg_throttle", "barrier", "not_selected", "wait",
     "math_pipe_throttle", "branch_resolving", "no_instruction")]
+
+
+def kernel_name(s):  # "void k_stats<1>(EngineView, ...)" -> "k_stats"
+    return re.sub(r"<.*>", "", re.sub(r"^void ", "", s.split("(")[0])).strip()
 
 
 def raw(rep):
@@ -44,7 +49,7 @@ def main():
         hdr, units, rows = raw(rep)
         kn = hdr.index("Kernel Name")
         for r in rows:
-            k = r[kn].split("(")[0]
+            k = kernel_name(r[kn])
             if k in seen:
                 continue
             seen.add(k)
@@ -85,7 +90,7 @@ def main():
                     v = float(d["Metric Value"].replace(",", ""))
                 except ValueError:
                     continue
-                a = agg.setdefault(d["Kernel Name"].split("(")[0], [0, 0.0])
+                a = agg.setdefault(kernel_name(d["Kernel Name"]), [0, 0.0])
                 a[0] += 1
                 a[1] += v
         with open(os.path.join(dst, "launches.csv"), "w", newline="") as f:
