@@ -85,6 +85,23 @@ def test_other_read_length_and_seed(tmp_path):
 
 
 # ---- device-side framing (kernel_frame.cuh): the engine finds the record boundaries itself ----------------------
+def test_stats_direct_path_switch(tmp_path, monkeypatch):
+    """BQC_STATS_STAGE=0: k_stats reads the records straight from global memory instead of through the per-warp
+    shared-memory staging (same statements, other loaders); stress library so that clipped / indel reads are common."""
+    from bamqc_b200 import synth
+    monkeypatch.setenv("BQC_STATS_STAGE", "0")
+    lib_ = synth.Library(seed=31, n_pairs=6000)
+    lib_.stress()
+    _roundtrip(tmp_path, lib_)
+
+
+def test_long_reads_split_the_staging_span(tmp_path):
+    """2 x 250 bp: the 32 records of a warp (~15 KB) do not fit the 10 KB staging area of k_stats and are staged in
+    pieces; also an odd read length for the reverse-read nibble windows."""
+    from bamqc_b200 import synth
+    _roundtrip(tmp_path, synth.Library(seed=32, n_pairs=4000, read_len=251, ins_mean=450))
+
+
 def test_device_framing_whole_record_slices(tmp_path):
     from bamqc_b200 import synth
     _roundtrip(tmp_path, synth.Library(seed=21, n_pairs=20000), n_batches=3, mode="whole", expect_repaired=False)
