@@ -4,34 +4,14 @@
 //
 // One record per lane.  Control flow is organised in warp-uniform phases separated by __syncwarp():
 //   A  decode, CIGAR summary, aux walk, gates           (short, divergent per lane)
-//   B  triplet walk of the eligible lanes               (rolling 3-base windows over read and reference)
-//   C  per-cycle base / quality pass                    (common trip count = longest read of the warp)
+//   B  triplet walk of the eligible lanes               (CIGAR runs, 14 positions per 16-nibble window: swar.h)
+//   C  per-cycle base / quality pass                    (8 cycles per step, common trip count per warp)
 //   D  per-read histogram bumps, main-chromosome block
-// All tables of the CTA live in shared memory (u32) and are flushed with 64-bit REDs at the end.
+// All tables of the CTA live in shared memory (u32) and are flushed with 64-bit REDs at the end; the record bytes of
+// a warp are staged in shared memory with cp.async (k_stats<true>) or read from global memory (k_stats<false>).
 #pragma once
 
 namespace bqc {
-
-// per-base stream over the 4-bit SEQ field: 16 bases per 8-byte chunk, next base in the low nibble
-struct NibStream {
-    const uint8_t* p;
-    uint64_t w;
-    __device__ __forceinline__ void seek(const uint8_t* seq, uint32_t i) {  // position on base i
-        p = seq + ((i >> 4) << 3);
-        w = swap_nibbles(ldu64(p)) >> (4 * (i & 15u));
-    }
-    static __device__ __forceinline__ uint64_t swap_nibbles(uint64_t x) {
-        return ((x & 0x0F0F0F0F0F0F0F0FULL) << 4) | ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL);
-    }
-    // base i (the caller passes i so that chunk boundaries are detected without extra state)
-    __device__ __forceinline__ uint32_t get(uint32_t i) {
-        if ((i & 15u) == 0) { w = swap_nibbles(ldu64(p)); }
-        uint32_t v = (uint32_t)w & 15u;
-        w >>= 4;
-        if ((i & 15u) == 15u) p += 8;
-        return v;
-    }
-};
 
 __device__ __forceinline__ void red_shared_inc(uint32_t saddr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr));

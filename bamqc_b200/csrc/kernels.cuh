@@ -3,15 +3,16 @@
 // Execution model: one THREAD per BAM record, records dealt to persistent CTAs in
 // an interleaved grid-stride order so neighbouring threads read neighbouring records.  Each statistic
 // family gets its own kernel so that its hot table can be privatised in shared memory:
-//   k_stats  : gate + scalars, QualityCheck per-cycle tables and histograms, TripletCounting walk,
-//              coverage difference-array scatter            (~30 KB of smem tables per CTA)
-//   k_eightmer: OverallNumbers::count8mers                 (32768-bin half table = 128 KB smem per CTA)
+//   k_stats  : gate + scalars, QualityCheck per-cycle tables and histograms, TripletCounting walk
+//              (~21 KB of smem tables + 8 x 10 KB of per-warp record staging per CTA)
+//   k_eightmer: OverallNumbers::count8mers                 (65536 x 16-bit counters = 128 KB smem per CTA)
 //   k_sketch : ReadQualityHasher + RepHash + StreamCounter (F2 table = 128 KB smem per CTA; the 8 MiB
 //              4-bit sketch stays in L2 and is updated with load-test-CAS)
 //   k_cov_*  : coverage windows: prefix sum of the difference ring + histogram
 // Measured on B200 (profiles/ubench): shared-memory atomics sustain ~1700 G/s chip-wide, global REDs to
 // an L2-resident table ~150 G/s and collapse to <14 G/s on hot bins, hence the privatisation.
 //
+// Per-base tests are evaluated 8 or 16 bases at a time on packed words (swar.h); only the table update is per base.
 // All arithmetic is integer; every table update is a commutative add (or a saturating 4-bit add for
 // the sketch), so results do not depend on scheduling and are bit-exact against the oracle.
 #pragma once
