@@ -102,37 +102,16 @@ static void run_parallel(HostPool* pool, int n, const std::function<void(int)>& 
     for (auto& t : th) t.join();
 }
 
-typedef bqc::FrameMeta ScanMeta;  // {rid (< 0: not part of the coverage statistic), pos}: pass 1 (host or k_frame_emit) -> pass 2
-
-struct CovState {  // OverallNumbers::{first,id,shift} (src/OverallNumbers.hpp:37-41) + virtual window index
-    bool first = true;
-    int32_t id = 0;
-    uint32_t shift = 0;
-    uint64_t v1 = 0;         // absolute virtual index of the window held in v1
-    uint64_t flushed = 0;    // absolute virtual position up to which windows have been flushed
-};
-
-struct Segment {  // a run of records of one submission that fits the coverage ring
-    uint64_t r0, r1;
-    std::vector<uint64_t> base_window;  // per lane: window index that code 0 refers to
-    std::vector<uint64_t> flush_to;     // per lane: absolute virtual position to flush up to afterwards
-};
-
 struct DeviceBatch {
     uint8_t* bytes = nullptr;        // allocation: kFrameHead bytes of head room, then the staged data
     const uint8_t* base = nullptr;   // what the record offsets are relative to (bytes + kFrameHead when the host framed, bytes when the device did)
     uint32_t* offsets = nullptr;
-    uint32_t* cov = nullptr;
-    const uint32_t* cov_src = nullptr;  // what k_cov_scatter reads: `cov`, or the slot's pinned host array (device-framed path: 4 bytes per
-                                         // record read once over PCIe instead of an H2D copy that would queue behind the next buffer's copy)
     uint8_t* rec_lane = nullptr;
     uint64_t n_records = 0, n_bytes = 0;
     uint32_t max_lseq = 0;
-    std::vector<Segment> segs;
     uint64_t first_record = 0;
     bool owns = false;
-    std::vector<CovState> cov_after;  // anchor state after this batch (resident path replays)
-    uint64_t records_after = 0;
+    uint64_t records_after = 0;      // records seen once this batch has run (resident path replays)
 };
 struct bqc_batch {
     DeviceBatch d;
@@ -141,23 +120,16 @@ struct bqc_batch {
 struct Slot {  // one half of the staging double buffer
     uint8_t* pinned = nullptr;
     uint32_t* h_offsets = nullptr;
-    uint32_t* h_cov = nullptr;
     uint8_t* h_lane = nullptr;
     DeviceBatch dev;
     cudaEvent_t done = nullptr;
     bool in_flight = false;
     bool queued = false;           // handed to the commit thread, not yet enqueued on the GPU
-    std::vector<ScanMeta> meta;    // pass 1 -> pass 2 (host framing)
     // device framing (kernel_frame.cuh)
     FrameResult* h_frame = nullptr;  // pinned
     FrameResult* d_frame = nullptr;
-    ScanMeta* h_meta = nullptr;      // pinned
-    ScanMeta* d_meta = nullptr;
     uint32_t *d_ws = nullptr, *d_we = nullptr, *d_wc = nullptr, *d_ws2 = nullptr, *d_we2 = nullptr, *d_wc2 = nullptr, *d_bsum = nullptr, *d_bbase = nullptr;
-    cudaEvent_t framed = nullptr, aux_done = nullptr;
-    cudaEvent_t tables_go = nullptr;   // compute-stream position before this buffer's table kernels (coverage waits for it)
-    cudaEvent_t cov_end = nullptr;     // this buffer's coverage kernels are done (recorded by the anchor thread)
-    bool cov_pending = false;          // cov_end has been recorded for the buffer in flight
+    cudaEvent_t framed = nullptr;
     // device inflate (kernel_inflate.cuh)
     uint8_t* d_cin = nullptr;          // compressed BGZF bytes of the submission
     InflateBlock* h_blocks = nullptr;  // pinned
@@ -177,16 +149,17 @@ struct bqc_engine {
     uint32_t n_lanes = 1, n_qk = 1;
     uint64_t sketch_words_per_qk = 0;  // uint32 words
     uint64_t staging_bytes = 0, max_records_per_slot = 0;
-    uint32_t ring_log2 = 26;
 
     // device state
     uint64_t* d_counters = nullptr;
     uint32_t* d_sketch = nullptr;
-    uint32_t* d_ring = nullptr;
-    uint32_t* d_cov_carry = nullptr;
-    uint8_t* d_touch = nullptr;  // one byte per 32 ring entries: granules that received coverage events
-    uint32_t* d_cov_sums = nullptr;
-    uint64_t cov_sums_cap = 0;
+    // coverage (kernel_cov.cuh): carried anchor state + the two open windows per lane, scratch for the batch in flight
+    CovCarry* d_cov_carry = nullptr;   // [n_lanes]
+    int32_t* d_cov_d = nullptr;        // [n_lanes][2][kCovD]
+    uint8_t* d_cov_scratch = nullptr;  // one allocation, carved by cov_scratch_carve
+    uint64_t cov_scratch_cap = 0;      // records
+    uint64_t cov_ctl_bytes = 0;        // tickets + look-back states at the front of the scratch (zeroed per launch group)
+    CovScratch cov_scratch;
     unsigned long long* d_error = nullptr;
     const uint32_t** d_ref = nullptr;
     uint64_t* d_ref_len = nullptr;
@@ -195,7 +168,6 @@ struct bqc_engine {
     std::vector<uint32_t*> ref_bufs;
     std::vector<uint64_t> ref_len;
     cudaStream_t compute = nullptr, copy = nullptr, covs = nullptr;  // covs: coverage scatter + flush (HBM bound) overlaps the table kernels
-    cudaStream_t aux = nullptr;    // small D2H / H2D of the device-framing path (must not queue behind the next big H2D)
     cudaStream_t frames = nullptr; // framing kernels: the H2D copy of the next buffer (copy stream) overlaps them
     cudaEvent_t cov_done = nullptr, cov_go = nullptr;
     static const int kSlots = 4;  // depth of the staging pipeline: framing / anchor pass / H2D / kernels each hold one
@@ -204,7 +176,6 @@ struct bqc_engine {
     cudaEvent_t copied = nullptr;
 
     // host state
-    std::vector<ScanMeta> scan_meta;
     std::vector<uint64_t> frame_offsets;
     int host_threads = 1;
     std::unique_ptr<HostPool> pool;
@@ -218,12 +189,6 @@ struct bqc_engine {
         bool must_align;   // the bytes must end on a record boundary (whole-record submissions, last stream chunk)
     };
     std::deque<Task> ingest;       // stream tasks whose H2D copy + framing kernels are enqueued, not yet launched
-    // the anchor thread takes the sequential coverage recurrence (host_scan_pass2, ~4 ms per 256 MB buffer) and the
-    // coverage launches of device-framed buffers off the commit thread, which then only enqueues copies and kernels
-    std::thread anchor_thread;
-    std::deque<Task> aq;
-    std::condition_variable acv;
-    bool abusy = false;
     int last_stream_slot = -1;     // slot of the previous stream submission (source of the carried partial record)
     bool device_framing = true;    // BQC_HOST_FRAMING=1 turns it off (A/B tests)
     bool trace = false;            // BQC_TRACE=1: per-buffer timings of the commit thread on stderr
@@ -237,8 +202,7 @@ struct bqc_engine {
     int async_rc = 0;
     int tune_stats_bps = 0, tune_sketch_threads = 1024, tune_stats_stage = 1;  // BQC_STATS_STAGE=0: k_stats reads records straight from global memory (A/B tests)
     int _pad_tune = 0;   // BQC_STATS_BPS / BQC_SKETCH_THREADS (tuning knobs)
-    int tune_cov_bps = 8;                                // BQC_COV_BPS: coverage CTAs per SM (upper bound)
-    std::vector<CovState> cov;
+    int tune_cov_bps = 4;                                // BQC_COV_BPS: k_cov_tiles CTAs per SM
     uint64_t records_seen = 0, frames_repaired = 0;
     std::atomic<uint64_t> launches{0};   // kernels launched (commit thread, anchor thread, caller)
     bool finished = false;
@@ -323,7 +287,6 @@ static void free_device_batch(DeviceBatch& d) {
     if (!d.owns) return;
     cudaFree(d.bytes);
     cudaFree(d.offsets);
-    cudaFree(d.cov);
     cudaFree(d.rec_lane);
     d = DeviceBatch();
 }
@@ -331,42 +294,33 @@ static void free_device_batch(DeviceBatch& d) {
 extern "C" void bqc_destroy(bqc_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
-    if (e->commit_thread.joinable() || e->anchor_thread.joinable()) {
+    if (e->commit_thread.joinable()) {
         { std::lock_guard<std::mutex> g(e->cm); e->cstop = true; }
         e->ccv.notify_all();
-        if (e->commit_thread.joinable()) e->commit_thread.join();
-        e->acv.notify_all();
-        if (e->anchor_thread.joinable()) e->anchor_thread.join();
+        e->commit_thread.join();
     }
     if (e->compute) cudaStreamSynchronize(e->compute);
     if (e->copy) cudaStreamSynchronize(e->copy);
     if (e->covs) cudaStreamSynchronize(e->covs);
-    if (e->aux) cudaStreamSynchronize(e->aux);
     if (e->frames) cudaStreamSynchronize(e->frames);
     for (auto& s : e->slots) {
         if (s.pinned) cudaFreeHost(s.pinned);
         if (s.h_offsets) cudaFreeHost(s.h_offsets);
-        if (s.h_cov) cudaFreeHost(s.h_cov);
         if (s.h_lane) cudaFreeHost(s.h_lane);
         if (s.h_frame) cudaFreeHost(s.h_frame);
-        if (s.h_meta) cudaFreeHost(s.h_meta);
         if (s.h_blocks) cudaFreeHost(s.h_blocks);
         cudaFree(s.d_cin); cudaFree(s.d_blocks); cudaFree(s.d_ictl);
-        cudaFree(s.d_frame); cudaFree(s.d_meta); cudaFree(s.d_ws); cudaFree(s.d_we); cudaFree(s.d_wc); cudaFree(s.d_ws2); cudaFree(s.d_we2); cudaFree(s.d_wc2); cudaFree(s.d_bsum); cudaFree(s.d_bbase);
+        cudaFree(s.d_frame); cudaFree(s.d_ws); cudaFree(s.d_we); cudaFree(s.d_wc); cudaFree(s.d_ws2); cudaFree(s.d_we2); cudaFree(s.d_wc2); cudaFree(s.d_bsum); cudaFree(s.d_bbase);
         free_device_batch(s.dev);
         if (s.done) cudaEventDestroy(s.done);
         if (s.framed) cudaEventDestroy(s.framed);
-        if (s.aux_done) cudaEventDestroy(s.aux_done);
-        if (s.tables_go) cudaEventDestroy(s.tables_go);
-        if (s.cov_end) cudaEventDestroy(s.cov_end);
     }
     for (auto p : e->ref_bufs) cudaFree(p);
     cudaFree(e->d_counters);
     cudaFree(e->d_sketch);
-    cudaFree(e->d_ring);
     cudaFree(e->d_cov_carry);
-    cudaFree(e->d_touch);
-    cudaFree(e->d_cov_sums);
+    cudaFree(e->d_cov_d);
+    cudaFree(e->d_cov_scratch);
     cudaFree(e->d_error);
     cudaFree((void*)e->d_ref);
     cudaFree(e->d_ref_len);
@@ -376,7 +330,6 @@ extern "C" void bqc_destroy(bqc_engine* e) {
     if (e->cov_done) cudaEventDestroy(e->cov_done);
     if (e->cov_go) cudaEventDestroy(e->cov_go);
     if (e->covs) cudaStreamDestroy(e->covs);
-    if (e->aux) cudaStreamDestroy(e->aux);
     if (e->frames) cudaStreamDestroy(e->frames);
     if (e->compute) cudaStreamDestroy(e->compute);
     if (e->copy) cudaStreamDestroy(e->copy);
@@ -391,7 +344,6 @@ static int alloc_device_batch(bqc_engine* e, DeviceBatch& d, uint64_t bytes_cap,
     CU(cudaMemset(d.bytes, 0, kFrameHead + bytes_cap + 256));
     d.base = d.bytes + kFrameHead;
     CU(cudaMalloc(&d.offsets, (rec_cap + 1) * sizeof(uint32_t)));
-    CU(cudaMalloc(&d.cov, (rec_cap + 1) * sizeof(uint32_t)));
     if (e->n_lanes > 1) CU(cudaMalloc(&d.rec_lane, rec_cap + 1));
     return 0;
 }
@@ -404,23 +356,21 @@ extern "C" int bqc_reset(bqc_engine* e) {
     CU(cudaStreamSynchronize(e->compute));
     CU(cudaStreamSynchronize(e->copy));
     CU(cudaStreamSynchronize(e->covs));
-    CU(cudaStreamSynchronize(e->aux));
     CU(cudaStreamSynchronize(e->frames));
     e->last_stream_slot = -1;
     e->host_carry.clear();
     CU(cudaMemsetAsync(e->d_counters, 0, e->n_lanes * e->L.lane_stride * 8, e->compute));
     CU(cudaMemsetAsync(e->d_sketch, 0, e->n_lanes * e->n_qk * e->sketch_words_per_qk * 4, e->compute));
-    CU(cudaMemsetAsync(e->d_ring, 0, (uint64_t)e->n_lanes * (1ull << e->ring_log2) * 4, e->compute));
-    CU(cudaMemsetAsync(e->d_cov_carry, 0, e->n_lanes * 4, e->compute));
-    CU(cudaMemsetAsync(e->d_touch, 0, (uint64_t)e->n_lanes * ((1ull << e->ring_log2) >> 5), e->compute));
+    // OverallNumbers(): first = true, v1 = v2 = 0 (src/OverallNumbers.hpp:50-57)
+    CU(cudaMemsetAsync(e->d_cov_d, 0, (uint64_t)e->n_lanes * 2 * kCovD * 4, e->compute));
+    k_cov_init<<<(e->n_lanes + 63) / 64, 64, 0, e->compute>>>(e->d_cov_carry, e->n_lanes);
     CU(cudaMemsetAsync(e->d_error, 0xFF, 8, e->compute));
-    CU(cudaStreamSynchronize(e->compute));  // the coverage stream starts from a clean ring
-    e->cov.assign(e->n_lanes, CovState());
+    CU(cudaStreamSynchronize(e->compute));  // the coverage stream starts from a clean state
     e->records_seen = 0;
     e->finished = false;
     e->have_results = false;
     e->host_error.code = 0;
-    for (auto& s : e->slots) { s.in_flight = false; s.cov_pending = false; }
+    for (auto& s : e->slots) s.in_flight = false;
     return 0;
 }
 
@@ -465,17 +415,15 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     if (e->staging_bytes > 0xF0000000ull) e->staging_bytes = 0xF0000000ull;
     e->max_records_per_slot = e->staging_bytes / 36 + 16;  // a record is at least 37 bytes (block_size + 32 fixed + a NUL name)
     e->blocks_per_slot = e->staging_bytes / 4096 + 4096;   // BGZF blocks per submission (larger inputs are split)
-    e->ring_log2 = cfg->cov_ring_log2 ? cfg->cov_ring_log2 : 28;
     if (const char* v = getenv("BQC_STATS_BPS")) e->tune_stats_bps = atoi(v);
     if (const char* v = getenv("BQC_STATS_STAGE")) e->tune_stats_stage = atoi(v);
-    if (const char* v = getenv("BQC_COV_BPS")) e->tune_cov_bps = std::max(1, std::min(8, atoi(v)));
+    if (const char* v = getenv("BQC_COV_BPS")) e->tune_cov_bps = std::max(1, std::min(6, atoi(v)));
     if (const char* v = getenv("BQC_HOST_FRAMING")) e->device_framing = atoi(v) == 0;
     if (const char* v = getenv("BQC_TRACE")) e->trace = atoi(v) != 0;
     if (const char* v = getenv("BQC_FRAME_FORCE_REPAIR")) e->force_bad_frames = atoi(v) != 0;
     if (const char* v = getenv("BQC_SKETCH_THREADS")) e->tune_sketch_threads = std::max(32, std::min(1024, atoi(v) & ~31));
     e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     if (e->host_threads > 1) e->pool.reset(new HostPool(e->host_threads - 1));
-    if (e->ring_log2 < 13 || e->ring_log2 > 30) { set_error(e, "bqc_create: cov_ring_log2 out of range"); delete e; return BQC_ERR_ARG; }
 
     int rc = [&]() -> int {
         CU(cudaSetDevice(cfg->device));
@@ -485,18 +433,14 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         CU(cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&e->covs, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&e->frames, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&e->cov_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&e->cov_go, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&e->copied, cudaEventDisableTiming));
         CU(cudaMalloc(&e->d_counters, e->n_lanes * e->L.lane_stride * 8));
         CU(cudaMalloc(&e->d_sketch, std::max<uint64_t>(4, e->n_lanes * e->n_qk * e->sketch_words_per_qk * 4)));
-        CU(cudaMalloc(&e->d_ring, (uint64_t)e->n_lanes * (1ull << e->ring_log2) * 4));
-        CU(cudaMalloc(&e->d_cov_carry, e->n_lanes * 4));
-        CU(cudaMalloc(&e->d_touch, (uint64_t)e->n_lanes * ((1ull << e->ring_log2) >> 5)));
-        e->cov_sums_cap = ((1ull << e->ring_log2) + kCovTile - 1) / kCovTile + 4;
-        CU(cudaMalloc(&e->d_cov_sums, e->cov_sums_cap * 8));
+        CU(cudaMalloc(&e->d_cov_carry, e->n_lanes * sizeof(CovCarry)));
+        CU(cudaMalloc(&e->d_cov_d, (uint64_t)e->n_lanes * 2 * kCovD * 4));
         CU(cudaMalloc(&e->d_error, 8));
         int nref = std::max(1, cfg->n_ref);
         CU(cudaMalloc((void**)&e->d_ref, nref * sizeof(uint32_t*)));
@@ -517,9 +461,6 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         for (auto& s : e->slots) {
             CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s.framed, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&s.aux_done, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&s.tables_go, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&s.cov_end, cudaEventDisableTiming));
         }
         // opt in to large dynamic shared memory
         CU(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kInflateStreams * sizeof(InflateTabs))));
@@ -529,6 +470,8 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         CU(cudaFuncSetAttribute(k_stats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(k_eightmer, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CU(cudaFuncSetAttribute(k_sketch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        CU(cudaFuncSetAttribute(k_cov_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCovBlockSmem));
+        CU(cudaFuncSetAttribute(k_cov_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCovCodesSmem));
         CU(cudaFuncSetAttribute(k_sketch32, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024 + (int)sizeof(HashPairTable) + (int)(kSketchThreads / 32 * kSketchQueue * 8)));
         return 0;
     }();
@@ -701,12 +644,11 @@ static uint32_t host_lane(const bqc_engine* e, const uint8_t* r, uint32_t avail)
     return 0;
 }
 
-// Pass 1 of the host pre-pass (host threads): touch every record header once; 32-bit offsets, lane, longest
-// read and a compact (rid, pos) pair for the records that take part in the coverage statistic.
-static void host_scan_pass1(bqc_engine* e, const uint8_t* data, const uint64_t* offs, uint64_t n_records, uint32_t* o32, uint8_t* lane_out, ScanMeta* meta, uint32_t& max_lseq) {
+// Host pre-pass of a host-framed submission (host threads): touch every record header once; 32-bit offsets, lane
+// and longest read.  (The coverage statistic needs nothing from the host any more: kernel_cov.cuh.)
+static void host_scan_pass1(bqc_engine* e, const uint8_t* data, const uint64_t* offs, uint64_t n_records, uint32_t* o32, uint8_t* lane_out, uint32_t& max_lseq) {
     max_lseq = 0;
     const uint64_t base_off = offs[0];
-    typedef ScanMeta Meta;
     const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)e->host_threads, n_records / 65536));
     std::vector<uint32_t> tmax((size_t)T, 0);
     auto pass1 = [&](int t) {
@@ -717,18 +659,12 @@ static void host_scan_pass1(bqc_engine* e, const uint8_t* data, const uint64_t* 
             if (r + 16 < r1) __builtin_prefetch(data + offs[r + 16]);
             o32[r] = (uint32_t)(offs[r] - base_off);
             uint32_t avail = (uint32_t)(offs[r + 1] - offs[r]);
-            Meta m = {-1, 0};  // rid -1 = does not take part
             uint32_t lane = 0;
             if (avail >= 36) {
-                int32_t rid = (int32_t)rd32(p + 4);
-                uint32_t flag = p[18] | (p[19] << 8);
                 int32_t lseq = (int32_t)rd32(p + 20);
                 if (lseq > 0 && (uint32_t)lseq > mx) mx = (uint32_t)lseq;
                 if (e->n_lanes > 1) lane = host_lane(e, p, avail);
-                bool q = !(flag & 0x900u) && (flag & 0xC0u) && !(flag & 0x4u) && !(flag & 0x400u) && rid >= 0 && rid < e->cfg.n_ref && e->main_chrom[rid];
-                if (q) { m.rid = rid; m.pos = rd32(p + 8); }
             }
-            meta[r] = m;
             if (lane_out) lane_out[r] = (uint8_t)lane;
         }
         tmax[(size_t)t] = mx;
@@ -738,105 +674,6 @@ static void host_scan_pass1(bqc_engine* e, const uint8_t* data, const uint64_t* 
     for (uint32_t v : tmax) max_lseq = std::max(max_lseq, v);
     o32[n_records] = (uint32_t)(offs[n_records] - base_off);
     if (e->profiling) { e->prof_ms[6] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_p1).count(); e->prof_n[6] += 1; }
-}
-
-// Pass 2 (sequential, 8 bytes per record): the anchor recurrence of OverallNumbers::coverage -- the only
-// order-dependent part of the reference (src/OverallNumbers.hpp:84-110) -- and the segments that keep the
-// coverage ring within capacity.
-static void host_scan_pass2(bqc_engine* e, const ScanMeta* meta, uint64_t n_records, uint32_t* cov, const uint8_t* lane_out, std::vector<Segment>& segs) {
-    auto t_p2 = std::chrono::steady_clock::now();
-    const uint64_t ring_size = 1ull << e->ring_log2;
-    auto open_segment = [&](uint64_t r0) {
-        Segment s;
-        s.r0 = r0;
-        s.r1 = r0;
-        s.base_window.resize(e->n_lanes);
-        s.flush_to.resize(e->n_lanes);
-        for (uint32_t l = 0; l < e->n_lanes; ++l) s.base_window[l] = e->cov[l].flushed / 1000;
-        segs.push_back(s);
-    };
-    auto close_segment = [&](uint64_t r1) {
-        Segment& s = segs.back();
-        s.r1 = r1;
-        for (uint32_t l = 0; l < e->n_lanes; ++l) {
-            s.flush_to[l] = e->cov[l].v1 * 1000;
-            e->cov[l].flushed = s.flush_to[l];
-        }
-    };
-    segs.clear();
-    open_segment(0);
-    // (segment changes never alter the anchor state, only which ring window code 0 refers to)
-    const uint64_t* base_window = segs.back().base_window.data();
-    uint64_t seg_r0 = segs.back().r0;
-    if (!lane_out) {
-        // single read group: the anchor state lives in registers.  (A branch-free form of this loop was measured
-        // slower: the predicted branches break the dependency chain through `shift`.)
-        CovState& st = e->cov[0];
-        bool first = st.first;
-        int32_t id = st.id;
-        uint32_t shift = st.shift;
-        uint64_t v1 = st.v1, base0 = base_window[0];
-        const uint64_t limit = ring_size - 8 - 2001;
-        for (uint64_t r = 0; r < n_records; ++r) {
-            const int32_t rid = meta[r].rid;
-            uint32_t code = kNone;
-            if (rid >= 0) {
-                const uint32_t b = meta[r].pos;
-                if (first) { first = false; id = rid; shift = b; }
-                if (id != rid || (uint32_t)(b - shift) > 2000u) { id = rid; v1 += 2; shift = b; }
-                uint32_t pos = b - shift;
-                if (pos > 1000u && pos < 2000u) { v1 += 1; shift += 1000u; pos = b - shift; }
-                if (v1 * 1000 - st.flushed > limit && r > seg_r0) {
-                    close_segment(r);  // uses the state stored before this record
-                    open_segment(r);
-                    base0 = segs.back().base_window[0];
-                    seg_r0 = r;
-                }
-                st.first = false;
-                st.id = id;
-                st.shift = shift;
-                st.v1 = v1;
-                code = (uint32_t)((v1 - base0) << 11) | pos;
-            }
-            cov[r] = code;
-        }
-    } else
-    for (uint64_t r = 0; r < n_records; ++r) {
-        const int32_t rid = meta[r].rid;
-        if (rid < 0) { cov[r] = kNone; continue; }
-        const uint32_t b = meta[r].pos;
-        const uint32_t lane = lane_out ? lane_out[r] : 0u;
-        CovState& st = e->cov[lane];
-        int32_t id = st.id;
-        uint32_t shift = st.shift;
-        uint64_t v1 = st.v1;
-        if (st.first) { id = rid; shift = b; }                                   // src/OverallNumbers.hpp:84-89
-        if (id != rid || (uint32_t)(b - shift) > 2000u) { id = rid; v1 += 2; shift = b; }  // :91-100 reset: two windows flushed
-        uint32_t pos = b - shift;
-        if (pos > 1000u && pos < 2000u) { v1 += 1; shift += 1000u; pos = b - shift; }       // :104-110 roll: one window flushed
-        // everything this record can touch must fit the ring behind the unflushed position
-        if (v1 * 1000 + 2001 - st.flushed > ring_size - 8 && r > seg_r0) {
-            close_segment(r);
-            open_segment(r);
-            base_window = segs.back().base_window.data();
-            seg_r0 = r;
-        }
-        st.first = false;
-        st.id = id;
-        st.shift = shift;
-        st.v1 = v1;
-        cov[r] = (uint32_t)((v1 - base_window[lane]) << 11) | pos;
-    }
-    close_segment(n_records);
-    if (e->profiling) { e->prof_ms[7] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_p2).count(); e->prof_n[7] += 1; }
-}
-
-// both passes back to back (resident path)
-static int host_scan(bqc_engine* e, const uint8_t* data, const uint64_t* offs, uint64_t n_records, uint32_t* o32, uint32_t* cov, uint8_t* lane_out, uint32_t& max_lseq, std::vector<Segment>& segs) {
-    if (e->scan_meta.size() < n_records) e->scan_meta.resize(n_records);
-    host_scan_pass1(e, data, offs, n_records, o32, lane_out, e->scan_meta.data(), max_lseq);
-    host_scan_pass2(e, e->scan_meta.data(), n_records, cov, lane_out, segs);
-    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -888,26 +725,49 @@ extern "C" int bqc_profile_read(bqc_engine* e, double ms_out[12], uint64_t n_out
 // ------------------------------------------------------------------------------------------------
 // kernel launches for one device-resident batch
 // ------------------------------------------------------------------------------------------------
-static int launch_cov_flush(bqc_engine* e, uint32_t lane, uint64_t from_abs, uint64_t to_abs) {
-    if (to_abs <= from_abs) return 0;
-    uint64_t len = to_abs - from_abs;
-    uint32_t mask = (uint32_t)((1ull << e->ring_log2) - 1);
-    uint32_t* ring = e->d_ring + (uint64_t)lane * (1ull << e->ring_log2);
-    uint32_t start = (uint32_t)(from_abs & mask);
-    uint64_t ntiles = (len + 31 + kCovTile - 1) / kCovTile;  // tiles are aligned to 32-entry granules
-    if (ntiles + 1 > e->cov_sums_cap) { set_error(e, "coverage flush larger than the ring"); return BQC_ERR_ARG; }
-    // a small grid: the flush is bound by the look-back latency, not by throughput, and a full-occupancy grid would
-    // evict the table kernels it is meant to overlap with
-    int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)e->n_sm * e->tune_cov_bps);
-    unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
-    ProfScope prof(e, 3, e->covs);
-    // tile states + ticket live in one buffer: [0] = ticket, [1..] = states
-    CU(cudaMemsetAsync(e->d_cov_sums, 0, (ntiles + 1) * 8, e->covs));
-    uint8_t* touch = e->d_touch + (uint64_t)lane * ((1ull << e->ring_log2) >> 5);
-    k_cov_flush<<<grid, kCovThreads, 0, e->covs>>>(ring, touch, mask, start, len, e->d_cov_carry + lane, (unsigned long long*)e->d_cov_sums + 1,
-                                               (uint32_t*)e->d_cov_sums, poscov);
-    e->launches += 1;
-    CU(cudaGetLastError());
+// Scratch of the coverage kernels for a batch of up to n records: one allocation, grown on demand (rare: the first
+// batch, or a larger resident batch).  Layout: control words that are zeroed before every launch group (tickets,
+// look-back states), then the per-record and per-block arrays.
+static int ensure_cov_scratch(bqc_engine* e, uint64_t n_records) {
+    if (n_records <= e->cov_scratch_cap && e->d_cov_scratch) return 0;
+    const uint64_t N = std::max<uint64_t>(n_records + n_records / 8, 1u << 16);
+    const uint64_t nblk = N / kCovRB + 2, nprep = N / kCovPrepTile + 2, ntile = N / 4 + 16;
+    auto up = [](uint64_t x) { return (x + 255) & ~255ull; };
+    uint64_t o = 0;
+    const uint64_t o_tickets = o; o += up(16);
+    const uint64_t o_lbp = o; o += up(nprep * 8);
+    const uint64_t o_lbc = o; o += up(nblk * 8);
+    const uint64_t ctl = o;
+    const uint64_t o_rid = o; o += up(N * 4);
+    const uint64_t o_b = o; o += up(N * 4);
+    const uint64_t o_iv = o; o += up(N * 4);
+    const uint64_t o_rec = o; o += up(N * 4);
+    const uint64_t o_base = o; o += up(N * 8);
+    const uint64_t o_ab = o; o += up(N * 4);
+    const uint64_t o_tab = o; o += up(nblk * 1024 * 2);
+    const uint64_t o_desc = o; o += up(nblk * 16);
+    const uint64_t o_state = o; o += up(nblk * 4);
+    const uint64_t o_first = o; o += up(ntile * 4);
+    CU(cudaStreamSynchronize(e->covs));
+    if (e->d_cov_scratch) { cudaFree(e->d_cov_scratch); e->d_cov_scratch = nullptr; e->cov_scratch_cap = 0; }
+    CU(cudaMalloc(&e->d_cov_scratch, o));
+    uint8_t* m = e->d_cov_scratch;
+    CovScratch& S = e->cov_scratch;
+    S.tickets = (uint32_t*)(m + o_tickets);
+    S.lb_prep = (unsigned long long*)(m + o_lbp);
+    S.lb_codes = (unsigned long long*)(m + o_lbc);
+    S.q_rid = (int32_t*)(m + o_rid);
+    S.q_b = (uint32_t*)(m + o_b);
+    S.q_iv = (uint32_t*)(m + o_iv);
+    S.q_rec = (uint32_t*)(m + o_rec);
+    S.base = (unsigned long long*)(m + o_base);
+    S.ab = (uint32_t*)(m + o_ab);
+    S.tables = (uint16_t*)(m + o_tab);
+    S.desc = (uint4*)(m + o_desc);
+    S.state_in = (uint32_t*)(m + o_state);
+    S.first_rec = (uint32_t*)(m + o_first);
+    e->cov_scratch_cap = N;
+    e->cov_ctl_bytes = ctl;
     return 0;
 }
 
@@ -916,9 +776,6 @@ static EngineView make_view(bqc_engine* e) {
     E.L = e->L;
     E.counters = e->d_counters;
     E.sketch = e->d_sketch;
-    E.ring = e->d_ring;
-    E.touch = e->d_touch;
-    E.ring_mask = (uint32_t)((1ull << e->ring_log2) - 1);
     E.ref = e->d_ref;
     E.ref_len = e->d_ref_len;
     E.main_chrom = e->d_main_chrom;
@@ -951,32 +808,37 @@ static int batch_launch_setup(bqc_engine* e, const DeviceBatch& d, BatchLaunch& 
     return 0;
 }
 
-// The coverage work (scatter + window flush) is HBM bound, the table kernels are issue bound: it runs on its own
-// stream so that the two overlap.  The caller has made e->covs wait for the batch's data.
+// OverallNumbers::coverage for one device-resident batch (kernel_cov.cuh), on its own stream so that it overlaps the
+// table kernels.  The caller has made e->covs wait for the batch's data.  Nothing comes back to the host: the anchor
+// state and the two open windows are carried on the device from batch to batch.
 static int launch_cov(bqc_engine* e, const DeviceBatch& d, const BatchLaunch& BL) {
-    const uint64_t ring_size = 1ull << e->ring_log2;
-    // the coverage ring is fed and drained segment by segment (a segment is what fits the ring)
-    for (const Segment& sg : d.segs) {
-        uint64_t ns = sg.r1 - sg.r0;
+    const uint64_t n = d.n_records;
+    if (n) {
+        int rc = ensure_cov_scratch(e, n);
+        if (rc) return rc;
+        const CovScratch& S = e->cov_scratch;
+        BatchView B;
+        B.bytes = d.base;
+        B.offsets = d.offsets;
+        B.rec_lane = d.rec_lane;
+        B.n_records = (uint32_t)n;
+        B.cycb = BL.cycb;
+        B.first_record = d.first_record;
+        const uint32_t nprep = (uint32_t)((n + kCovPrepTile - 1) / kCovPrepTile);
+        const uint32_t nblk = (uint32_t)((n + kCovRB - 1) / kCovRB);
+        ProfScope prof(e, 3, e->covs);
         for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
-            if (ns) {
-                BatchView B;
-                B.bytes = d.base;
-                B.offsets = d.offsets + sg.r0;
-                B.cov = (d.cov_src ? d.cov_src : d.cov) + sg.r0;
-                B.rec_lane = d.rec_lane ? d.rec_lane + sg.r0 : nullptr;
-                B.n_records = (uint32_t)ns;
-                B.cycb = BL.cycb;
-                B.first_record = d.first_record + sg.r0;
-                B.ring_base = (uint32_t)((sg.base_window[lane] * 1000) & (ring_size - 1));
-                int grid = (int)std::min<uint64_t>((ns + 255) / 256, (uint64_t)e->n_sm * e->tune_cov_bps);
-                ProfScope prof(e, 3, e->covs);
-                k_cov_scatter<<<grid, 256, 0, e->covs>>>(BL.E, B, lane);
-                e->launches += 1;
-            }
-            uint64_t from = sg.base_window[lane] * 1000;
-            int rc = launch_cov_flush(e, lane, from, sg.flush_to[lane]);
-            if (rc) return rc;
+            CovCarry* carry = e->d_cov_carry + lane;
+            int32_t* cd = e->d_cov_d + (uint64_t)lane * 2 * kCovD;
+            unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
+            CU(cudaMemsetAsync(e->d_cov_scratch, 0, e->cov_ctl_bytes, e->covs));
+            k_cov_prep<<<(int)std::min<uint32_t>(nprep, (uint32_t)e->n_sm * 8u), 256, 0, e->covs>>>(BL.E, B, lane, S, carry);
+            k_cov_tables<<<nblk, kCovBlockThreads, kCovBlockSmem, e->covs>>>(S, carry);
+            k_cov_link<<<1, 256, 0, e->covs>>>(S, carry);
+            k_cov_codes<<<(int)std::min<uint32_t>(nblk, (uint32_t)e->n_sm * 2u), kCovBlockThreads, kCovCodesSmem, e->covs>>>(S, carry);
+            k_cov_tiles<<<e->n_sm * e->tune_cov_bps, kCovTileThreads, 0, e->covs>>>(B, S, carry, cd, poscov);
+            k_cov_carry<<<1, 1024, 0, e->covs>>>(B, S, carry, cd);
+            e->launches += 6;
         }
     }
     CU(cudaEventRecord(e->cov_done, e->covs));
@@ -992,12 +854,10 @@ static int launch_tables(bqc_engine* e, const DeviceBatch& d, const BatchLaunch&
         BatchView B;
         B.bytes = d.base;
         B.offsets = d.offsets;
-        B.cov = d.cov;
         B.rec_lane = d.rec_lane;
         B.n_records = (uint32_t)n;
         B.cycb = BL.cycb;
         B.first_record = d.first_record;
-        B.ring_base = 0;
         int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * BL.bps);
         {
             ProfScope prof(e, 0);
@@ -1054,14 +914,11 @@ static int ensure_slot(bqc_engine* e, Slot& s) {
     // kFrameHead bytes of head room in front of the staging area: a carried partial record goes there
     CU(cudaHostAlloc((void**)&s.pinned, kFrameHead + e->staging_bytes + 256, cudaHostAllocDefault));
     CU(cudaHostAlloc((void**)&s.h_offsets, (rc_ + 1) * 4, cudaHostAllocDefault));
-    CU(cudaHostAlloc((void**)&s.h_cov, (rc_ + 1) * 4, cudaHostAllocDefault));
     if (e->n_lanes > 1) CU(cudaHostAlloc((void**)&s.h_lane, rc_ + 1, cudaHostAllocDefault));
     CU(cudaHostAlloc((void**)&s.h_frame, sizeof(FrameResult), cudaHostAllocDefault));
-    CU(cudaHostAlloc((void**)&s.h_meta, (rc_ + 1) * sizeof(ScanMeta), cudaHostAllocDefault));
     const uint64_t nwin = (kFrameHead + e->staging_bytes + kFrameWindow - 1) / kFrameWindow + 1;
     const uint64_t nblk = (nwin + kFrameThreads - 1) / kFrameThreads;
     CU(cudaMalloc(&s.d_frame, sizeof(FrameResult)));
-    CU(cudaMalloc(&s.d_meta, (rc_ + 1) * sizeof(ScanMeta)));
     CU(cudaMalloc(&s.d_ws, nwin * 4));
     CU(cudaMalloc(&s.d_we, nwin * 4));
     CU(cudaMalloc(&s.d_wc, nwin * 4));
@@ -1078,21 +935,18 @@ static int ensure_slot(bqc_engine* e, Slot& s) {
     return alloc_device_batch(e, s.dev, e->staging_bytes, rc_);
 }
 
-// host-framed task: anchor pass, copies and launches
+// host-framed task: copies and launches
 static int commit_task(bqc_engine* e, const bqc_engine::Task& t) {
     Slot& s = e->slots[t.slot];
     DeviceBatch& d = s.dev;
     const uint64_t n_records = t.n_records;
-    host_scan_pass2(e, s.meta.data(), n_records, s.h_cov, e->n_lanes > 1 ? s.h_lane : nullptr, d.segs);
     d.max_lseq = t.max_lseq;
     d.n_records = n_records;
     d.n_bytes = t.span;
     d.first_record = e->records_seen;
     d.base = d.bytes + kFrameHead;
-    d.cov_src = nullptr;
     CU(cudaMemcpyAsync(d.bytes + kFrameHead, t.h2d_src, t.span, cudaMemcpyHostToDevice, e->copy));
     CU(cudaMemcpyAsync(d.offsets, s.h_offsets, (n_records + 1) * 4, cudaMemcpyHostToDevice, e->copy));
-    CU(cudaMemcpyAsync(d.cov, s.h_cov, n_records * 4, cudaMemcpyHostToDevice, e->copy));
     if (e->n_lanes > 1) CU(cudaMemcpyAsync(d.rec_lane, s.h_lane, n_records, cudaMemcpyHostToDevice, e->copy));
     CU(cudaEventRecord(e->copied, e->copy));
     CU(cudaStreamWaitEvent(e->compute, e->copied, 0));
@@ -1139,8 +993,8 @@ static int stream_stage_a(bqc_engine* e, const bqc_engine::Task& t) {
     }
     k_frame_blocksum<<<nblk, kFrameThreads, 0, e->frames>>>(nwin, s.d_wc, s.d_bsum);
     k_frame_verify<<<1, 1024, 0, e->frames>>>(s.d_frame, nwin, nblk, s.d_ws, s.d_we, s.d_bsum, s.d_bbase, d.offsets, rec_cap, e->force_bad_frames ? 1u : 0u, t.mode == 2 ? s.d_ictl : nullptr);
-    k_frame_repair<<<1, 32, 0, e->frames>>>(d.bytes, s.d_frame, e->cfg.n_ref, e->d_main_chrom, d.offsets, s.d_meta, rec_cap);
-    k_frame_emit<<<nblk, kFrameThreads, 0, e->frames>>>(d.bytes, s.d_frame, e->cfg.n_ref, e->d_main_chrom, nwin, s.d_ws, s.d_wc, s.d_bbase, d.offsets, s.d_meta);
+    k_frame_repair<<<1, 32, 0, e->frames>>>(d.bytes, s.d_frame, e->cfg.n_ref, e->d_main_chrom, d.offsets, nullptr, rec_cap);
+    k_frame_emit<<<nblk, kFrameThreads, 0, e->frames>>>(d.bytes, s.d_frame, e->cfg.n_ref, e->d_main_chrom, nwin, s.d_ws, s.d_wc, s.d_bbase, d.offsets, nullptr);
     e->launches += 10;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(s.h_frame, s.d_frame, sizeof(FrameResult), cudaMemcpyDeviceToHost, e->frames));
@@ -1149,8 +1003,7 @@ static int stream_stage_a(bqc_engine* e, const bqc_engine::Task& t) {
     return 0;
 }
 
-// stage B: read the frame header back, launch the table kernels, run the anchor pass on the (rid, pos) pairs of
-// the buffer and launch the coverage kernels
+// stage B: read the frame header back (record count, longest read), launch the coverage and the table kernels
 static int stream_stage_b(bqc_engine* e, const bqc_engine::Task& t) {
     Slot& s = e->slots[t.slot];
     DeviceBatch& d = s.dev;
@@ -1188,75 +1041,17 @@ static int stream_stage_b(bqc_engine* e, const bqc_engine::Task& t) {
     d.base = d.bytes;
     e->records_seen += n;
     if (n) {
-        // the (rid, pos) pairs come back on the aux stream while the table kernels are being launched
-        CU(cudaStreamWaitEvent(e->aux, s.framed, 0));
-        CU(cudaMemcpyAsync(s.h_meta, s.d_meta, n * sizeof(ScanMeta), cudaMemcpyDeviceToHost, e->aux));
-        CU(cudaEventRecord(s.aux_done, e->aux));
-        BatchLaunch BL;
-        int rc = batch_launch_setup(e, d, BL);
-        if (rc) return rc;
         CU(cudaStreamWaitEvent(e->compute, s.framed, 0));
-        CU(cudaEventRecord(s.tables_go, e->compute));  // coverage of this batch does not overtake the previous batch's tables
-        rc = launch_tables(e, d, BL);
+        int rc = run_device_batch(e, d);
         if (rc) return rc;
         if (e->trace) {
             auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-            fprintf(stderr, "[bqc trace] slot %d: repaired %u, wait framed %.2f ms, launch tables %.2f ms, n=%llu\n", t.slot, fr.repaired, ms(t_b0, t_b1),
+            fprintf(stderr, "[bqc trace] slot %d: repaired %u, wait framed %.2f ms, launches %.2f ms, n=%llu\n", t.slot, fr.repaired, ms(t_b0, t_b1),
                     ms(t_b1, std::chrono::steady_clock::now()), (unsigned long long)n);
         }
     }
     CU(cudaEventRecord(s.done, e->compute));
     return 0;
-}
-
-// anchor thread: the sequential coverage recurrence over the (rid, pos) pairs of a device-framed buffer, then its
-// coverage kernels (own stream; they wait for the data and for the position of the compute stream before this buffer)
-static int anchor_stage(bqc_engine* e, const bqc_engine::Task& t) {
-    Slot& s = e->slots[t.slot];
-    DeviceBatch& d = s.dev;
-    const uint64_t n = d.n_records;
-    auto t0 = std::chrono::steady_clock::now();
-    CU(cudaEventSynchronize(s.aux_done));
-    auto t1 = std::chrono::steady_clock::now();
-    host_scan_pass2(e, s.h_meta, n, s.h_cov, nullptr, d.segs);
-    if (e->trace) {
-        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        fprintf(stderr, "[bqc trace] slot %d (anchor): wait pairs %.2f ms, pass2 %.2f ms, segs=%zu\n", t.slot, ms(t0, t1), ms(t1, std::chrono::steady_clock::now()), d.segs.size());
-    }
-    d.cov_src = s.h_cov;
-    BatchLaunch BL;
-    int rc = batch_launch_setup(e, d, BL);
-    if (rc) return rc;
-    CU(cudaStreamWaitEvent(e->covs, s.tables_go, 0));
-    rc = launch_cov(e, d, BL);
-    if (rc) return rc;
-    CU(cudaEventRecord(s.cov_end, e->covs));
-    s.cov_pending = true;
-    return 0;
-}
-
-static void anchor_loop(bqc_engine* e) {
-    cudaSetDevice(e->cfg.device);
-    for (;;) {
-        bqc_engine::Task t;
-        {
-            std::unique_lock<std::mutex> g(e->cm);
-            e->acv.wait(g, [&] { return e->cstop || !e->aq.empty(); });
-            if (e->aq.empty()) return;
-            t = e->aq.front();
-            e->aq.pop_front();
-            e->abusy = true;
-        }
-        int rc = e->async_rc ? e->async_rc : anchor_stage(e, t);
-        {
-            std::lock_guard<std::mutex> g(e->cm);
-            e->slots[t.slot].queued = false;
-            e->slots[t.slot].in_flight = rc == 0;
-            e->abusy = false;
-            if (rc && !e->async_rc) e->async_rc = rc;
-        }
-        e->ccv_idle.notify_all();
-    }
 }
 
 static void commit_loop(bqc_engine* e) {
@@ -1269,7 +1064,7 @@ static void commit_loop(bqc_engine* e) {
             e->ccv.wait(g, [&] { return e->cstop || !e->cq.empty() || !e->ingest.empty(); });
             if (e->cq.empty() && e->ingest.empty()) return;  // stop requested and nothing left
             // keep up to two stream buffers in the copy + framing stage so that the H2D copy of the next buffer
-            // overlaps the anchor pass and the launches of this one
+            // overlaps the launches of this one
             // (tasks complete in submission order: a host-framed task waits for the stream tasks before it)
             const bool take_new = !e->cq.empty() && (e->cq.front().mode != 0 ? e->ingest.size() < 2 : e->ingest.empty());
             if (take_new) {
@@ -1287,10 +1082,6 @@ static void commit_loop(bqc_engine* e) {
         bool finished_slot = false;
         if (have_new) {
             if (t.mode == 0) {
-                {   // the host-framed path runs the recurrence here: wait until the anchor thread has caught up
-                    std::unique_lock<std::mutex> g(e->cm);
-                    e->ccv_idle.wait(g, [&] { return e->aq.empty() && !e->abusy; });
-                }
                 if (!rc) rc = commit_task(e, t);
                 finished_slot = true;
             }
@@ -1299,13 +1090,6 @@ static void commit_loop(bqc_engine* e) {
         } else if (have_old) {
             if (!rc) rc = stream_stage_b(e, t);
             finished_slot = true;
-            if (!rc && e->slots[t.slot].dev.n_records) {  // the anchor thread finishes the slot
-                finished_slot = false;
-                std::lock_guard<std::mutex> g(e->cm);
-                if (!e->anchor_thread.joinable()) e->anchor_thread = std::thread(anchor_loop, e);
-                e->aq.push_back(t);
-                e->acv.notify_all();
-            }
         }
         {
             std::lock_guard<std::mutex> g(e->cm);
@@ -1324,7 +1108,7 @@ static void commit_loop(bqc_engine* e) {
 // wait until the commit thread has enqueued everything handed to it; returns its sticky error
 static int drain_commits(bqc_engine* e) {
     std::unique_lock<std::mutex> g(e->cm);
-    e->ccv_idle.wait(g, [&] { return e->cq.empty() && e->ingest.empty() && !e->cbusy && e->aq.empty() && !e->abusy; });
+    e->ccv_idle.wait(g, [&] { return e->cq.empty() && e->ingest.empty() && !e->cbusy; });
     return e->async_rc;
 }
 
@@ -1335,7 +1119,6 @@ static int wait_slot(bqc_engine* e, Slot& s) {
     }
     if (s.in_flight) {
         CU(cudaEventSynchronize(s.done));
-        if (s.cov_pending) { CU(cudaEventSynchronize(s.cov_end)); s.cov_pending = false; }
         s.in_flight = false;
     }
     return 0;
@@ -1392,14 +1175,13 @@ static int submit_host_framed(bqc_engine* e, Slot& s, const uint8_t* src, size_t
     }
     if (n_records > e->max_records_per_slot) { set_error(e, "bqc_submit: too many records for one staging buffer"); return BQC_ERR_ARG; }
     if (n_records == 0) return 0;
-    // pass 1 on the caller's thread (+ pool); pass 2, copies and launches on the commit thread
-    if (s.meta.size() < n_records) s.meta.resize(n_records);
+    // the header pre-pass on the caller's thread (+ pool); copies and launches on the commit thread
     bqc_engine::Task t;
     t.slot = e->next_slot;
     t.n_records = n_records;
     t.mode = 0;
     t.must_align = true;
-    host_scan_pass1(e, src, record_offsets, n_records, s.h_offsets, e->n_lanes > 1 ? s.h_lane : nullptr, s.meta.data(), t.max_lseq);
+    host_scan_pass1(e, src, record_offsets, n_records, s.h_offsets, e->n_lanes > 1 ? s.h_lane : nullptr, t.max_lseq);
     const uint8_t* first = src + record_offsets[0];
     t.span = (size_t)(record_offsets[n_records] - record_offsets[0]);
     t.h2d_src = h2d_source(e, s, first, t.span);
@@ -1584,20 +1366,18 @@ extern "C" int bqc_batch_prepare(bqc_engine* e, const void* data, size_t n_bytes
     DeviceBatch& d = b->d;
     int rc = alloc_device_batch(e, d, n_bytes, n_records);
     if (rc) { free_device_batch(d); delete b; return rc; }
-    std::vector<uint32_t> o32(n_records + 1), cov(n_records + 1);
+    std::vector<uint32_t> o32(n_records + 1);
     std::vector<uint8_t> lanes(e->n_lanes > 1 ? n_records + 1 : 0);
-    host_scan(e, src, record_offsets, n_records, o32.data(), cov.data(), lanes.empty() ? nullptr : lanes.data(), d.max_lseq, d.segs);
+    host_scan_pass1(e, src, record_offsets, n_records, o32.data(), lanes.empty() ? nullptr : lanes.data(), d.max_lseq);
     size_t span = n_records ? (size_t)(record_offsets[n_records] - record_offsets[0]) : 0;
     d.n_records = n_records;
     d.n_bytes = span;
     d.first_record = e->records_seen;
     e->records_seen += n_records;
-    d.cov_after = e->cov;
     d.records_after = e->records_seen;
     if (n_records) {
         CU(cudaMemcpy(d.bytes + kFrameHead, src + record_offsets[0], span, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.offsets, o32.data(), (n_records + 1) * 4, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(d.cov, cov.data(), n_records * 4, cudaMemcpyHostToDevice));
         if (e->n_lanes > 1) CU(cudaMemcpy(d.rec_lane, lanes.data(), n_records, cudaMemcpyHostToDevice));
     }
     *out = b;
@@ -1607,8 +1387,7 @@ extern "C" int bqc_batch_run(bqc_engine* e, bqc_batch* b) {
     CU(cudaSetDevice(e->cfg.device));
     if (e->finished) { set_error(e, "bqc_batch_run after bqc_finish (call bqc_reset)"); return BQC_ERR_ARG; }
     drain_commits(e);
-    e->cov = b->d.cov_after;  // replaying a prepared batch restores the anchor state that follows it
-    e->records_seen = b->d.records_after;
+    e->records_seen = b->d.records_after;  // (the coverage anchor state is carried on the device)
     return run_device_batch(e, b->d);
 }
 extern "C" void bqc_batch_free(bqc_engine* e, bqc_batch* b) {
@@ -1679,12 +1458,10 @@ extern "C" int bqc_finish(bqc_engine* e) {
     if (!e->finished) {
         // src/bamqualcheck.cpp:447-453: update_coverage(); update_vectors(); update_coverage() for every lane
         for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
-            CovState& st = e->cov[lane];
-            uint64_t to = (st.v1 + 2) * 1000;
-            int rc = launch_cov_flush(e, lane, st.flushed, to);
-            if (rc) return rc;
-            st.flushed = to;
-            st.v1 += 2;
+            unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
+            ProfScope prof(e, 3, e->covs);
+            k_cov_final<<<1, kCovTileThreads, 0, e->covs>>>(e->d_cov_carry + lane, e->d_cov_d + (uint64_t)lane * 2 * kCovD, poscov);
+            e->launches += 1;
         }
         CU(cudaEventRecord(e->cov_done, e->covs));
         CU(cudaStreamWaitEvent(e->compute, e->cov_done, 0));

@@ -247,7 +247,7 @@ __global__ void k_frame_repair(const uint8_t* __restrict__ d, FrameResult* fr, i
         if (bs < 32u || p + 4 + (uint64_t)bs > n) break;
         if (cnt >= rec_cap) { over = true; break; }
         offsets[cnt] = (uint32_t)p;
-        meta[cnt] = frame_meta_of(d, p, n_ref, main_chrom, mx);
+        { const FrameMeta m = frame_meta_of(d, p, n_ref, main_chrom, mx); if (meta) meta[cnt] = m; }
         ++cnt;
         p += 4 + (uint64_t)bs;
     }
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame_emit(const uint8_t* __r
         for (uint32_t i = 0; i < c; ++i) {
             const uint32_t bs = ldu32(d + p);
             offsets[base + i] = (uint32_t)p;
-            meta[base + i] = frame_meta_of(d, p, n_ref, main_chrom, mx);
+            { const FrameMeta m = frame_meta_of(d, p, n_ref, main_chrom, mx); if (meta) meta[base + i] = m; }
             p += 4 + (uint64_t)bs;
         }
     }

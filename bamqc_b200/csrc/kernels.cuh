@@ -8,7 +8,8 @@
 //   k_eightmer: OverallNumbers::count8mers                 (65536 x 16-bit counters = 128 KB smem per CTA)
 //   k_sketch : ReadQualityHasher + RepHash + StreamCounter (F2 table = 128 KB smem per CTA; the 8 MiB
 //              4-bit sketch stays in L2 and is updated with load-test-CAS)
-//   k_cov_*  : coverage windows: prefix sum of the difference ring + histogram
+//   k_cov_*  : coverage windows entirely on the device (kernel_cov.cuh): anchor recurrence as a scan, tiled
+//              shared-memory depth histogram
 // Measured on B200 (profiles/ubench): shared-memory atomics sustain ~1700 G/s chip-wide, global REDs to
 // an L2-resident table ~150 G/s and collapse to <14 G/s on hot bins, hence the privatisation.
 //
@@ -30,27 +31,22 @@ namespace bqc {
 struct BatchView {
     const uint8_t* bytes;      // inflated BAM records, padded with >= 64 readable bytes
     const uint32_t* offsets;   // n_records + 1 byte offsets
-    const uint32_t* cov;       // per record coverage code (window << 11 | pos) or kNone; may be NULL
     const uint8_t* rec_lane;   // per record lane (multi-lane runs) or NULL
     uint32_t n_records;
     uint32_t cycb;             // per-cycle smem capacity for this batch (>= max l_seq, multiple of 8)
     uint64_t first_record;     // global index of record 0 (error reporting)
-    uint32_t ring_base;        // ring index of coverage window 0 of this batch
 };
 
 struct EngineView {
     Layout L;
     uint64_t* counters;              // [n_lanes][lane_stride]
     uint32_t* sketch;                // [n_lanes][n_qk][32][sk_size*2] 4-bit counters, 8 per word
-    uint32_t* ring;                  // [n_lanes][ring_mask+1] coverage difference ring
-    uint32_t ring_mask;
     const uint32_t* const* ref;      // [n_ref] 2-bit packed contigs (16 bases per word) or NULL
     const uint64_t* ref_len;         // [n_ref]
     const uint8_t* main_chrom;       // [n_ref]
     int32_t n_ref;
     unsigned long long* error;       // min over (record << 8 | code), ~0 if none
     uint32_t insert_smem;            // insert-size bins kept in shared memory
-    uint8_t* touch;                  // [n_lanes][(ring_mask+1)/32] granules of the ring that hold events
 };
 
 struct SketchParams {
@@ -503,177 +499,6 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch(EngineView E, Batc
 }
 
 // ------------------------------------------------------------------------------------------------
-// coverage windows (src/OverallNumbers.hpp:59-77): depth = prefix sum of the difference ring over the
-// flushed range, poscov[min(depth,100)]++ for every position, ring range zeroed for reuse.
-// ------------------------------------------------------------------------------------------------
-// k_cov_scatter: OverallNumbers::coverage (src/OverallNumbers.hpp:79-135).  The window anchor is the only
-// order-dependent piece of the reference; it comes from the host scan as a per-record code
-// (window << 11 | pos).  Here only the commutative part: for every M/D run of the read-oriented CIGAR
-// (S lengths added to the offset, as the reference does) +1 at its first position and -1 one past its
-// last, clipped at pos + j < 2*vsize where the reference's writes leave v2.
-__global__ void __launch_bounds__(256) k_cov_scatter(EngineView E, BatchView B, uint32_t lane) {
-    uint32_t* ring = E.ring + (uint64_t)lane * ((uint64_t)E.ring_mask + 1);
-    uint8_t* touch = E.touch + (uint64_t)lane * (((uint64_t)E.ring_mask + 1) >> 5);  // one byte per 32 ring entries
-    for (uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x; rec < B.n_records; rec += gridDim.x * blockDim.x) {
-        const uint32_t code = B.cov[rec];
-        if (code == kNone) continue;
-        if (B.rec_lane && B.rec_lane[rec] != lane) continue;
-        const uint8_t* p = B.bytes + B.offsets[rec];
-        const uint32_t x = ldu32(p + 12), y = ldu32(p + 16);
-        const uint32_t lname = x & 255u, ncig = y & 0xFFFFu;
-        const bool rc = ((y >> 16) & 0x10u) != 0;
-        const uint8_t* cig = p + 36u + lname;
-        const uint32_t pos = code & 2047u;
-        const uint32_t base_idx = B.ring_base + (code >> 11) * 1000u + pos;
-        const uint32_t lim = 2000u - pos;
-        uint32_t c = 0;
-        for (uint32_t i = 0; i < ncig; ++i) {
-            uint32_t ce = ldu32(cig + 4 * (rc ? (ncig - 1 - i) : i));
-            uint32_t op = ce & 15u, n = ce >> 4;
-            if (op == 4u) c += n;
-            if (op == 0u || op == 2u) {
-                if (c < lim && n > 0) {
-                    uint32_t hi = min(c + n, lim);
-                    const uint32_t i0 = (base_idx + c) & E.ring_mask, i1 = (base_idx + hi) & E.ring_mask;
-                    atomicAdd(ring + i0, 1u);
-                    atomicAdd(ring + i1, 0xFFFFFFFFu);
-                    touch[i0 >> 5] = 1;  // plain stores of the same value: races are benign
-                    touch[i1 >> 5] = 1;
-                }
-                c += n;
-            }
-        }
-    }
-}
-
-// Window flush = one pass over the ring range: single-pass prefix sum with decoupled look-back (tile aggregate /
-// inclusive-prefix flags), fused with the min(depth,100) histogram and the re-zeroing of the ring.  One thread owns
-// one 32-entry granule (= one byte of the touch map written by the scatter kernel): an untouched granule is neither
-// read nor written (its 32 positions have the running depth), a touched one is read with eight 16-byte loads.  The
-// pass is bound by the latency of the look-back chain per tile, so tiles are large (8192 positions).
-static const uint32_t kCovThreads = 256;
-static const uint32_t kCovTile = kCovThreads * 32;   // ring entries per tile
-static const uint32_t kTileAggregate = 1u, kTileInclusive = 2u;
-// [start, start+len) is the range to flush (ring indices, multiples of 8); tiles are aligned to granules in ring
-// index space: lead = start & 31 entries of the first granule lie before the range.
-__global__ void __launch_bounds__(kCovThreads) k_cov_flush(uint32_t* ring, uint8_t* touch, uint32_t ring_mask, uint32_t start, uint64_t len, uint32_t* carry,
-                                                           unsigned long long* tile_state, uint32_t* ticket, unsigned long long* poscov) {
-    __shared__ uint32_t hist[128];
-    __shared__ uint32_t wsum[32];
-    __shared__ uint32_t s_tile, s_prefix;
-    const uint32_t lead = start & 31u;
-    const uint32_t astart = start - lead;            // aligned ring index of entry 0 of tile 0 (no wrap: start >= lead)
-    const uint64_t alen = len + lead;                // entries from astart to the end of the range
-    const uint64_t ntiles = (alen + kCovTile - 1) / kCovTile;
-    if (threadIdx.x < 128) hist[threadIdx.x] = 0;
-    __syncthreads();
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);  // tiles are handed out in order => no deadlock
-        __syncthreads();
-        const uint64_t tile = s_tile;
-        if (tile >= ntiles) break;
-        const uint64_t g0 = tile * kCovTile + 32ull * threadIdx.x;   // first entry of this thread's granule, relative to astart
-        // part of the granule inside the range, as entry offsets [ka, kb) within the granule (multiples of 8)
-        const uint32_t ka = g0 < lead ? min(32u, (uint32_t)(lead - g0)) : 0u;
-        const uint32_t kb = g0 >= alen ? 0u : (uint32_t)min((uint64_t)32, alen - g0);
-        const bool inside = ka < kb;
-        const uint32_t ridx = (astart + (uint32_t)g0) & ring_mask;
-        const uint32_t gidx = ridx >> 5;
-        const bool touched = inside && touch[gidx] != 0;
-        uint32_t v[32];
-        uint32_t acc = 0;
-        if (touched) {
-            const uint4* src = reinterpret_cast<const uint4*>(ring + ridx);
-#pragma unroll
-            for (uint32_t q = 0; q < 8; ++q) {
-                uint4 a = make_uint4(0, 0, 0, 0);
-                if (4 * q >= ka && 4 * q < kb) a = __ldcs(src + q);   // streamed once: do not keep in L2
-                v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
-                acc += a.x + a.y + a.z + a.w;
-            }
-        }
-        uint32_t incl = acc;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if ((threadIdx.x & 31u) >= (uint32_t)o) incl += t;
-        }
-        if ((threadIdx.x & 31u) == 31u) wsum[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t w = threadIdx.x < (kCovThreads >> 5) ? wsum[threadIdx.x] : 0u, wi = w;
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-                if (threadIdx.x >= (uint32_t)o) wi += t;
-            }
-            wsum[threadIdx.x] = wi - w;  // exclusive warp offsets
-            const uint32_t total = __shfl_sync(0xFFFFFFFFu, wi, 31);
-            // publish, then look back over the predecessor tiles (one warp, one lane per predecessor)
-            uint32_t prefix = 0;
-            if (tile == 0) {
-                prefix = *carry;
-            } else {
-                if (threadIdx.x == 0) {
-                    atomicExch(tile_state + tile, ((unsigned long long)kTileAggregate << 32) | total);
-                }
-                int64_t look = (int64_t)tile - 1;
-                for (;;) {
-                    int64_t t = look - (int64_t)threadIdx.x;
-                    unsigned long long st = 0;
-                    if (t >= 0) {
-                        do { st = *((volatile unsigned long long*)(tile_state + t)); } while ((st >> 32) == 0);
-                    } else {
-                        st = (unsigned long long)kTileInclusive << 32;  // before tile 0: contributes nothing
-                    }
-                    const uint32_t flag = (uint32_t)(st >> 32), val = (uint32_t)st;
-                    const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, flag == kTileInclusive);
-                    // lanes up to and including the first inclusive one contribute
-                    const uint32_t first = incl_mask ? (uint32_t)(__ffs((int)incl_mask) - 1) : 32u;
-                    uint32_t contrib = (threadIdx.x <= first) ? val : 0u;
-                    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, o);
-                    prefix += contrib;
-                    if (incl_mask) break;
-                    look -= 32;
-                }
-            }
-            if (threadIdx.x == 0) {
-                atomicExch(tile_state + tile, ((unsigned long long)kTileInclusive << 32) | (uint32_t)(prefix + total));
-                s_prefix = prefix;
-                if (tile == ntiles - 1) *carry = prefix + total;
-            }
-        }
-        __syncthreads();
-        uint32_t depth = s_prefix + wsum[threadIdx.x >> 5] + (incl - acc);
-        if (inside) {
-            if (touched) {
-                // the depth changes only at events: one histogram update per run of equal depth
-                uint32_t runlen = 0;
-#pragma unroll
-                for (uint32_t k = 0; k < 32; ++k) {
-                    if (k >= ka && k < kb) {
-                        if (v[k] != 0u) {
-                            if (runlen) atomicAdd(hist + min(depth, 100u), runlen);
-                            runlen = 0;
-                            depth += v[k];
-                        }
-                        ++runlen;
-                    }
-                }
-                if (runlen) atomicAdd(hist + min(depth, 100u), runlen);
-                uint4* dst = reinterpret_cast<uint4*>(ring + ridx);
-#pragma unroll
-                for (uint32_t q = 0; q < 8; ++q)
-                    if (4 * q >= ka && 4 * q < kb) __stcs(dst + q, make_uint4(0, 0, 0, 0));
-                if (kb == 32u) touch[gidx] = 0;   // the rest of a granule cut by the end of the range is flushed later
-            } else {
-                atomicAdd(hist + min(depth, 100u), kb - ka);  // no events in this granule: constant depth
-            }
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x < 101 && hist[threadIdx.x]) atomicAdd(poscov + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
-}
-
-// ------------------------------------------------------------------------------------------------
 // sketch export / import / merge (StreamCounter::join, src/kmerstream/StreamCounter.hpp:95-112)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_sketch_export_u8(const uint32_t* sk, uint64_t nwords, uint8_t* out) {
@@ -711,3 +536,4 @@ __global__ void k_counters_add(unsigned long long* dst, const unsigned long long
 
 }  // namespace bqc
 #include "kernel_sketch.cuh"
+#include "kernel_cov.cuh"
