@@ -41,6 +41,12 @@ class bqc_error_info(ctypes.Structure):
     _fields_ = [("code", ctypes.c_int32), ("record", ctypes.c_uint64), ("message", ctypes.c_char * 256)]
 
 
+class bqc_cov_shard(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_uint64), ("first_rid", ctypes.c_int32), ("last_rid", ctypes.c_int32),
+                ("first_b", ctypes.c_uint32), ("last_b", ctypes.c_uint32), ("span", ctypes.c_uint64),
+                ("head", ctypes.c_int32 * 2001), ("tail", ctypes.c_int32 * 2001)]
+
+
 class bqc_bam_header(ctypes.Structure):
     _fields_ = [
         ("text", ctypes.c_char_p), ("n_ref", ctypes.c_int32), ("ref_names", ctypes.POINTER(ctypes.c_char_p)),
@@ -100,6 +106,13 @@ PROTOTYPES = {
     "bqc_sketch_export_u8": (ctypes.c_int, [_vp, _vp]),
     "bqc_sketch_import_u8": (ctypes.c_int, [_vp, _vp]),
     "bqc_merge_from": (ctypes.c_int, [_vp, _vp]),
+    "bqc_cov_defer": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "bqc_cov_shard_boundary": (ctypes.c_int, [_vp, _P(bqc_cov_shard)]),
+    "bqc_cov_shard_function": (ctypes.c_int, [_vp, _i32, _i32, _u32, _vp]),
+    "bqc_cov_shard_run": (ctypes.c_int, [_vp, _i32, _i32, _u32, _u32, _P(bqc_cov_shard)]),
+    "bqc_cov_shards_combine": (None, [_vp, _i32, _vp]),
+    "bqc_cov_apply": (_u32, [_vp, _u32]),
+    "bqc_poscov_adjust": (ctypes.c_int, [_vp, _i32, _vp]),
     "bqc_n_lanes": (_i32, [_vp]),
     "bqc_lane_id": (ctypes.c_char_p, [_vp, _i32]),
     "bqc_qk_lists": (None, [_vp, _P(_P(_i32)), _P(_u32), _P(_P(_u64)), _P(_u32)]),

@@ -18,8 +18,9 @@
 //
 // Parallel form: a record is a CANDIDATE if it changes contig or its gap is >= 1000 (mod 2^32, so backward steps
 // are candidates too).  Between candidates no reset can happen and p has the closed form cov_posf(); only
-// candidates need the state, and a block of candidates is a function on the 1002 possible states (all-states
-// simulation, kernel_cov.cuh).
+// candidates need the state.  A candidate that changes contig or whose gap is in [2001, 2^32 - 2001] resets from
+// every state ("definite"); the others depend on p, and a block of them is a function on the 1002 possible states
+// (all-states simulation, kernel_cov.cuh).
 #pragma once
 #include <stdint.h>
 
@@ -51,6 +52,9 @@ BQC_CM uint32_t cov_step(uint32_t p, uint32_t g, bool other, bool& reset) {
     return x;
 }
 
+// A gap that resets whatever the state is: p + g > 2000 for every p in [0, 2000] without wrapping.
+BQC_CM bool cov_gap_definite(uint32_t g) { return (uint32_t)(g - 2001u) <= 0xFFFFFFFFu - 2000u - 2001u; }
+
 // State of a record in the stretch that follows a candidate (all gaps in the stretch are < 1000 on the same contig):
 // q = state right after the candidate, dd = b_record - b_candidate, ddj = b_record - b_j* where j* is the first
 // record of the stretch whose begin differs from the candidate's (only used when q is the edge state: records at
@@ -70,6 +74,57 @@ BQC_CM uint32_t cov_dx(uint32_t p_before, uint32_t g, bool reset) { return reset
 static const uint32_t kCovComplex = 0x80000000u;
 BQC_CM uint32_t cov_pack_iv(uint32_t c0, uint32_t len, bool complex) {
     return (c0 > 2047u ? 2047u : c0) | ((len > 2047u ? 2047u : len) << 11) | (complex ? kCovComplex : 0u);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Shards: one coordinate-ordered record stream cut at arbitrary records, every piece processed by its own engine
+// (SURVEY 8e "the exception").  A shard that does not know what came before it works in its own virtual
+// coordinates (origin = start of the window v1 that was open when it began) with empty windows, and reports
+//   n, first/last (rid, begin) of its qualifying records,
+//   F      its anchor recurrence as a function of the state at its entry (1002 values),
+//   span   virtual coordinate of the window start of its last record,
+//   head   difference array of its own depth over [0, 2000] (the two windows that were open at its entry),
+//   tail   difference array of its own depth over [span, span + 2000] (the two windows open at its end).
+// cov_shards_combine() then adds what the open windows of the shards before contribute to a shard's first 2000
+// positions and flushes the last two windows (src/bamqualcheck.cpp:447-453).  Host only.
+// ------------------------------------------------------------------------------------------------
+struct CovShardPiece {
+    uint64_t n;           // qualifying records (0: the shard leaves state and windows untouched)
+    uint64_t span;
+    const int32_t* head;  // [2001]
+    const int32_t* tail;  // [2001]
+};
+
+// delta[101]: to be added to the sum of the shards' own poscov histograms
+inline void cov_shards_combine(const CovShardPiece* sh, int n_shards, long long* delta) {
+    for (int i = 0; i <= 100; ++i) delta[i] = 0;
+    long long carry[2001];
+    for (int i = 0; i <= 2000; ++i) carry[i] = 0;
+    for (int k = 0; k < n_shards; ++k) {
+        const CovShardPiece& S = sh[k];
+        if (S.n == 0) continue;
+        // the first min(2000, span) positions of the shard were counted with the shard's own depth only
+        const uint64_t L = S.span < 2000 ? S.span : 2000;
+        long long own = 0, both = 0;
+        for (uint64_t i = 0; i < L; ++i) {
+            own += S.head[i];
+            both += S.head[i] + carry[i];
+            delta[own > 100 ? 100 : own] -= 1;
+            delta[both > 100 ? 100 : both] += 1;
+        }
+        // windows open after the shard: its own tail plus what is left of the incoming windows beyond span
+        long long next[2001];
+        for (int i = 0; i <= 2000; ++i) next[i] = S.tail[i];
+        for (uint64_t d = 0; d <= 2000; ++d) {
+            if (!carry[d]) continue;
+            if (d <= S.span) next[0] += carry[d];
+            else next[d - S.span] += carry[d];
+        }
+        for (int i = 0; i <= 2000; ++i) carry[i] = next[i];
+    }
+    long long depth = 0;   // end of the run: the two open windows
+    for (int i = 0; i < 2000; ++i) { depth += carry[i]; delta[depth > 100 ? 100 : depth] += 1; }
 }
 
 }  // namespace bqc

@@ -156,8 +156,13 @@ struct bqc_engine {
     // coverage (kernel_cov.cuh): carried anchor state + the two open windows per lane, scratch for the batch in flight
     CovCarry* d_cov_carry = nullptr;   // [n_lanes]
     int32_t* d_cov_d = nullptr;        // [n_lanes][2][kCovD]
-    uint8_t* d_cov_scratch = nullptr;  // one allocation, carved by cov_scratch_carve
+    uint8_t* d_cov_scratch = nullptr;  // one allocation, carved by ensure_cov_scratch
     uint64_t cov_scratch_cap = 0;      // records
+    uint8_t* d_cov_q = nullptr;        // the compact qualifying records (rid, begin, interval, record index)
+    uint64_t cov_q_cap = 0;
+    bool cov_deferred = false;         // shard mode: records are collected, the statistic is resolved by bqc_cov_shard_*
+    uint64_t cov_acc_bound = 0;        // shard mode: upper bound of the records collected so far
+    uint16_t* d_cov_fn = nullptr;      // shard mode: [1024] shard function; [2048 int32] head
     uint64_t cov_ctl_bytes = 0;        // tickets + look-back states at the front of the scratch (zeroed per launch group)
     CovScratch cov_scratch;
     unsigned long long* d_error = nullptr;
@@ -202,7 +207,7 @@ struct bqc_engine {
     int async_rc = 0;
     int tune_stats_bps = 0, tune_sketch_threads = 1024, tune_stats_stage = 1;  // BQC_STATS_STAGE=0: k_stats reads records straight from global memory (A/B tests)
     int _pad_tune = 0;   // BQC_STATS_BPS / BQC_SKETCH_THREADS (tuning knobs)
-    int tune_cov_bps = 4;                                // BQC_COV_BPS: k_cov_tiles CTAs per SM
+    int tune_cov_bps = 6;                                // BQC_COV_BPS: k_cov_tiles CTAs per SM
     uint64_t records_seen = 0, frames_repaired = 0;
     std::atomic<uint64_t> launches{0};   // kernels launched (commit thread, anchor thread, caller)
     bool finished = false;
@@ -321,6 +326,8 @@ extern "C" void bqc_destroy(bqc_engine* e) {
     cudaFree(e->d_cov_carry);
     cudaFree(e->d_cov_d);
     cudaFree(e->d_cov_scratch);
+    cudaFree(e->d_cov_q);
+    cudaFree(e->d_cov_fn);
     cudaFree(e->d_error);
     cudaFree((void*)e->d_ref);
     cudaFree(e->d_ref_len);
@@ -367,6 +374,7 @@ extern "C" int bqc_reset(bqc_engine* e) {
     CU(cudaMemsetAsync(e->d_error, 0xFF, 8, e->compute));
     CU(cudaStreamSynchronize(e->compute));  // the coverage stream starts from a clean state
     e->records_seen = 0;
+    e->cov_acc_bound = 0;
     e->finished = false;
     e->have_results = false;
     e->host_error.code = 0;
@@ -727,21 +735,36 @@ extern "C" int bqc_profile_read(bqc_engine* e, double ms_out[12], uint64_t n_out
 // ------------------------------------------------------------------------------------------------
 // Scratch of the coverage kernels for a batch of up to n records: one allocation, grown on demand (rare: the first
 // batch, or a larger resident batch).  Layout: control words that are zeroed before every launch group (tickets,
-// look-back states), then the per-record and per-block arrays.
+// look-back states), then the per-record and per-block arrays.  The compact records themselves live in their own
+// allocation because shard mode keeps collecting them over the whole run (`keep` entries survive a growth).
+static int ensure_cov_q(bqc_engine* e, uint64_t n_records, uint64_t keep) {
+    if (n_records <= e->cov_q_cap && e->d_cov_q) return 0;
+    const uint64_t N = std::max<uint64_t>(n_records + n_records / 4, 1u << 16);
+    uint8_t* m = nullptr;
+    CU(cudaStreamSynchronize(e->covs));
+    CU(cudaMalloc(&m, N * 16));
+    if (e->d_cov_q && keep)
+        for (int a = 0; a < 4; ++a) CU(cudaMemcpy(m + (uint64_t)a * N * 4, e->d_cov_q + (uint64_t)a * e->cov_q_cap * 4, keep * 4, cudaMemcpyDeviceToDevice));
+    cudaFree(e->d_cov_q);
+    e->d_cov_q = m;
+    e->cov_q_cap = N;
+    CovScratch& S = e->cov_scratch;
+    S.q_rid = (int32_t*)m;
+    S.q_b = (uint32_t*)(m + N * 4);
+    S.q_iv = (uint32_t*)(m + N * 8);
+    S.q_rec = (uint32_t*)(m + N * 12);
+    return 0;
+}
 static int ensure_cov_scratch(bqc_engine* e, uint64_t n_records) {
     if (n_records <= e->cov_scratch_cap && e->d_cov_scratch) return 0;
     const uint64_t N = std::max<uint64_t>(n_records + n_records / 8, 1u << 16);
-    const uint64_t nblk = N / kCovRB + 2, nprep = N / kCovPrepTile + 2, ntile = N / 4 + 16;
+    const uint64_t nblk = N / kCovRB + 2, nprep = N / kCovPrepTile + 2, ntile = 2 * N + 16;  // <= 2000 virtual positions per record
     auto up = [](uint64_t x) { return (x + 255) & ~255ull; };
     uint64_t o = 0;
     const uint64_t o_tickets = o; o += up(16);
     const uint64_t o_lbp = o; o += up(nprep * 8);
     const uint64_t o_lbc = o; o += up(nblk * 8);
     const uint64_t ctl = o;
-    const uint64_t o_rid = o; o += up(N * 4);
-    const uint64_t o_b = o; o += up(N * 4);
-    const uint64_t o_iv = o; o += up(N * 4);
-    const uint64_t o_rec = o; o += up(N * 4);
     const uint64_t o_base = o; o += up(N * 8);
     const uint64_t o_ab = o; o += up(N * 4);
     const uint64_t o_tab = o; o += up(nblk * 1024 * 2);
@@ -756,10 +779,6 @@ static int ensure_cov_scratch(bqc_engine* e, uint64_t n_records) {
     S.tickets = (uint32_t*)(m + o_tickets);
     S.lb_prep = (unsigned long long*)(m + o_lbp);
     S.lb_codes = (unsigned long long*)(m + o_lbc);
-    S.q_rid = (int32_t*)(m + o_rid);
-    S.q_b = (uint32_t*)(m + o_b);
-    S.q_iv = (uint32_t*)(m + o_iv);
-    S.q_rec = (uint32_t*)(m + o_rec);
     S.base = (unsigned long long*)(m + o_base);
     S.ab = (uint32_t*)(m + o_ab);
     S.tables = (uint16_t*)(m + o_tab);
@@ -808,13 +827,32 @@ static int batch_launch_setup(bqc_engine* e, const DeviceBatch& d, BatchLaunch& 
     return 0;
 }
 
+// The anchor recurrence, the virtual coordinates and the depth histogram of the records collected in the compact
+// arrays (a batch, or a whole shard), from the state in CovCarry; n_bound >= the number of compact records.
+static int launch_cov_resolve(bqc_engine* e, uint32_t lane, const BatchView& B, uint64_t n_bound, bool tables_done) {
+    const CovScratch& S = e->cov_scratch;
+    CovCarry* carry = e->d_cov_carry + lane;
+    int32_t* cd = e->d_cov_d + (uint64_t)lane * 2 * kCovD;
+    unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
+    const uint32_t nblk = (uint32_t)((n_bound + kCovRB - 1) / kCovRB);
+    if (!tables_done) k_cov_tables<<<nblk, kCovBlockThreads, kCovBlockSmem, e->covs>>>(S, carry);
+    k_cov_link<<<1, 1024, 0, e->covs>>>(S, carry);
+    k_cov_codes<<<(int)std::min<uint32_t>(nblk, (uint32_t)e->n_sm * 2u), kCovBlockThreads, kCovCodesSmem, e->covs>>>(S, carry);
+    k_cov_tiles<<<e->n_sm * e->tune_cov_bps, kCovTileThreads, 0, e->covs>>>(B, S, carry, cd, poscov);
+    e->launches += tables_done ? 3 : 4;
+    return 0;
+}
+
 // OverallNumbers::coverage for one device-resident batch (kernel_cov.cuh), on its own stream so that it overlaps the
 // table kernels.  The caller has made e->covs wait for the batch's data.  Nothing comes back to the host: the anchor
-// state and the two open windows are carried on the device from batch to batch.
+// state and the two open windows are carried on the device from batch to batch.  Shard mode only collects the
+// records that take part (bqc_cov_shard_* resolve them at the end).
 static int launch_cov(bqc_engine* e, const DeviceBatch& d, const BatchLaunch& BL) {
     const uint64_t n = d.n_records;
     if (n) {
         int rc = ensure_cov_scratch(e, n);
+        if (rc) return rc;
+        rc = ensure_cov_q(e, e->cov_acc_bound + n, e->cov_acc_bound);
         if (rc) return rc;
         const CovScratch& S = e->cov_scratch;
         BatchView B;
@@ -825,21 +863,19 @@ static int launch_cov(bqc_engine* e, const DeviceBatch& d, const BatchLaunch& BL
         B.cycb = BL.cycb;
         B.first_record = d.first_record;
         const uint32_t nprep = (uint32_t)((n + kCovPrepTile - 1) / kCovPrepTile);
-        const uint32_t nblk = (uint32_t)((n + kCovRB - 1) / kCovRB);
         ProfScope prof(e, 3, e->covs);
         for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
             CovCarry* carry = e->d_cov_carry + lane;
-            int32_t* cd = e->d_cov_d + (uint64_t)lane * 2 * kCovD;
-            unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
             CU(cudaMemsetAsync(e->d_cov_scratch, 0, e->cov_ctl_bytes, e->covs));
-            k_cov_prep<<<(int)std::min<uint32_t>(nprep, (uint32_t)e->n_sm * 8u), 256, 0, e->covs>>>(BL.E, B, lane, S, carry);
-            k_cov_tables<<<nblk, kCovBlockThreads, kCovBlockSmem, e->covs>>>(S, carry);
-            k_cov_link<<<1, 256, 0, e->covs>>>(S, carry);
-            k_cov_codes<<<(int)std::min<uint32_t>(nblk, (uint32_t)e->n_sm * 2u), kCovBlockThreads, kCovCodesSmem, e->covs>>>(S, carry);
-            k_cov_tiles<<<e->n_sm * e->tune_cov_bps, kCovTileThreads, 0, e->covs>>>(B, S, carry, cd, poscov);
-            k_cov_carry<<<1, 1024, 0, e->covs>>>(B, S, carry, cd);
-            e->launches += 6;
+            k_cov_prep<<<(int)std::min<uint32_t>(nprep, (uint32_t)e->n_sm * 8u), 256, 0, e->covs>>>(BL.E, B, lane, S, carry, e->cov_deferred ? 1u : 0u);
+            e->launches += 1;
+            if (e->cov_deferred) continue;
+            rc = launch_cov_resolve(e, lane, B, n, false);
+            if (rc) return rc;
+            k_cov_carry<<<1, 1024, 0, e->covs>>>(B, S, carry, e->d_cov_d + (uint64_t)lane * 2 * kCovD);
+            e->launches += 1;
         }
+        if (e->cov_deferred) e->cov_acc_bound += n;
     }
     CU(cudaEventRecord(e->cov_done, e->covs));
     CU(cudaGetLastError());
@@ -1460,7 +1496,8 @@ extern "C" int bqc_finish(bqc_engine* e) {
         for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
             unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
             ProfScope prof(e, 3, e->covs);
-            k_cov_final<<<1, kCovTileThreads, 0, e->covs>>>(e->d_cov_carry + lane, e->d_cov_d + (uint64_t)lane * 2 * kCovD, poscov);
+            if (e->cov_deferred) continue;  // shard mode: bqc_cov_shards_combine flushes the last windows
+            k_cov_final<<<1, 32, 0, e->covs>>>(e->d_cov_carry + lane, e->d_cov_d + (uint64_t)lane * 2 * kCovD, poscov);
             e->launches += 1;
         }
         CU(cudaEventRecord(e->cov_done, e->covs));
@@ -1469,6 +1506,129 @@ extern "C" int bqc_finish(bqc_engine* e) {
     }
     e->have_results = false;
     return bqc_sync(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one record stream cut across several engines: the coverage statistic (include/bamqc_b200.h, cov_math.h "Shards")
+// ------------------------------------------------------------------------------------------------
+extern "C" int bqc_cov_defer(bqc_engine* e, int on) {
+    if (on && e->n_lanes != 1) { set_error(e, "bqc_cov_defer: shard mode supports a single read group"); return BQC_ERR_ARG; }
+    if (e->records_seen || e->cov_acc_bound) { set_error(e, "bqc_cov_defer: call it right after bqc_reset"); return BQC_ERR_ARG; }
+    e->cov_deferred = on != 0;
+    return 0;
+}
+
+static int cov_shard_sync(bqc_engine* e, uint32_t& nq) {
+    CU(cudaSetDevice(e->cfg.device));
+    { int arc = drain_commits(e); if (arc) return arc; }
+    CU(cudaStreamSynchronize(e->compute));
+    CU(cudaStreamSynchronize(e->covs));
+    CovCarry c;
+    CU(cudaMemcpy(&c, e->d_cov_carry, sizeof(c), cudaMemcpyDeviceToHost));
+    nq = c.nq;
+    return 0;
+}
+
+extern "C" int bqc_cov_shard_boundary(bqc_engine* e, bqc_cov_shard* out) {
+    memset(out, 0, sizeof(*out));
+    if (!e->cov_deferred) { set_error(e, "bqc_cov_shard_boundary: engine is not in shard mode (bqc_cov_defer)"); return BQC_ERR_ARG; }
+    uint32_t nq = 0;
+    int rc = cov_shard_sync(e, nq);
+    if (rc) return rc;
+    out->n = nq;
+    if (nq) {
+        const CovScratch& S = e->cov_scratch;
+        CU(cudaMemcpy(&out->first_rid, S.q_rid, 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&out->first_b, S.q_b, 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&out->last_rid, S.q_rid + (nq - 1), 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&out->last_b, S.q_b + (nq - 1), 4, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+extern "C" int bqc_cov_shard_function(bqc_engine* e, int32_t have_prev, int32_t prev_rid, uint32_t prev_b, uint16_t* table1002) {
+    if (!e->cov_deferred) { set_error(e, "bqc_cov_shard_function: engine is not in shard mode"); return BQC_ERR_ARG; }
+    uint32_t nq = 0;
+    int rc = cov_shard_sync(e, nq);
+    if (rc) return rc;
+    for (uint32_t s = 0; s < kCovStates; ++s) table1002[s] = (uint16_t)s;   // no record: the state passes through
+    if (!nq) return 0;
+    rc = ensure_cov_scratch(e, nq);
+    if (rc) return rc;
+    if (!e->d_cov_fn) CU(cudaMalloc(&e->d_cov_fn, 1024 * 2 + kCovD * 4));
+    const uint32_t nblk = (nq + kCovRB - 1) / kCovRB;
+    k_cov_set_state<<<1, 1, 0, e->covs>>>(e->d_cov_carry, have_prev ? 0u : 1u, prev_rid, prev_b, 0u);
+    k_cov_tables<<<nblk, kCovBlockThreads, kCovBlockSmem, e->covs>>>(e->cov_scratch, e->d_cov_carry);
+    k_cov_shard_function<<<1, 1024, 0, e->covs>>>(e->cov_scratch, e->d_cov_carry, e->d_cov_fn);
+    e->launches += 3;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->covs));
+    CU(cudaMemcpy(table1002, e->d_cov_fn, kCovStates * 2, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int bqc_cov_shard_run(bqc_engine* e, int32_t have_prev, int32_t prev_rid, uint32_t prev_b, uint32_t p_in, bqc_cov_shard* out) {
+    if (!e->cov_deferred) { set_error(e, "bqc_cov_shard_run: engine is not in shard mode"); return BQC_ERR_ARG; }
+    uint32_t nq = 0;
+    int rc = cov_shard_sync(e, nq);
+    if (rc) return rc;
+    bqc_cov_shard keep = *out;
+    memset(out->head, 0, sizeof(out->head));
+    memset(out->tail, 0, sizeof(out->tail));
+    out->span = 0;
+    out->n = nq;
+    (void)keep;
+    if (!nq) return 0;
+    rc = ensure_cov_scratch(e, nq);
+    if (rc) return rc;
+    if (!e->d_cov_fn) CU(cudaMalloc(&e->d_cov_fn, 1024 * 2 + kCovD * 4));
+    int32_t* d_head = (int32_t*)(e->d_cov_fn + 1024);
+    BatchView B;
+    memset(&B, 0, sizeof(B));
+    CU(cudaMemsetAsync(e->d_cov_scratch, 0, e->cov_ctl_bytes, e->covs));
+    CU(cudaMemsetAsync(e->d_cov_d, 0, 2 * kCovD * 4, e->covs));
+    k_cov_set_state<<<1, 1, 0, e->covs>>>(e->d_cov_carry, have_prev ? 0u : 1u, prev_rid, prev_b, p_in);
+    {
+        ProfScope prof(e, 3, e->covs);
+        rc = launch_cov_resolve(e, 0, B, nq, false);
+        if (rc) return rc;
+        k_cov_head<<<1, 1024, 0, e->covs>>>(B, e->cov_scratch, e->d_cov_carry, d_head);
+        k_cov_carry<<<1, 1024, 0, e->covs>>>(B, e->cov_scratch, e->d_cov_carry, e->d_cov_d);
+        e->launches += 3;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->covs));
+    CovCarry c;
+    CU(cudaMemcpy(&c, e->d_cov_carry, sizeof(c), cudaMemcpyDeviceToHost));
+    out->span = c.xc;
+    CU(cudaMemcpy(out->head, d_head, sizeof(out->head), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out->tail, e->d_cov_d + (uint64_t)c.parity * kCovD, sizeof(out->tail), cudaMemcpyDeviceToHost));
+    e->have_results = false;
+    return 0;
+}
+
+extern "C" void bqc_cov_shards_combine(const bqc_cov_shard* shards, int32_t n_shards, int64_t delta[101]) {
+    std::vector<CovShardPiece> pc((size_t)std::max(0, n_shards));
+    for (int32_t k = 0; k < n_shards; ++k) { pc[k].n = shards[k].n; pc[k].span = shards[k].span; pc[k].head = shards[k].head; pc[k].tail = shards[k].tail; }
+    long long d[101];
+    cov_shards_combine(pc.data(), n_shards, d);
+    for (int i = 0; i <= 100; ++i) delta[i] = d[i];
+}
+
+extern "C" uint32_t bqc_cov_apply(const uint16_t* table1002, uint32_t p) { return cov_state_value(table1002[cov_state_index(p)]); }
+
+extern "C" int bqc_poscov_adjust(bqc_engine* e, int32_t lane, const int64_t delta[101]) {
+    if (lane < 0 || (uint32_t)lane >= e->n_lanes) { set_error(e, "bqc_poscov_adjust: bad lane"); return BQC_ERR_ARG; }
+    CU(cudaSetDevice(e->cfg.device));
+    long long* d = nullptr;
+    CU(cudaMalloc(&d, 101 * 8));
+    CU(cudaMemcpy(d, delta, 101 * 8, cudaMemcpyHostToDevice));
+    k_poscov_adjust<<<1, 128, 0, e->compute>>>((unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov), d);
+    e->launches += 1;
+    CU(cudaStreamSynchronize(e->compute));
+    cudaFree(d);
+    e->have_results = false;
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -28,7 +28,7 @@ namespace bqc {
 
 static const uint32_t kCovRB = 2048;        // compact records per anchor block
 static const uint32_t kCovBlockThreads = 1024;
-static const uint32_t kCovTile = 8192;      // virtual positions per tile (> 2000 + longest reach)
+static const uint32_t kCovTile = 1024;      // virtual positions per tile: one warp, 32 positions per lane
 static const uint32_t kCovTileThreads = 256;
 static const uint32_t kCovD = 2048;         // entries of a carry difference array (2001 used)
 static const uint32_t kCovPrepTile = 1024;  // records per compaction tile
@@ -61,7 +61,7 @@ struct CovScratch {  // sized for the largest batch; reused by every batch and l
     uint16_t* tables;                // [block][1024] state -> state (COV_TABLE blocks)
     uint4* desc;                     // [block] {type, a, b, -}
     uint32_t* state_in;              // [block] state at block entry
-    uint32_t* first_rec;             // [tile] first compact record whose window start lies in the tile
+    uint32_t* first_rec;             // [tile] first compact record whose window start lies in the tile or beyond
     unsigned long long* lb_prep;     // look-back states
     unsigned long long* lb_codes;
     uint32_t* tickets;               // [0] prep, [1] codes
@@ -166,11 +166,13 @@ __device__ __forceinline__ void cov_walk_cigar(const uint8_t* p, F emit) {
 // k_cov_prep: which records take part (src/bamqualcheck.cpp:318-327,385-389,392,430: primary, first or last, mapped,
 // not duplicate, rID in the -c set) and their (rid, begin, interval), compacted in file order.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cov_prep(EngineView E, BatchView B, uint32_t lane, CovScratch S, CovCarry* carry) {
+// append != 0 (shard mode): the records are added behind the carry->nq already collected instead of replacing them.
+__global__ void __launch_bounds__(256) k_cov_prep(EngineView E, BatchView B, uint32_t lane, CovScratch S, CovCarry* carry, uint32_t append) {
     __shared__ uint32_t ws[33];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
     const uint32_t ntile = (B.n_records + kCovPrepTile - 1u) / kCovPrepTile;
+    const uint32_t have = append ? carry->nq : 0u;   // only tile 0 uses it, and the last tile overwrites it after tile 0 has published
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(S.tickets + 0, 1u);
         __syncthreads();
@@ -199,13 +201,14 @@ __global__ void __launch_bounds__(256) k_cov_prep(EngineView E, BatchView B, uin
             rid[k] = id;
             b[k] = ldu32(p + 8);
             iv[k] = cov_pack_iv(s0, e0 - s0, nint > 1u);
+            if (append && nint > 1u) report_error(E, B.first_record + r, 16);  // the record bytes are gone when a shard is resolved
             flags |= 1u << k;
         }
         uint32_t total;
         const uint32_t cnt = __popc(flags);
         const uint32_t excl = cov_block_scan(cnt, ws, total) - cnt;
         if (threadIdx.x < 32) {
-            const unsigned long long pre = cov_lookback(S.lb_prep, tile, total, 0ull);
+            const unsigned long long pre = cov_lookback(S.lb_prep, tile, total, (unsigned long long)have);
             if (threadIdx.x == 0) {
                 s_base = pre;
                 if (tile == ntile - 1u) carry->nq = (uint32_t)(pre + total);
@@ -236,7 +239,7 @@ struct CovBlock {
     uint16_t* cord;   // [RB+2] per position: ordinal of the governing candidate
     uint16_t* cpos;   // [RB+2] per candidate: position; cpos[nc + 1] = n + 1
     uint16_t* cjs;    // [RB+2] per candidate: j* (first position of the stretch whose begin differs), 0 = none
-    uint8_t* cdef;    // [RB+2] per candidate: definite reset (contig change or first record ever)
+    uint8_t* cdef;    // [RB+2] per candidate: resets from every state (contig change, first record ever, gap in [2001, 2^32 - 2001])
     uint32_t* ws;     // [36]
     uint32_t n, nc;
     bool isfirst;
@@ -276,7 +279,8 @@ __device__ __forceinline__ void cov_block_analyse(CovBlock& K, const CovScratch&
         const uint32_t i = 2u * threadIdx.x + 1u + k;
         if (i <= n) {
             const bool other = K.srid[i] != K.srid[i - 1] || (K.isfirst && i == 1u);
-            if (other || (uint32_t)(K.sb[i] - K.sb[i - 1]) >= kCovV) f |= (other ? 3u : 1u) << (2u * k);
+            const uint32_t g = K.sb[i] - K.sb[i - 1];
+            if (other || g >= kCovV) f |= ((other || cov_gap_definite(g)) ? 3u : 1u) << (2u * k);
         }
     }
     uint32_t total;
@@ -356,23 +360,33 @@ __global__ void __launch_bounds__(kCovBlockThreads) k_cov_tables(CovScratch S, c
     }
 }
 
-__global__ void __launch_bounds__(256) k_cov_link(CovScratch S, const CovCarry* carry) {
-    __shared__ uint4 sd[1024];
+// State at the entry of every block.  A COV_CONST block ends in a known state, so the chain falls into independent
+// segments (one thread each); inside a segment the blocks are applied one after the other.
+static const uint32_t kCovLinkChunk = 2048;
+__global__ void __launch_bounds__(1024) k_cov_link(CovScratch S, const CovCarry* carry) {
+    __shared__ uint4 sd[kCovLinkChunk];
+    __shared__ uint32_t s_p;
     const uint32_t nq = carry->nq;
     const uint32_t nblk = (nq + kCovRB - 1u) / kCovRB;
-    uint32_t p = carry->p_prev;
-    for (uint32_t b0 = 0; b0 < nblk; b0 += 1024u) {
-        const uint32_t m = min(1024u, nblk - b0);
+    if (threadIdx.x == 0) s_p = carry->p_prev;
+    for (uint32_t b0 = 0; b0 < nblk; b0 += kCovLinkChunk) {
+        const uint32_t m = min(kCovLinkChunk, nblk - b0);
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) sd[i] = S.desc[b0 + i];
         __syncthreads();
-        if (threadIdx.x == 0) {
-            for (uint32_t i = 0; i < m; ++i) {
-                S.state_in[b0 + i] = p;
-                const uint4 d = sd[i];
+        const uint32_t p_chunk = s_p;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+            if (i != 0u && sd[i - 1].x != COV_CONST) continue;   // not the start of a segment
+            uint32_t p = i ? sd[i - 1].y : p_chunk;
+            for (uint32_t k = i;; ++k) {
+                S.state_in[b0 + k] = p;
+                const uint4 d = sd[k];
                 if (d.x == COV_CLOSED) p = cov_stretch(p, d.y, d.z);
                 else if (d.x == COV_CONST) p = d.y;
-                else p = cov_state_value(S.tables[(size_t)(b0 + i) * 1024u + cov_state_index(p)]);
+                else p = cov_state_value(S.tables[(size_t)(b0 + k) * 1024u + cov_state_index(p)]);
+                if (k + 1u == m) { s_p = p; break; }
+                if (d.x == COV_CONST) break;
             }
         }
     }
@@ -397,19 +411,26 @@ __global__ void __launch_bounds__(kCovBlockThreads) k_cov_codes(CovScratch S, Co
         if (blk >= nblk) break;
         cov_block_analyse(K, S, carry, blk, nq);
         const uint32_t p_in = S.state_in[blk];
-        // one thread runs the candidates with the true state: cGs[c] <- state right after candidate c, cg[c] <- advance of X
-        if (threadIdx.x == 0) {
+        // the candidates with the true state: cGs[c] <- state right after candidate c, cg[c] <- advance of X at c.  A
+        // definite candidate starts from a reset whatever came before, so every run [definite candidate .. next one)
+        // is walked by its own thread; the walker also leaves the advance of X for the definite candidate that ends
+        // its run (2000 - p of the record before it).
+        for (uint32_t c0 = threadIdx.x; c0 <= K.nc; c0 += blockDim.x) {
+            if (c0 != 0u && !K.cdef[c0]) continue;
             uint32_t p = p_in;
-            for (uint32_t c = 0; c <= K.nc; ++c) {
-                uint32_t q = p, dx = 0;
-                if (c) {
+            for (uint32_t c = c0;; ++c) {
+                uint32_t q = p;
+                if (c == c0) { if (c) q = 0u; }
+                else {
                     bool reset;
-                    q = cov_step(p, K.cg[c], K.cdef[c] != 0, reset);
-                    dx = (K.isfirst && c == 1u) ? 0u : cov_dx(p, K.cg[c], reset);
+                    const uint32_t g = K.cg[c];
+                    q = cov_step(p, g, false, reset);
+                    K.cg[c] = cov_dx(p, g, reset);
                 }
                 p = cov_stretch(q, K.cGs[c], K.cGj[c]);
                 K.cGs[c] = q;
-                K.cg[c] = dx;
+                if (c == K.nc) break;
+                if (K.cdef[c + 1u]) { K.cg[c + 1u] = (K.isfirst && c == 0u) ? 0u : 2u * kCovV - p; break; }
             }
         }
         __syncthreads();
@@ -465,10 +486,11 @@ __global__ void __launch_bounds__(kCovBlockThreads) k_cov_codes(CovScratch S, Co
                 }
                 S.base[r] = X;
                 S.ab[r] = code;
-                // window starts never decrease and advance by at most 2000 per record: every tile up to the last has a first record
+                // window starts never decrease (and advance by at most 2000 per record): the record is the first one at or
+                // beyond every tile boundary it crosses
                 const unsigned long long V = X0 + (long long)vrel[i], Vp = X0 + (long long)vrel[i - 1];
                 const uint32_t t1 = (uint32_t)((V - xc) / kCovTile);
-                if (r == 0 || t1 != (uint32_t)((Vp - xc) / kCovTile)) S.first_rec[t1] = r;
+                for (uint32_t tt = r ? (uint32_t)((Vp - xc) / kCovTile) + 1u : 0u; tt <= t1; ++tt) S.first_rec[tt] = r;
                 if (r == nq - 1u) {
                     carry->xl = V;
                     carry->ntiles = (uint32_t)((V - xc + kCovTile - 1u) / kCovTile);
@@ -483,63 +505,65 @@ __global__ void __launch_bounds__(kCovBlockThreads) k_cov_codes(CovScratch S, Co
 }
 
 // ------------------------------------------------------------------------------------------------
-// depth histogram of one range of <= kCovTile positions whose difference array sits in shared memory
-// (update_coverage, src/OverallNumbers.hpp:66-77: poscov[min(depth, 100)]++ per position).  Warp w owns positions
-// [1024 w, 1024 w + 1024): first its sum (for the depth at its start), then 32 positions per step; a step without
-// events is one histogram add of 32, otherwise the lanes that start a run of equal depth add the run length.
+// depth histogram of one tile of <= 1024 positions by one warp (update_coverage, src/OverallNumbers.hpp:66-77:
+// poscov[min(depth, 100)]++ per position).  The events of the tile sit in a difference array in shared memory and a
+// bitmap (one word per lane) marks the positions that hold one, so the pass touches the bitmap and the events, not
+// the positions: lane l owns positions [32 l, 32 l + 32); depth at its first position = d0 + warp prefix sum of the
+// events before it; between events the depth is constant and a whole run goes into the histogram with one add
+// (lanes without events are aggregated per depth).  The events are cleared on the way, so the difference array is
+// all zero again afterwards.  No block-wide barrier: the 8 warps of a CTA work on different tiles.  Returns the depth
+// after the last position.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cov_hist_tile(const int32_t* diff, uint32_t len, uint32_t* hist, uint32_t* wsum) {
-    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const uint32_t seg = w * 1024u;
-    int32_t acc = 0;
-    if (seg < len) {
-        const int4* src = reinterpret_cast<const int4*>(diff + seg);
-#pragma unroll
-        for (uint32_t q = 0; q < 8; ++q) { const int4 a = src[q * 32u + lane]; acc += a.x + a.y + a.z + a.w; }
+__device__ __forceinline__ int32_t cov_warp_tile(int32_t* diff, const uint32_t* bm, uint32_t len, int32_t d0, uint32_t* hist) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t m0 = bm[lane];
+    int32_t* my = diff + 32u * lane;
+    int32_t sum = 0;
+    for (uint32_t m = m0; m; m &= m - 1u) sum += my[__ffs((int)m) - 1];
+    int32_t incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
     }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-    if (lane == 0) wsum[w] = (uint32_t)acc;
-    __syncthreads();
-    int32_t depth = 0;
-    for (uint32_t u = 0; u < w; ++u) depth += (int32_t)wsum[u];
-    if (seg < len) {
-        const uint32_t steps = min(32u, (len - seg + 31u) >> 5);
-        for (uint32_t it = 0; it < steps; ++it) {
-            const uint32_t idx = seg + it * 32u + lane;
-            const bool valid = idx < len;
-            const int32_t v = valid ? diff[idx] : 0;
-            const uint32_t ev = __ballot_sync(0xFFFFFFFFu, v != 0);
-            const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
-            if (ev == 0u) {
-                if (lane == 0) atomicAdd(hist + min((uint32_t)depth, 100u), (uint32_t)__popc(vm));
-                continue;
-            }
-            int32_t incl = v;
-            for (int o = 1; o < 32; o <<= 1) {
-                const int32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= (uint32_t)o) incl += t;
-            }
-            const int32_t d = depth + incl;                       // depth at this position
-            const uint32_t heads = (ev | 1u) & vm;                 // lanes where a run of equal depth starts
-            if ((heads >> lane) & 1u) {
-                const uint32_t rest = (heads >> lane) >> 1;       // next head above this lane
-                const uint32_t end = rest ? lane + (uint32_t)__ffs((int)rest) : (uint32_t)__popc(vm);
-                atomicAdd(hist + min((uint32_t)d, 100u), end - lane);
-            }
-            depth += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    int32_t d = d0 + incl - sum;   // depth before this lane's first position
+    const uint32_t first = 32u * lane;
+    const uint32_t nvalid = first >= len ? 0u : min(32u, len - first);
+    // lanes whose 32 positions hold no event and lie inside the range: one add per depth
+    const bool plain = m0 == 0u && nvalid == 32u;
+    const uint32_t key = plain ? min((uint32_t)d, 100u) : (0x100u | lane);
+    const uint32_t grp = __match_any_sync(0xFFFFFFFFu, key);
+    if (plain) {
+        if ((uint32_t)(__ffs((int)grp) - 1) == lane) atomicAdd(hist + key, 32u * (uint32_t)__popc(grp));
+    } else if (nvalid) {
+        uint32_t pos = 0;
+        for (uint32_t m = m0; m; m &= m - 1u) {
+            const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+            if (b > pos) atomicAdd(hist + min((uint32_t)d, 100u), b - pos);
+            d += my[b];
+            my[b] = 0;
+            pos = b;
         }
+        if (nvalid > pos) atomicAdd(hist + min((uint32_t)d, 100u), nvalid - pos);
     }
-    __syncthreads();
+    __syncwarp();
+    return d0 + __shfl_sync(0xFFFFFFFFu, incl, 31);
 }
 
-// adds the covered interval(s) of compact record j, clipped to [T0, T1), to a difference array over [T0, T1]
-__device__ __forceinline__ void cov_tile_add(const CovScratch& S, const BatchView& B, uint32_t j, unsigned long long T0, unsigned long long T1, int32_t* diff) {
+// adds the covered interval(s) of compact record j, clipped to [T0, T1), to a difference array over [T0, T1] and marks
+// the positions in the bitmap (bm may be NULL)
+__device__ __forceinline__ void cov_tile_add(const CovScratch& S, const BatchView& B, uint32_t j, unsigned long long T0, unsigned long long T1, int32_t* diff, uint32_t* bm) {
     const unsigned long long X = S.base[j];
     const uint32_t code = S.ab[j];
     auto add = [&](unsigned long long A, unsigned long long Bv) {
         if (Bv <= T0 || A >= T1 || A >= Bv) return;
-        atomicAdd(diff + (uint32_t)((A > T0 ? A : T0) - T0), 1);
-        if (Bv < T1) atomicAdd(diff + (uint32_t)(Bv - T0), -1);
+        const uint32_t s = (uint32_t)((A > T0 ? A : T0) - T0);
+        atomicAdd(diff + s, 1);
+        if (bm) atomicOr(bm + (s >> 5), 1u << (s & 31u));
+        if (Bv < T1) {
+            const uint32_t e = (uint32_t)(Bv - T0);
+            atomicAdd(diff + e, -1);
+            if (bm) atomicOr(bm + (e >> 5), 1u << (e & 31u));
+        }
     };
     if (!(code & kCovComplex)) {
         add(X + (code & 2047u), X + ((code >> 11) & 2047u));
@@ -549,34 +573,46 @@ __device__ __forceinline__ void cov_tile_add(const CovScratch& S, const BatchVie
     }
 }
 
+// One warp per tile of 1024 positions.  A record writes into [V, V + 2000) (V = start of its window v1): the records
+// of a tile are those whose V lies in the tile or in the two before it.
 __global__ void __launch_bounds__(kCovTileThreads) k_cov_tiles(BatchView B, CovScratch S, const CovCarry* carry, const int32_t* carry_d, unsigned long long* poscov) {
-    __shared__ __align__(16) int32_t diff[kCovTile];
+    __shared__ __align__(16) int32_t diff_all[(kCovTileThreads / 32) * kCovTile];
+    __shared__ uint32_t bm_all[kCovTileThreads];
     __shared__ uint32_t hist[104];
-    __shared__ uint32_t wsum[8];
     const uint32_t ntiles = carry->ntiles, nq = carry->nq;
-    if (nq == 0 || blockIdx.x >= ntiles) return;
+    if (nq == 0 || blockIdx.x * (kCovTileThreads / 32u) >= ntiles) return;
     const unsigned long long xc = carry->xc, xl = carry->xl;
     const uint32_t vt_last = carry->vt_last;
     const int32_t* D = carry_d + (size_t)carry->parity * kCovD;
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    int32_t* diff = diff_all + w * kCovTile;
+    uint32_t* bm = bm_all + w * 32u;
     for (uint32_t i = threadIdx.x; i < 104u; i += blockDim.x) hist[i] = 0;
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (uint32_t i = lane; i < kCovTile; i += 32u) diff[i] = 0;
+    __syncthreads();
+    for (uint32_t t = blockIdx.x * (kCovTileThreads / 32u) + w; t < ntiles; t += gridDim.x * (kCovTileThreads / 32u)) {
         const unsigned long long T0 = xc + (unsigned long long)t * kCovTile;
         const unsigned long long T1 = min(T0 + kCovTile, xl);
         const uint32_t len = (uint32_t)(T1 - T0);
-        int4* z = reinterpret_cast<int4*>(diff);
-        for (uint32_t i = threadIdx.x; i < kCovTile / 4u; i += blockDim.x) z[i] = make_int4(0, 0, 0, 0);
-        __syncthreads();
-        // a record writes into [V, V + 2000): the records whose window start V lies in this tile or the one before
-        const uint32_t jlo = t ? S.first_rec[t - 1] : 0u;
-        const uint32_t jhi = t + 1u <= vt_last ? S.first_rec[t + 1] : nq;
-        for (uint32_t j = jlo + threadIdx.x; j < jhi; j += blockDim.x) cov_tile_add(S, B, j, T0, T1, diff);
-        if (t == 0)  // the two windows that were open when the batch started
-            for (uint32_t d = threadIdx.x; d <= 2u * kCovV; d += blockDim.x) {
-                const int32_t v = D[d];
-                if (v && d < len) atomicAdd(diff + d, v);
+        bm[lane] = 0;
+        const uint32_t jlo = t >= 2u ? S.first_rec[t - 2u] : 0u;
+        const uint32_t jhi = t + 1u <= vt_last ? S.first_rec[t + 1u] : nq;
+        __syncwarp();
+        for (uint32_t j = jlo + lane; j < jhi; j += 32u) cov_tile_add(S, B, j, T0, T1, diff, bm);
+        int32_t d0 = 0;
+        if (t < 2u) {  // the two windows that were open when the batch started: positions xc .. xc + 2000
+            const uint32_t o = t * kCovTile;
+            for (uint32_t i = lane; i < len && o + i <= 2u * kCovV; i += 32u) {
+                const int32_t v = D[o + i];
+                if (v) { atomicAdd(diff + i, v); atomicOr(bm + (i >> 5), 1u << (i & 31u)); }
             }
-        __syncthreads();
-        cov_hist_tile(diff, len, hist, wsum);
+            if (t == 1u) {  // depth they carry into tile 1
+                for (uint32_t i = lane; i < kCovTile; i += 32u) d0 += D[i];
+                for (int o2 = 16; o2 > 0; o2 >>= 1) d0 += __shfl_xor_sync(0xFFFFFFFFu, d0, o2);
+            }
+        }
+        __syncwarp();
+        cov_warp_tile(diff, bm, len, d0, hist);
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < 101u; i += blockDim.x)
@@ -595,8 +631,8 @@ __global__ void __launch_bounds__(1024) k_cov_carry(BatchView B, CovScratch S, C
     for (uint32_t i = threadIdx.x; i < kCovD; i += blockDim.x) dn[i] = 0;
     __syncthreads();
     const uint32_t vt_last = carry->vt_last;
-    const uint32_t jlo = vt_last >= 1u ? S.first_rec[vt_last - 1u] : 0u;   // window start > xl - 2000
-    for (uint32_t j = jlo + threadIdx.x; j < nq; j += blockDim.x) cov_tile_add(S, B, j, xl, xl + kCovD, dn);
+    const uint32_t jlo = vt_last >= 2u ? S.first_rec[vt_last - 2u] : 0u;   // window start > xl - 2000
+    for (uint32_t j = jlo + threadIdx.x; j < nq; j += blockDim.x) cov_tile_add(S, B, j, xl, xl + kCovD, dn, nullptr);
     for (uint32_t d = threadIdx.x; d <= 2u * kCovV; d += blockDim.x) {
         const int32_t v = D[d];
         if (v) {
@@ -622,17 +658,81 @@ __global__ void __launch_bounds__(1024) k_cov_carry(BatchView B, CovScratch S, C
 
 // End of the run (src/bamqualcheck.cpp:447-453): update_coverage(); update_vectors(); update_coverage() -- the two
 // open windows, 2000 positions (all of depth 0 if no record ever took part).
-__global__ void __launch_bounds__(kCovTileThreads) k_cov_final(const CovCarry* carry, const int32_t* carry_d, unsigned long long* poscov) {
+__global__ void __launch_bounds__(32) k_cov_final(const CovCarry* carry, const int32_t* carry_d, unsigned long long* poscov) {
     __shared__ __align__(16) int32_t diff[kCovTile];
+    __shared__ uint32_t bm[32];
     __shared__ uint32_t hist[104];
-    __shared__ uint32_t wsum[8];
     const int32_t* D = carry_d + (size_t)carry->parity * kCovD;
-    for (uint32_t i = threadIdx.x; i < 104u; i += blockDim.x) hist[i] = 0;
-    for (uint32_t i = threadIdx.x; i < kCovTile; i += blockDim.x) diff[i] = i < kCovD ? D[i] : 0;
-    __syncthreads();
-    cov_hist_tile(diff, 2u * kCovV, hist, wsum);
-    for (uint32_t i = threadIdx.x; i < 101u; i += blockDim.x)
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t i = lane; i < 104u; i += 32u) hist[i] = 0;
+    for (uint32_t i = lane; i < kCovTile; i += 32u) diff[i] = 0;
+    int32_t depth = 0;
+    for (uint32_t o = 0; o < 2u * kCovV; o += kCovTile) {
+        const uint32_t len = min(kCovTile, 2u * kCovV - o);
+        bm[lane] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < len; i += 32u) {
+            const int32_t v = D[o + i];
+            if (v) { diff[i] = v; atomicOr(bm + (i >> 5), 1u << (i & 31u)); }
+        }
+        __syncwarp();
+        depth = cov_warp_tile(diff, bm, len, depth, hist);
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < 101u; i += 32u)
         if (hist[i]) atomicAdd(poscov + i, (unsigned long long)hist[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shards (cov_math.h): the whole shard's anchor recurrence as a function of the state at its entry -- the block
+// descriptors of k_cov_tables applied one after the other for all 1002 states at once -- and the shard's own depth
+// over the two windows that were open at its entry.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_cov_shard_function(CovScratch S, const CovCarry* carry, uint16_t* out) {
+    __shared__ uint4 sd[1024];
+    const uint32_t nq = carry->nq;
+    const uint32_t nblk = (nq + kCovRB - 1u) / kCovRB;
+    uint32_t p = cov_state_value(min(threadIdx.x, kCovStates - 1u));
+    for (uint32_t b0 = 0; b0 < nblk; b0 += 1024u) {
+        const uint32_t m = min(1024u, nblk - b0);
+        __syncthreads();
+        if (threadIdx.x < m) sd[threadIdx.x] = S.desc[b0 + threadIdx.x];
+        __syncthreads();
+        for (uint32_t k = 0; k < m; ++k) {
+            const uint4 d = sd[k];
+            if (d.x == COV_CLOSED) p = cov_stretch(p, d.y, d.z);
+            else if (d.x == COV_CONST) p = d.y;
+            else p = cov_state_value(S.tables[(size_t)(b0 + k) * 1024u + cov_state_index(p)]);
+        }
+    }
+    if (threadIdx.x < kCovStates) out[threadIdx.x] = (uint16_t)cov_state_index(p);
+}
+
+// own depth (difference array) over [xc, xc + 2000]: the records whose window start lies in tiles 0 and 1
+__global__ void __launch_bounds__(1024) k_cov_head(BatchView B, CovScratch S, const CovCarry* carry, int32_t* head) {
+    __shared__ int32_t dn[kCovD];
+    const uint32_t nq = carry->nq;
+    for (uint32_t i = threadIdx.x; i < kCovD; i += blockDim.x) dn[i] = 0;
+    __syncthreads();
+    if (nq) {
+        const unsigned long long xc = carry->xc;
+        const uint32_t jhi = 2u <= carry->vt_last ? S.first_rec[2] : nq;
+        for (uint32_t j = threadIdx.x; j < jhi; j += blockDim.x) cov_tile_add(S, B, j, xc, xc + 2u * kCovV + 1u, dn, nullptr);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kCovD; i += blockDim.x) head[i] = dn[i];
+}
+
+__global__ void k_cov_set_state(CovCarry* carry, uint32_t first, int32_t rid_prev, uint32_t b_prev, uint32_t p_prev) {
+    carry->first = first;
+    carry->rid_prev = rid_prev;
+    carry->b_prev = b_prev;
+    carry->p_prev = p_prev;
+    carry->xc = 0;
+}
+
+__global__ void k_poscov_adjust(unsigned long long* poscov, const long long* delta) {
+    if (threadIdx.x <= 100u) poscov[threadIdx.x] += (unsigned long long)delta[threadIdx.x];
 }
 
 }  // namespace bqc

@@ -50,6 +50,94 @@ def reduce_engine(engine, bufs=None, group=None):
     return bufs
 
 
+# ------------------------------------------------------------------------------------------------------
+# One coordinate-ordered record stream cut at arbitrary records across engines (SURVEY 8e "the exception"): everything
+# but the coverage windows adds up; the windows are resolved with the four-step protocol of include/bamqc_b200.h.
+# `exchange(array) -> [array of piece 0, array of piece 1, ...]` is the only communication (an all-gather).
+# ------------------------------------------------------------------------------------------------------
+_SHARD_BYTES = None
+
+
+def _shard_to_array(sh):
+    import ctypes
+    return np.frombuffer(ctypes.string_at(ctypes.addressof(sh), ctypes.sizeof(sh)), dtype=np.uint8).copy()
+
+
+def _combine(lib, shard_arrays):
+    import ctypes
+    from . import _lib
+    n = len(shard_arrays)
+    arr = (_lib.bqc_cov_shard * n)()
+    for k, a in enumerate(shard_arrays):
+        ctypes.memmove(ctypes.addressof(arr[k]), np.ascontiguousarray(a, dtype=np.uint8).ctypes.data, ctypes.sizeof(_lib.bqc_cov_shard))
+    delta = np.zeros(101, dtype=np.int64)
+    lib.bqc_cov_shards_combine(ctypes.cast(arr, ctypes.c_void_p), n, delta.ctypes.data)
+    return delta
+
+
+def resolve_coverage_shards(engine, piece, exchange):
+    """Coverage statistic of piece number `piece` (stream order) of a record stream cut across engines in shard mode
+    (Engine.cov_defer()); call it on every piece after Engine.finish().  Returns the correction to add to the SUM of
+    the pieces' poscov tables (Engine.poscov_adjust on the merged result) -- identical on every piece."""
+    b = engine.cov_shard_boundary()
+    bounds = exchange(np.array([b.n, b.first_rid, b.first_b, b.last_rid, b.last_b], dtype=np.int64))
+    have_prev, prid, pb = 0, 0, 0
+    for k in range(piece):
+        if int(bounds[k][0]) > 0:
+            have_prev, prid, pb = 1, int(bounds[k][3]), int(bounds[k][4])
+    table = engine.cov_shard_function(have_prev, prid, pb)
+    tables = exchange(table)
+    p = 0
+    for k in range(piece):
+        if int(bounds[k][0]) > 0:
+            p = int(engine.lib.bqc_cov_apply(np.ascontiguousarray(tables[k], dtype=np.uint16).ctypes.data, p))
+    sh = engine.cov_shard_run(have_prev, prid, pb, p)
+    shards = exchange(_shard_to_array(sh))
+    return _combine(engine.lib, shards)
+
+
+def resolve_coverage_local(engines):
+    """The same protocol for engines that live in one process (pieces in list order)."""
+    import threading
+    n = len(engines)
+    slots = {}
+    barrier = threading.Barrier(n)
+    out = [None] * n
+
+    def run(k):
+        step = [0]
+
+        def exchange(a):
+            key = step[0]
+            step[0] += 1
+            slots[(key, k)] = np.array(a, copy=True)
+            barrier.wait()
+            res = [slots[(key, j)] for j in range(n)]
+            barrier.wait()
+            return res
+        out[k] = resolve_coverage_shards(engines[k], k, exchange)
+    ths = [threading.Thread(target=run, args=(k,)) for k in range(n)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    return out[0]
+
+
+def torch_exchange(device=None, group=None):
+    """exchange() over torch.distributed (NCCL: device tensors; gloo: CPU tensors)."""
+    import torch
+    import torch.distributed as dist
+
+    def exchange(a):
+        a = np.ascontiguousarray(a)
+        t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy())
+        if device is not None:
+            t = t.to(device)
+        outs = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(outs, t, group=group)
+        return [o.cpu().numpy().view(a.dtype).reshape(a.shape) for o in outs]
+    return exchange
+
+
 def clamp_sketch_numpy(total_u8):
     """Host restatement of the import clamp (for CPU tests)."""
     return np.minimum(total_u8, 15).astype(np.uint8)

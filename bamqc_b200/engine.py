@@ -202,6 +202,30 @@ class Engine:
     def merge_from(self, other):
         self._check(self.lib.bqc_merge_from(self.handle, other.handle))
 
+    # ---- one record stream cut across several engines: the coverage statistic (bamqc_b200.h) ------------
+    def cov_defer(self, on=True):
+        self._check(self.lib.bqc_cov_defer(self.handle, 1 if on else 0))
+
+    def cov_shard_boundary(self):
+        sh = _lib.bqc_cov_shard()
+        self._check(self.lib.bqc_cov_shard_boundary(self.handle, ctypes.byref(sh)))
+        return sh
+
+    def cov_shard_function(self, have_prev, prev_rid, prev_b):
+        out = np.zeros(1002, dtype=np.uint16)
+        self._check(self.lib.bqc_cov_shard_function(self.handle, int(have_prev), int(prev_rid), int(prev_b), out.ctypes.data))
+        return out
+
+    def cov_shard_run(self, have_prev, prev_rid, prev_b, p_in):
+        sh = _lib.bqc_cov_shard()
+        self._check(self.lib.bqc_cov_shard_run(self.handle, int(have_prev), int(prev_rid), int(prev_b), int(p_in), ctypes.byref(sh)))
+        return sh
+
+    def poscov_adjust(self, delta, lane=0):
+        d = np.ascontiguousarray(delta, dtype=np.int64)
+        assert d.size == 101
+        self._check(self.lib.bqc_poscov_adjust(self.handle, lane, d.ctypes.data))
+
     # ---- results ------------------------------------------------------------------------------------
     def table(self, field, lane=0, sub=0):
         f = FIELDS[field] if isinstance(field, str) else field

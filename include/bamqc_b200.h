@@ -53,8 +53,8 @@ typedef struct bqc_config {
     int32_t seed;                 /* -s (RepHash table, src/kmerstream/RepHash.cpp:4-17); 0 is rejected */
     int32_t max_read_len;         /* per-cycle table capacity; 0 => 512.  Longer reads => BQC_ERR_UNSUPPORTED */
     uint64_t staging_bytes;       /* capacity of each pinned staging buffer; 0 => 256 MiB */
-    uint32_t cov_ring_log2;       /* log2 entries of the coverage depth ring; 0 => 28 (1 GiB) */
-    int32_t host_threads;         /* host threads of the framing / anchor pre-pass inside bqc_submit; 0 => min(16, cores) */
+    uint32_t cov_ring_log2;       /* unused (the coverage statistic no longer keeps a depth ring); kept for ABI stability */
+    int32_t host_threads;         /* host threads of the framing pre-pass of host-framed submissions; 0 => min(16, cores) */
 } bqc_config;
 
 typedef struct bqc_error_info {
@@ -121,8 +121,8 @@ int bqc_get_error(bqc_engine* e, bqc_error_info* out); /* sticky device/host err
 
 /* Optional device timing of each kernel family with CUDA events on the compute stream.
  * bqc_profile_read: milliseconds and launch-group counts accumulated since the previous read, per family:
- * 0 k_stats, 1 k_eightmer, 2 k_sketch, 3 coverage scatter + flush, 4 merge/export, 5-7 host framing / pre-pass /
- * anchor pass (wall clock), 8 k_inflate, 9 framing kernels. */
+ * 0 k_stats, 1 k_eightmer, 2 k_sketch, 3 coverage kernels (own stream), 4 merge/export, 5-6 host framing / header
+ * pre-pass of host-framed submissions (wall clock), 7 unused, 8 k_inflate, 9 framing kernels. */
 void bqc_profile_enable(bqc_engine* e, int on);
 int bqc_profile_read(bqc_engine* e, double ms_out[12], uint64_t n_out[12]);
 
@@ -142,6 +142,38 @@ int bqc_sketch_export_u8(bqc_engine* e, void* dev_u8);
 int bqc_sketch_import_u8(bqc_engine* e, const void* dev_u8);
 /* Same merge inside one process (engines on different GPUs of one box; peer copy + merge kernels). */
 int bqc_merge_from(bqc_engine* dst, bqc_engine* src);
+
+/* ---- one record stream cut across several engines (SURVEY 8e "the exception") ---------------------- */
+/* Every statistic but one is a sum over records, so engines can take any pieces of the input.  The coverage
+ * windows (OverallNumbers::coverage, src/OverallNumbers.hpp:79-135) are anchored by the records before them: an
+ * engine that gets a later piece of a coordinate-ordered stream collects the records that take part
+ * (bqc_cov_defer) and resolves them once the pieces have told each other where they begin and end:
+ *   1. bqc_cov_shard_boundary  -> n, first/last (rid, begin) of the piece;
+ *   2. bqc_cov_shard_function  <- the last qualifying record before the piece (from 1.), -> the piece's anchor
+ *                                 recurrence as a function of the state at its entry (1002 x uint16);
+ *   3. bqc_cov_shard_run       <- the state at its entry (chain the functions of the pieces before it, starting
+ *                                 from 0), -> its histogram goes into its own poscov; head/tail/span describe the
+ *                                 windows that were open at its entry and at its end;
+ *   4. bqc_cov_shards_combine  (host arithmetic, any rank) -> what to add to the SUM of the pieces' poscov tables,
+ *                                 including the end-of-run flush (src/bamqualcheck.cpp:447-453); apply it to the
+ *                                 merged result with bqc_poscov_adjust.
+ * Single read group only.  Pieces are numbered in stream order. */
+typedef struct bqc_cov_shard {
+    uint64_t n;                  /* records of the piece that take part in the statistic */
+    int32_t first_rid, last_rid;
+    uint32_t first_b, last_b;
+    uint64_t span;               /* virtual coordinate of the window start of the piece's last record */
+    int32_t head[2001];          /* own depth (difference array) over the two windows open at its entry */
+    int32_t tail[2001];          /* ... open at its end */
+} bqc_cov_shard;
+int bqc_cov_defer(bqc_engine* e, int on);   /* after bqc_reset, before the first submission */
+int bqc_cov_shard_boundary(bqc_engine* e, bqc_cov_shard* out);
+int bqc_cov_shard_function(bqc_engine* e, int32_t have_prev, int32_t prev_rid, uint32_t prev_b, uint16_t* table1002);
+int bqc_cov_shard_run(bqc_engine* e, int32_t have_prev, int32_t prev_rid, uint32_t prev_b, uint32_t p_in, bqc_cov_shard* out);
+void bqc_cov_shards_combine(const bqc_cov_shard* shards, int32_t n_shards, int64_t delta[101]);
+int bqc_poscov_adjust(bqc_engine* e, int32_t lane, const int64_t delta[101]);
+/* State after a piece whose function is `table1002`, entered in state p (0..1000 or 2000). */
+uint32_t bqc_cov_apply(const uint16_t* table1002, uint32_t p);
 
 /* ---- configuration read-back ------------------------------------------------------------------- */
 int32_t bqc_n_lanes(bqc_engine* e);

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <string>
 #include <vector>
 
 #include "../bamqc_b200/csrc/cov_math.h"
@@ -66,7 +67,8 @@ static void analyse(Block& K, const std::vector<Rec>& q, uint32_t r0, uint32_t n
     uint32_t ord = 0;
     for (uint32_t i = 1; i <= n; ++i) {
         bool other = K.srid[i] != K.srid[i - 1] || (K.isfirst && i == 1);
-        if (other || (uint32_t)(K.sb[i] - K.sb[i - 1]) >= kCovV) { ++ord; K.cpos[ord] = i; K.cg[ord] = K.sb[i] - K.sb[i - 1]; K.cdef[ord] = other; }
+        const uint32_t g = K.sb[i] - K.sb[i - 1];
+        if (other || g >= kCovV) { ++ord; K.cpos[ord] = i; K.cg[ord] = g; K.cdef[ord] = other || cov_gap_definite(g); }
         K.cord[i] = ord;
     }
     K.nc = ord;
@@ -91,6 +93,7 @@ struct ParModel {
     Carry cy;
     std::vector<uint64_t> poscov = std::vector<uint64_t>(101, 0);
     std::vector<uint32_t> pstate;
+    std::vector<int64_t> head = std::vector<int64_t>(2048, 0);  // own depth over [0, 2000] of the first batch (shard mode)
     uint32_t RB;
     explicit ParModel(uint32_t rb) : RB(rb) {}
     void batch(const std::vector<Rec>& q) {
@@ -158,6 +161,11 @@ struct ParModel {
             if (b > xl) { dn[(size_t)(std::max(a, xl) - xl)] += 1; dn[(size_t)(b - xl)] -= 1; }
         };
         for (uint32_t r = 0; r < nq; ++r) add(base[r] + A[r], base[r] + Bv[r]);
+        if (xc == 0)
+            for (uint32_t r = 0; r < nq; ++r) {
+                const uint64_t a = base[r] + A[r], b = base[r] + Bv[r];
+                if (a < b && a <= 2000) { head[(size_t)a] += 1; if (b <= 2000) head[(size_t)b] -= 1; }
+            }
         for (uint32_t d = 0; d <= 2000; ++d) {
             int64_t v = cy.D[d];
             if (!v) continue;
@@ -166,7 +174,57 @@ struct ParModel {
             if (x <= xl) dn[0] += v; else dn[(size_t)(x - xl)] += v;
         }
         int64_t depth = 0;
-        for (uint64_t x = xc; x < xl; ++x) { depth += diff[(size_t)(x - xc)]; poscov[depth > 100 ? 100 : depth] += 1; }
+        std::vector<uint64_t> direct(101, 0);
+        for (uint64_t x = xc; x < xl; ++x) { depth += diff[(size_t)(x - xc)]; direct[depth > 100 ? 100 : depth] += 1; }
+        // the same histogram the way k_cov_tiles does it: tiles of T positions, record ranges from first_rec (first record
+        // whose window start lies at or beyond the tile), look-back of two tiles, carry entries in tiles 0 and 1
+        {
+            const uint64_t T = 1024;
+            std::vector<uint64_t> V(nq);
+            for (uint32_t r = 0; r < nq; ++r) V[r] = base[r] - pstate[pstate.size() - nq + r];
+            const uint32_t vt_last = (uint32_t)((V[nq - 1] - xc) / T);
+            const uint32_t ntiles = (uint32_t)((V[nq - 1] - xc + T - 1) / T);
+            std::vector<uint32_t> first_rec(vt_last + 2, 0xFFFFFFFFu);
+            for (uint32_t r = 0; r < nq; ++r) {
+                const uint32_t t1 = (uint32_t)((V[r] - xc) / T);
+                for (uint32_t tt = r ? (uint32_t)((V[r - 1] - xc) / T) + 1 : 0; tt <= t1; ++tt) first_rec[tt] = r;
+            }
+            std::vector<uint64_t> tiled(101, 0);
+            for (uint32_t t = 0; t < ntiles; ++t) {
+                const uint64_t T0 = xc + (uint64_t)t * T, T1 = std::min(T0 + T, xl);
+                const uint32_t len = (uint32_t)(T1 - T0);
+                std::vector<int64_t> d(T + 1, 0);
+                const uint32_t jlo = t >= 2 ? first_rec[t - 2] : 0, jhi = t + 1 <= vt_last ? first_rec[t + 1] : nq;
+                if (jlo == 0xFFFFFFFFu || jhi == 0xFFFFFFFFu) { printf("first_rec hole at tile %u\n", t); exit(4); }
+                for (uint32_t j = jlo; j < jhi; ++j) {
+                    const uint64_t a = base[j] + A[j], b = base[j] + Bv[j];
+                    if (b <= T0 || a >= T1 || a >= b) continue;
+                    d[(size_t)(std::max(a, T0) - T0)] += 1;
+                    if (b < T1) d[(size_t)(b - T0)] -= 1;
+                }
+                if (t < 2)
+                    for (uint32_t i = 0; i < len && t * T + i <= 2000; ++i) d[i] += cy.D[t * T + i];
+                int64_t dep = 0;
+                if (t == 1) for (uint32_t i = 0; i < T; ++i) dep += cy.D[i];   // depth the open windows carry into tile 1
+                for (uint32_t i = 0; i < len; ++i) { dep += d[i]; tiled[dep > 100 ? 100 : dep] += 1; }
+            }
+            if (tiled != direct) { printf("tiled histogram differs from the direct one (nq %u, ntiles %u)\n", nq, ntiles); exit(5); }
+            // k_cov_carry: only the records from first_rec[vt_last - 2] on can reach beyond xl
+            std::vector<int64_t> dn2(2048, 0);
+            const uint32_t jlo = vt_last >= 2 ? first_rec[vt_last - 2] : 0;
+            for (uint32_t j = jlo; j < nq; ++j) {
+                const uint64_t a = base[j] + A[j], b = base[j] + Bv[j];
+                if (a < b && b > xl) { dn2[(size_t)(std::max(a, xl) - xl)] += 1; dn2[(size_t)(b - xl)] -= 1; }
+            }
+            for (uint32_t d = 0; d <= 2000; ++d) {
+                int64_t v = cy.D[d];
+                if (!v) continue;
+                uint64_t x = xc + d;
+                if (x <= xl) dn2[0] += v; else dn2[(size_t)(x - xl)] += v;
+            }
+            if (dn2 != dn) { printf("carry from the tail records differs (nq %u, vt_last %u, jlo %u)\n", nq, vt_last, jlo); exit(6); }
+        }
+        for (int i = 0; i <= 100; ++i) poscov[i] += direct[i];
         cy.D = dn;
         cy.first = false; cy.rid_prev = q[nq - 1].rid; cy.b_prev = q[nq - 1].b; cy.p_prev = plast; cy.xc = xl;
     }
@@ -200,8 +258,112 @@ static int run_case(const std::vector<Rec>& recs, const std::vector<size_t>& cut
     return bad;
 }
 
-int main() {
+// One stream cut into shards, each processed on its own from an unknown state (cov_math.h "Shards")
+static int run_sharded(const std::vector<Rec>& recs, std::vector<size_t> cuts, uint32_t rb, const char* name, FILE* dump = nullptr) {
+    SeqModel S;
+    for (const Rec& r : recs) S.coverage(r);
+    S.finish();
+    cuts.push_back(recs.size());
+    const int K = (int)cuts.size();
+    std::vector<std::vector<Rec>> part((size_t)K);
+    size_t lo = 0;
+    for (int k = 0; k < K; ++k) { part[k].assign(recs.begin() + lo, recs.begin() + cuts[k]); lo = cuts[k]; }
+    // A: boundaries; B: what each shard needs to know about the record before it
+    std::vector<int> have_prev(K, 0); std::vector<int32_t> prid(K, 0); std::vector<uint32_t> pb(K, 0);
+    {
+        bool have = false; int32_t rid = 0; uint32_t b = 0;
+        for (int k = 0; k < K; ++k) {
+            have_prev[k] = have; prid[k] = rid; pb[k] = b;
+            if (!part[k].empty()) { have = true; rid = part[k].back().rid; b = part[k].back().b; }
+        }
+    }
+    // C: shard functions (state at entry -> state at exit); D: chain them
+    std::vector<uint32_t> p_in(K, 0);
+    std::vector<std::vector<uint16_t>> Fs((size_t)K);
+    uint32_t p = 0;
+    for (int k = 0; k < K; ++k) {
+        p_in[k] = p;
+        Fs[k].resize(kCovStates);
+        for (uint32_t s = 0; s < kCovStates; ++s) Fs[k][s] = (uint16_t)s;
+        if (part[k].empty()) continue;
+        std::vector<uint16_t>& F = Fs[k];
+        for (uint32_t s = 0; s < kCovStates; ++s) {
+            uint32_t q = cov_state_value(s);
+            int32_t rid = prid[k]; uint32_t b = pb[k];
+            bool first = !have_prev[k];
+            for (const Rec& r : part[k]) {
+                bool reset;
+                if (first) { q = 0; first = false; }
+                else q = cov_step(q, r.b - b, r.rid != rid, reset);
+                rid = r.rid; b = r.b;
+            }
+            F[s] = (uint16_t)cov_state_index(q);
+        }
+        p = cov_state_value(F[cov_state_index(p)]);
+    }
+    // E: every shard on its own; F: combine
+    std::vector<uint64_t> total(101, 0);
+    std::vector<std::vector<uint64_t>> own((size_t)K);
+    std::vector<std::vector<int32_t>> heads((size_t)K, std::vector<int32_t>(2001, 0)), tails((size_t)K, std::vector<int32_t>(2001, 0));
+    std::vector<CovShardPiece> pieces((size_t)K);
+    for (int k = 0; k < K; ++k) {
+        ParModel P(rb);
+        P.cy.first = !have_prev[k]; P.cy.rid_prev = prid[k]; P.cy.b_prev = pb[k]; P.cy.p_prev = p_in[k]; P.cy.xc = 0;
+        P.batch(part[k]);
+        for (int i = 0; i <= 100; ++i) total[i] += P.poscov[i];
+        own[k] = P.poscov;
+        for (int i = 0; i <= 2000; ++i) { heads[k][i] = (int32_t)P.head[i]; tails[k][i] = (int32_t)P.cy.D[i]; }
+        pieces[k].n = part[k].size(); pieces[k].span = P.cy.xc; pieces[k].head = heads[k].data(); pieces[k].tail = tails[k].data();
+    }
+    long long delta[101];
+    cov_shards_combine(pieces.data(), K, delta);
+    if (dump) {  // the pieces as JSON (tests/test_dist_gloo.py replays the exchange protocol with them)
+        fprintf(dump, "{\"expected\": [");
+        for (int i = 0; i <= 100; ++i) fprintf(dump, "%s%llu", i ? "," : "", (unsigned long long)S.poscov[i]);
+        fprintf(dump, "], \"pieces\": [");
+        for (int k = 0; k < K; ++k) {
+            fprintf(dump, "%s{\"n\": %zu, \"first_rid\": %d, \"first_b\": %u, \"last_rid\": %d, \"last_b\": %u, \"have_prev\": %d, \"prev_rid\": %d, \"prev_b\": %u, \"p_in\": %u, \"span\": %llu, ",
+                    k ? "," : "", part[k].size(), part[k].empty() ? 0 : part[k].front().rid, part[k].empty() ? 0u : part[k].front().b,
+                    part[k].empty() ? 0 : part[k].back().rid, part[k].empty() ? 0u : part[k].back().b, have_prev[k], prid[k], pb[k], p_in[k], (unsigned long long)pieces[k].span);
+            auto arr = [&](const char* key, auto& v, size_t n, const char* end) {
+                fprintf(dump, "\"%s\": [", key);
+                for (size_t i = 0; i < n; ++i) fprintf(dump, "%s%lld", i ? "," : "", (long long)v[i]);
+                fprintf(dump, "]%s", end);
+            };
+            arr("table", Fs[k], kCovStates, ", "); arr("head", heads[k], 2001, ", "); arr("tail", tails[k], 2001, ", "); arr("poscov", own[k], 101, "}");
+        }
+        fprintf(dump, "]}\n");
+    }
+    int bad = 0;
+    for (int i = 0; i <= 100; ++i)
+        if ((long long)S.poscov[i] != (long long)total[i] + delta[i]) {
+            if (bad < 6) printf("%s sharded x%d: poscov[%d]: sequential %llu, shards %lld\n", name, K, i, (unsigned long long)S.poscov[i], (long long)total[i] + delta[i]);
+            ++bad;
+        }
+    return bad;
+}
+
+int main(int argc, char** argv) {
     std::mt19937_64 rng(12345);
+    if (argc >= 4 && std::string(argv[1]) == "--dump-shards") {  // --dump-shards K out.json: one random stream in K pieces
+        const int K = atoi(argv[2]);
+        std::vector<Rec> recs;
+        uint32_t b = 1000;
+        int32_t rid = 0;
+        for (int i = 0; i < 6000; ++i) {
+            const uint32_t u = (uint32_t)(rng() % 1000);
+            b += u < 900 ? (uint32_t)(rng() % 400) : 900 + (uint32_t)(rng() % 1300);
+            if (rng() % 1500 == 0) { ++rid; b = (uint32_t)(rng() % 5000); }
+            Rec r; r.rid = rid; r.b = b; r.c0 = rng() % 10 == 0 ? (uint32_t)(rng() % 60) : 0; r.len = 100 + (uint32_t)(rng() % 60);
+            recs.push_back(r);
+        }
+        std::vector<size_t> cuts;
+        for (int k = 1; k < K; ++k) cuts.push_back(k == 2 ? cuts.back() : recs.size() * k / K + rng() % 50);  // piece 2 (if any) is empty
+        FILE* f = fopen(argv[3], "w");
+        const int bad = run_sharded(recs, cuts, 2048, "dump", f);
+        fclose(f);
+        return bad ? 1 : 0;
+    }
     int bad = 0, cases = 0;
     for (int it = 0; it < 400; ++it) {
         const int mode = it % 8;
@@ -239,11 +401,13 @@ int main() {
         char name[64];
         snprintf(name, sizeof(name), "case %d (mode %d, n %zu, rb %u)", it, mode, n, rb);
         bad += run_case(recs, cuts, rb, name);
-        ++cases;
+        bad += run_sharded(recs, cuts, rb, name);
+        cases += 2;
     }
     {   // no record at all: two empty windows
         bad += run_case(std::vector<Rec>(), std::vector<size_t>(), 2048, "empty");
-        ++cases;
+        bad += run_sharded(std::vector<Rec>(), std::vector<size_t>(1, 0), 2048, "empty");
+        cases += 2;
     }
     if (bad) { printf("cov_selftest: %d mismatches in %d cases\n", bad, cases); return 1; }
     printf("cov_selftest ok: %d cases, %llu records, %llu in the edge state (pos == 2000), %llu backward steps\n", cases, (unsigned long long)g_records, (unsigned long long)g_edges, (unsigned long long)g_backward);

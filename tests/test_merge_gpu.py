@@ -82,3 +82,45 @@ def test_two_shards_merge_exactly(tmp_path):
         assert not diffs, name + "\n" + "\n".join(diffs)
     for e in engines + [third]:
         e.close()
+
+
+@pytest.mark.parametrize("cuts", [(0.37,), (0.0, 0.52), (0.25, 0.25, 0.81)])
+def test_one_sorted_stream_cut_at_arbitrary_records(tmp_path, cuts):
+    """SURVEY 8e "the exception": ONE gap-free coordinate-sorted BAM cut at arbitrary record indices (also in the middle
+    of a pile of reads, with empty pieces) across engines in shard mode.  Everything adds up; the coverage windows are
+    resolved with the bqc_cov_shard_* protocol.  The merged result must be byte-identical to the oracle on the whole
+    file -- no re-anchoring gaps in the data."""
+    from bamqc_b200 import Engine, synth, dist
+    genome = util.small_genome(seed=23, lengths=(300000, 200000, 50000))
+    lib_ = synth.Library(seed=77, n_pairs=15000)
+    records, offsets = synth.generate(genome, lib_)
+    n = len(offsets) - 1
+    fasta, bam = tmp_path / "g.fa", tmp_path / "whole.ubam"
+    genome.write_fasta(fasta)
+    synth.write_bam(bam, genome, lib_, records, int(offsets[-1]))
+    r = util.run_oracle(bam, fasta, tmp_path / "oracle.bamqc", chroms="chr1,chr2")
+    assert r.returncode == 0, r.stderr
+    bounds = [0] + [int(n * c) for c in cuts] + [n]
+    engines = []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        e = Engine(lane_ids=["L1"], ref_names=genome.names, chroms="chr1,chr2", staging_bytes=8 << 20)
+        for rid, (p, m) in enumerate(zip(genome.packed, genome.lengths)):
+            e.set_reference(rid, p, m)
+        e.cov_defer()
+        # several submissions per piece: the records that take part are collected across batches
+        step = max(1, (hi - lo) // 3)
+        for a in range(lo, hi, step):
+            b = min(hi, a + step)
+            o = offsets[a:b + 1]
+            e.submit(records[int(o[0]):int(o[-1])], None)
+        e.finish()
+        engines.append(e)
+    delta = dist.resolve_coverage_local(engines)
+    for e in engines[1:]:
+        engines[0].merge_from(e)
+    engines[0].poscov_adjust(delta)
+    engines[0].write_bamqc("S1", tmp_path / "merged.bamqc")
+    diffs = util.diff_bamqc(tmp_path / "oracle.bamqc", tmp_path / "merged.bamqc")
+    for e in engines:
+        e.close()
+    assert not diffs, "\n".join(diffs)
