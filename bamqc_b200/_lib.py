@@ -1,6 +1,7 @@
-"""ctypes loader for libbamqc_b200.so (built in-tree by ``bamqc_b200/csrc/Makefile``).
+"""ctypes loaders for libbamqc_b200.so (the product: CUDA engine + host front end) and libbamqc_synth.so (the seeded
+synthetic data generator used by the tests and bench.py), both built in-tree by ``bamqc_b200/csrc/Makefile``.
 
-There is no Python or CPU fallback: if the library is missing, importing the engine fails loudly.
+There is no Python or CPU fallback: if the product library is missing, importing the engine fails loudly.
 """
 import ctypes
 import os
@@ -8,6 +9,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_SYNTH = None
 
 
 def library_path():
@@ -130,7 +132,10 @@ PROTOTYPES = {
     "bqc_fasta_contig": (ctypes.c_int64, [_vp, ctypes.c_char_p, _P(_vp)]),
     "bqc_fasta_close": (None, [_vp]),
     "bqc_main": (ctypes.c_int, [ctypes.c_int, _P(ctypes.c_char_p)]),
-    # include/bamqc_synth.h
+}
+
+# include/bamqc_synth.h (libbamqc_synth.so)
+SYNTH_PROTOTYPES = {
     "bqc_synth_default_params": (None, [_P(bqc_synth_params)]),
     "bqc_synth_reference": (None, [_u64, _i32, _u64, _vp]),
     "bqc_synth_write_fasta": (ctypes.c_int, [ctypes.c_char_p, _i32, _P(ctypes.c_char_p), _P(_u64), _P(_vp)]),
@@ -139,6 +144,23 @@ PROTOTYPES = {
     "bqc_synth_write_bam": (ctypes.c_int, [ctypes.c_char_p, _P(bqc_synth_params), ctypes.c_char_p, _vp, _u64, ctypes.c_int]),
     "bqc_synth_bgzf_compress": (_u64, [_vp, _u64, ctypes.c_int, _vp, _u64]),
 }
+
+
+def load_synth():
+    """Load libbamqc_synth.so (generator only: no CUDA, no product code)."""
+    global _SYNTH
+    if _SYNTH is not None:
+        return _SYNTH
+    path = os.path.join(_HERE, "libbamqc_synth.so")
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `make -C bamqc_b200/csrc`")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SYNTH_PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _SYNTH = lib
+    return lib
 
 
 def load_library():

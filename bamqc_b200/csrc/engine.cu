@@ -161,6 +161,8 @@ struct bqc_engine {
     uint8_t* d_cov_q = nullptr;        // the compact qualifying records (rid, begin, interval, record index)
     uint64_t cov_q_cap = 0;
     bool cov_deferred = false;         // shard mode: records are collected, the statistic is resolved by bqc_cov_shard_*
+    bool cov_head_piece = false;       // shard mode of the FIRST piece of a stream: its entry state is known, so it runs like a
+                                       // normal engine; only the end-of-run flush is left to bqc_cov_shards_combine
     uint64_t cov_acc_bound = 0;        // shard mode: upper bound of the records collected so far
     uint16_t* d_cov_fn = nullptr;      // shard mode: [1024] shard function; [2048 int32] head
     uint64_t cov_ctl_bytes = 0;        // tickets + look-back states at the front of the scratch (zeroed per launch group)
@@ -217,6 +219,8 @@ struct bqc_engine {
 
     // optional per-kernel-family timing (CUDA events on the compute stream)
     bool profiling = false;
+    bool prof_serial = false;      // bqc_profile_enable(e, 2): the coverage kernels run on the compute stream so that the per-family
+                                   // times do not overlap (exclusive shares for the roofline report); slower than the default
     struct ProfEv { int family; cudaEvent_t a, b; };
     std::mutex prof_m;             // ProfScope is used from the commit and the anchor thread
     std::vector<ProfEv> prof_pending;
@@ -710,7 +714,8 @@ struct ProfScope {  // records an event pair around the launches of one kernel f
         e->prof_pending.push_back(ev);
     }
 };
-extern "C" void bqc_profile_enable(bqc_engine* e, int on) { e->profiling = on != 0; }
+extern "C" void bqc_profile_enable(bqc_engine* e, int on) { e->profiling = on != 0; e->prof_serial = on == 2; }
+static inline cudaStream_t cov_stream(bqc_engine* e) { return e->prof_serial ? e->compute : e->covs; }
 // Accumulated device time per kernel family since the last call: 0 k_stats, 1 k_eightmer, 2 k_sketch,
 // 3 coverage flush (3 kernels per launch group), 4 merge/export.  Synchronises the compute stream.
 extern "C" int bqc_profile_read(bqc_engine* e, double ms_out[12], uint64_t n_out[12]) {
@@ -831,14 +836,15 @@ static int batch_launch_setup(bqc_engine* e, const DeviceBatch& d, BatchLaunch& 
 // arrays (a batch, or a whole shard), from the state in CovCarry; n_bound >= the number of compact records.
 static int launch_cov_resolve(bqc_engine* e, uint32_t lane, const BatchView& B, uint64_t n_bound, bool tables_done) {
     const CovScratch& S = e->cov_scratch;
+    cudaStream_t cs = cov_stream(e);
     CovCarry* carry = e->d_cov_carry + lane;
     int32_t* cd = e->d_cov_d + (uint64_t)lane * 2 * kCovD;
     unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
     const uint32_t nblk = (uint32_t)((n_bound + kCovRB - 1) / kCovRB);
-    if (!tables_done) k_cov_tables<<<nblk, kCovBlockThreads, kCovBlockSmem, e->covs>>>(S, carry);
-    k_cov_link<<<1, 1024, 0, e->covs>>>(S, carry);
-    k_cov_codes<<<(int)std::min<uint32_t>(nblk, (uint32_t)e->n_sm * 2u), kCovBlockThreads, kCovCodesSmem, e->covs>>>(S, carry);
-    k_cov_tiles<<<e->n_sm * e->tune_cov_bps, kCovTileThreads, 0, e->covs>>>(B, S, carry, cd, poscov);
+    if (!tables_done) k_cov_tables<<<nblk, kCovBlockThreads, kCovBlockSmem, cs>>>(S, carry);
+    k_cov_link<<<1, 1024, 0, cs>>>(S, carry);
+    k_cov_codes<<<(int)std::min<uint32_t>(nblk, (uint32_t)e->n_sm * 2u), kCovBlockThreads, kCovCodesSmem, cs>>>(S, carry);
+    k_cov_tiles<<<e->n_sm * e->tune_cov_bps, kCovTileThreads, 0, cs>>>(B, S, carry, cd, poscov);
     e->launches += tables_done ? 3 : 4;
     return 0;
 }
@@ -849,6 +855,7 @@ static int launch_cov_resolve(bqc_engine* e, uint32_t lane, const BatchView& B, 
 // records that take part (bqc_cov_shard_* resolve them at the end).
 static int launch_cov(bqc_engine* e, const DeviceBatch& d, const BatchLaunch& BL) {
     const uint64_t n = d.n_records;
+    cudaStream_t cs = cov_stream(e);
     if (n) {
         int rc = ensure_cov_scratch(e, n);
         if (rc) return rc;
@@ -863,21 +870,21 @@ static int launch_cov(bqc_engine* e, const DeviceBatch& d, const BatchLaunch& BL
         B.cycb = BL.cycb;
         B.first_record = d.first_record;
         const uint32_t nprep = (uint32_t)((n + kCovPrepTile - 1) / kCovPrepTile);
-        ProfScope prof(e, 3, e->covs);
+        ProfScope prof(e, 3, cs);
         for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
             CovCarry* carry = e->d_cov_carry + lane;
-            CU(cudaMemsetAsync(e->d_cov_scratch, 0, e->cov_ctl_bytes, e->covs));
-            k_cov_prep<<<(int)std::min<uint32_t>(nprep, (uint32_t)e->n_sm * 8u), 256, 0, e->covs>>>(BL.E, B, lane, S, carry, e->cov_deferred ? 1u : 0u);
+            CU(cudaMemsetAsync(e->d_cov_scratch, 0, e->cov_ctl_bytes, cs));
+            k_cov_prep<<<(int)std::min<uint32_t>(nprep, (uint32_t)e->n_sm * 8u), 256, 0, cs>>>(BL.E, B, lane, S, carry, e->cov_deferred ? 1u : 0u);
             e->launches += 1;
             if (e->cov_deferred) continue;
             rc = launch_cov_resolve(e, lane, B, n, false);
             if (rc) return rc;
-            k_cov_carry<<<1, 1024, 0, e->covs>>>(B, S, carry, e->d_cov_d + (uint64_t)lane * 2 * kCovD);
+            k_cov_carry<<<1, 1024, 0, cs>>>(B, S, carry, e->d_cov_d + (uint64_t)lane * 2 * kCovD);
             e->launches += 1;
         }
         if (e->cov_deferred) e->cov_acc_bound += n;
     }
-    CU(cudaEventRecord(e->cov_done, e->covs));
+    CU(cudaEventRecord(e->cov_done, cs));
     CU(cudaGetLastError());
     return 0;
 }
@@ -1495,12 +1502,12 @@ extern "C" int bqc_finish(bqc_engine* e) {
         // src/bamqualcheck.cpp:447-453: update_coverage(); update_vectors(); update_coverage() for every lane
         for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
             unsigned long long* poscov = (unsigned long long*)(e->d_counters + (uint64_t)lane * e->L.lane_stride + e->L.o_poscov);
-            ProfScope prof(e, 3, e->covs);
-            if (e->cov_deferred) continue;  // shard mode: bqc_cov_shards_combine flushes the last windows
-            k_cov_final<<<1, 32, 0, e->covs>>>(e->d_cov_carry + lane, e->d_cov_d + (uint64_t)lane * 2 * kCovD, poscov);
+            ProfScope prof(e, 3, cov_stream(e));
+            if (e->cov_deferred || e->cov_head_piece) continue;  // shard mode: bqc_cov_shards_combine flushes the last windows
+            k_cov_final<<<1, 32, 0, cov_stream(e)>>>(e->d_cov_carry + lane, e->d_cov_d + (uint64_t)lane * 2 * kCovD, poscov);
             e->launches += 1;
         }
-        CU(cudaEventRecord(e->cov_done, e->covs));
+        CU(cudaEventRecord(e->cov_done, cov_stream(e)));
         CU(cudaStreamWaitEvent(e->compute, e->cov_done, 0));
         e->finished = true;
     }
@@ -1514,7 +1521,8 @@ extern "C" int bqc_finish(bqc_engine* e) {
 extern "C" int bqc_cov_defer(bqc_engine* e, int on) {
     if (on && e->n_lanes != 1) { set_error(e, "bqc_cov_defer: shard mode supports a single read group"); return BQC_ERR_ARG; }
     if (e->records_seen || e->cov_acc_bound) { set_error(e, "bqc_cov_defer: call it right after bqc_reset"); return BQC_ERR_ARG; }
-    e->cov_deferred = on != 0;
+    e->cov_deferred = on == 1;
+    e->cov_head_piece = on == 2;
     return 0;
 }
 
@@ -1531,10 +1539,18 @@ static int cov_shard_sync(bqc_engine* e, uint32_t& nq) {
 
 extern "C" int bqc_cov_shard_boundary(bqc_engine* e, bqc_cov_shard* out) {
     memset(out, 0, sizeof(*out));
-    if (!e->cov_deferred) { set_error(e, "bqc_cov_shard_boundary: engine is not in shard mode (bqc_cov_defer)"); return BQC_ERR_ARG; }
+    if (!e->cov_deferred && !e->cov_head_piece) { set_error(e, "bqc_cov_shard_boundary: engine is not in shard mode (bqc_cov_defer)"); return BQC_ERR_ARG; }
     uint32_t nq = 0;
     int rc = cov_shard_sync(e, nq);
     if (rc) return rc;
+    if (e->cov_head_piece) {  // already resolved batch by batch: what matters to the pieces behind is the last record
+        CovCarry c;
+        CU(cudaMemcpy(&c, e->d_cov_carry, sizeof(c), cudaMemcpyDeviceToHost));
+        out->n = c.first ? 0 : 1;   // (a count is not kept; non-zero = some record took part)
+        out->last_rid = c.rid_prev;
+        out->last_b = c.b_prev;
+        return 0;
+    }
     out->n = nq;
     if (nq) {
         const CovScratch& S = e->cov_scratch;
@@ -1547,37 +1563,49 @@ extern "C" int bqc_cov_shard_boundary(bqc_engine* e, bqc_cov_shard* out) {
 }
 
 extern "C" int bqc_cov_shard_function(bqc_engine* e, int32_t have_prev, int32_t prev_rid, uint32_t prev_b, uint16_t* table1002) {
-    if (!e->cov_deferred) { set_error(e, "bqc_cov_shard_function: engine is not in shard mode"); return BQC_ERR_ARG; }
+    if (!e->cov_deferred && !e->cov_head_piece) { set_error(e, "bqc_cov_shard_function: engine is not in shard mode"); return BQC_ERR_ARG; }
     uint32_t nq = 0;
     int rc = cov_shard_sync(e, nq);
     if (rc) return rc;
     for (uint32_t s = 0; s < kCovStates; ++s) table1002[s] = (uint16_t)s;   // no record: the state passes through
+    if (e->cov_head_piece) {  // the first piece ends in the state it carries
+        CovCarry c;
+        CU(cudaMemcpy(&c, e->d_cov_carry, sizeof(c), cudaMemcpyDeviceToHost));
+        if (!c.first) for (uint32_t s = 0; s < kCovStates; ++s) table1002[s] = (uint16_t)cov_state_index(c.p_prev);
+        return 0;
+    }
     if (!nq) return 0;
     rc = ensure_cov_scratch(e, nq);
     if (rc) return rc;
     if (!e->d_cov_fn) CU(cudaMalloc(&e->d_cov_fn, 1024 * 2 + kCovD * 4));
     const uint32_t nblk = (nq + kCovRB - 1) / kCovRB;
-    k_cov_set_state<<<1, 1, 0, e->covs>>>(e->d_cov_carry, have_prev ? 0u : 1u, prev_rid, prev_b, 0u);
-    k_cov_tables<<<nblk, kCovBlockThreads, kCovBlockSmem, e->covs>>>(e->cov_scratch, e->d_cov_carry);
-    k_cov_shard_function<<<1, 1024, 0, e->covs>>>(e->cov_scratch, e->d_cov_carry, e->d_cov_fn);
+    k_cov_set_state<<<1, 1, 0, cov_stream(e)>>>(e->d_cov_carry, have_prev ? 0u : 1u, prev_rid, prev_b, 0u);
+    k_cov_tables<<<nblk, kCovBlockThreads, kCovBlockSmem, cov_stream(e)>>>(e->cov_scratch, e->d_cov_carry);
+    k_cov_shard_function<<<1, 1024, 0, cov_stream(e)>>>(e->cov_scratch, e->d_cov_carry, e->d_cov_fn);
     e->launches += 3;
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(e->covs));
+    CU(cudaStreamSynchronize(cov_stream(e)));
     CU(cudaMemcpy(table1002, e->d_cov_fn, kCovStates * 2, cudaMemcpyDeviceToHost));
     return 0;
 }
 
 extern "C" int bqc_cov_shard_run(bqc_engine* e, int32_t have_prev, int32_t prev_rid, uint32_t prev_b, uint32_t p_in, bqc_cov_shard* out) {
-    if (!e->cov_deferred) { set_error(e, "bqc_cov_shard_run: engine is not in shard mode"); return BQC_ERR_ARG; }
+    if (!e->cov_deferred && !e->cov_head_piece) { set_error(e, "bqc_cov_shard_run: engine is not in shard mode"); return BQC_ERR_ARG; }
     uint32_t nq = 0;
     int rc = cov_shard_sync(e, nq);
     if (rc) return rc;
-    bqc_cov_shard keep = *out;
     memset(out->head, 0, sizeof(out->head));
     memset(out->tail, 0, sizeof(out->tail));
     out->span = 0;
     out->n = nq;
-    (void)keep;
+    if (e->cov_head_piece) {  // nothing left to resolve: report the two windows that are still open
+        CovCarry c;
+        CU(cudaMemcpy(&c, e->d_cov_carry, sizeof(c), cudaMemcpyDeviceToHost));
+        out->n = c.first ? 0 : 1;
+        out->span = c.xc;
+        CU(cudaMemcpy(out->tail, e->d_cov_d + (uint64_t)c.parity * kCovD, sizeof(out->tail), cudaMemcpyDeviceToHost));
+        return 0;
+    }
     if (!nq) return 0;
     rc = ensure_cov_scratch(e, nq);
     if (rc) return rc;
@@ -1585,19 +1613,19 @@ extern "C" int bqc_cov_shard_run(bqc_engine* e, int32_t have_prev, int32_t prev_
     int32_t* d_head = (int32_t*)(e->d_cov_fn + 1024);
     BatchView B;
     memset(&B, 0, sizeof(B));
-    CU(cudaMemsetAsync(e->d_cov_scratch, 0, e->cov_ctl_bytes, e->covs));
-    CU(cudaMemsetAsync(e->d_cov_d, 0, 2 * kCovD * 4, e->covs));
-    k_cov_set_state<<<1, 1, 0, e->covs>>>(e->d_cov_carry, have_prev ? 0u : 1u, prev_rid, prev_b, p_in);
+    CU(cudaMemsetAsync(e->d_cov_scratch, 0, e->cov_ctl_bytes, cov_stream(e)));
+    CU(cudaMemsetAsync(e->d_cov_d, 0, 2 * kCovD * 4, cov_stream(e)));
+    k_cov_set_state<<<1, 1, 0, cov_stream(e)>>>(e->d_cov_carry, have_prev ? 0u : 1u, prev_rid, prev_b, p_in);
     {
-        ProfScope prof(e, 3, e->covs);
+        ProfScope prof(e, 3, cov_stream(e));
         rc = launch_cov_resolve(e, 0, B, nq, false);
         if (rc) return rc;
-        k_cov_head<<<1, 1024, 0, e->covs>>>(B, e->cov_scratch, e->d_cov_carry, d_head);
-        k_cov_carry<<<1, 1024, 0, e->covs>>>(B, e->cov_scratch, e->d_cov_carry, e->d_cov_d);
+        k_cov_head<<<1, 1024, 0, cov_stream(e)>>>(B, e->cov_scratch, e->d_cov_carry, d_head);
+        k_cov_carry<<<1, 1024, 0, cov_stream(e)>>>(B, e->cov_scratch, e->d_cov_carry, e->d_cov_d);
         e->launches += 3;
     }
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(e->covs));
+    CU(cudaStreamSynchronize(cov_stream(e)));
     CovCarry c;
     CU(cudaMemcpy(&c, e->d_cov_carry, sizeof(c), cudaMemcpyDeviceToHost));
     out->span = c.xc;

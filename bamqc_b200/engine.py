@@ -171,7 +171,7 @@ class Engine:
         return int(self.lib.bqc_kernel_launches(self.handle))
 
     def profile_enable(self, on=True):
-        self.lib.bqc_profile_enable(self.handle, 1 if on else 0)
+        self.lib.bqc_profile_enable(self.handle, int(on))  # 2: serialised (coverage kernels on the compute stream)
 
     def profile_read(self):
         """{family: (milliseconds, launch groups)} since the previous read (CUDA events on the compute stream)."""
@@ -203,8 +203,9 @@ class Engine:
         self._check(self.lib.bqc_merge_from(self.handle, other.handle))
 
     # ---- one record stream cut across several engines: the coverage statistic (bamqc_b200.h) ------------
-    def cov_defer(self, on=True):
-        self._check(self.lib.bqc_cov_defer(self.handle, 1 if on else 0))
+    def cov_defer(self, mode=1):
+        """1: a piece of a stream whose entry state is unknown; 2: the first piece of the stream; 0: stand-alone."""
+        self._check(self.lib.bqc_cov_defer(self.handle, int(mode)))
 
     def cov_shard_boundary(self):
         sh = _lib.bqc_cov_shard()

@@ -22,7 +22,7 @@ class Genome:
 
     @staticmethod
     def make(seed, names, lengths):
-        lib = _lib.load_library()
+        lib = _lib.load_synth()
         packed = []
         for i, n in enumerate(lengths):
             a = np.zeros((n + 31) // 32 * 8 + 16, dtype=np.uint8)
@@ -31,7 +31,7 @@ class Genome:
         return Genome(list(names), list(lengths), packed, seed)
 
     def write_fasta(self, path):
-        lib = _lib.load_library()
+        lib = _lib.load_synth()
         n = len(self.names)
         names = (ctypes.c_char_p * n)(*[s.encode() for s in self.names])
         lens = (ctypes.c_uint64 * n)(*self.lengths)
@@ -78,7 +78,7 @@ class Library:
 class _Params:
     def __init__(self, genome, lib_):
         self.c = _lib.bqc_synth_params()
-        L = _lib.load_library()
+        L = _lib.load_synth()
         L.bqc_synth_default_params(ctypes.byref(self.c))
         n = len(genome.names)
         self._names = (ctypes.c_char_p * n)(*[s.encode() for s in genome.names])
@@ -103,7 +103,7 @@ class _Params:
 
 def generate(genome, lib_):
     """Return (records uint8[n_bytes + 64 pad], offsets uint64[n_records+1]) -- coordinate-sorted inflated BAM records."""
-    L = _lib.load_library()
+    L = _lib.load_synth()
     p = _Params(genome, lib_)
     est_rec = int(lib_.n_pairs * 2.05) + 1024
     per = 4 + 32 + 12 + 40 + (lib_.read_len + 1) // 2 + lib_.read_len + 24
@@ -120,7 +120,7 @@ def generate(genome, lib_):
 
 
 def header_text(genome, lib_, sample_id="S1"):
-    L = _lib.load_library()
+    L = _lib.load_synth()
     p = _Params(genome, lib_)
     n = L.bqc_synth_header_text(ctypes.byref(p.c), sample_id.encode(), None, 0)
     buf = ctypes.create_string_buffer(n + 1)
@@ -130,14 +130,14 @@ def header_text(genome, lib_, sample_id="S1"):
 
 def write_bam(path, genome, lib_, records, n_bytes, sample_id="S1", level=-1):
     """level -1: raw uncompressed BAM stream; 0..9: BGZF."""
-    L = _lib.load_library()
+    L = _lib.load_synth()
     p = _Params(genome, lib_)
     if L.bqc_synth_write_bam(str(path).encode(), ctypes.byref(p.c), sample_id.encode(), records.ctypes.data, n_bytes, level):
         raise IOError(path)
 
 
 def bgzf_compress(data, level=1):
-    L = _lib.load_library()
+    L = _lib.load_synth()
     a = np.ascontiguousarray(data, dtype=np.uint8)
     out = np.zeros(int(a.size * 1.01) + (a.size // 0xff00 + 2) * 64 + 1024, dtype=np.uint8)
     n = L.bqc_synth_bgzf_compress(a.ctypes.data, a.size, level, out.ctypes.data, out.size)

@@ -166,7 +166,10 @@ typedef struct bqc_cov_shard {
     int32_t head[2001];          /* own depth (difference array) over the two windows open at its entry */
     int32_t tail[2001];          /* ... open at its end */
 } bqc_cov_shard;
-int bqc_cov_defer(bqc_engine* e, int on);   /* after bqc_reset, before the first submission */
+int bqc_cov_defer(bqc_engine* e, int on);   /* after bqc_reset, before the first submission.  1: a piece whose entry state is
+                                               unknown (records are collected, resolved in step 3); 2: the FIRST piece of the
+                                               stream (runs like a normal engine; only the end-of-run flush is left to step 4);
+                                               0: back to a stand-alone engine */
 int bqc_cov_shard_boundary(bqc_engine* e, bqc_cov_shard* out);
 int bqc_cov_shard_function(bqc_engine* e, int32_t have_prev, int32_t prev_rid, uint32_t prev_b, uint16_t* table1002);
 int bqc_cov_shard_run(bqc_engine* e, int32_t have_prev, int32_t prev_rid, uint32_t prev_b, uint32_t p_in, bqc_cov_shard* out);
