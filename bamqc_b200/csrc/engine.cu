@@ -208,7 +208,9 @@ struct bqc_engine {
     bool cstop = false, cbusy = false;
     int async_rc = 0;
     int tune_stats_bps = 0, tune_sketch_threads = 1024, tune_stats_stage = 1;  // BQC_STATS_STAGE=0: k_stats reads records straight from global memory (A/B tests)
-    int _pad_tune = 0;   // BQC_STATS_BPS / BQC_SKETCH_THREADS (tuning knobs)
+    int tune_sketch_v2 = 3;   // BQC_SKETCH_V2: 0 = k_sketch32 of round 1 (per-base ballot, pair table), 1/2/3/4 = k_sketch32v2 with
+                              // 1024/512/640/768 threads per CTA (64/88/86/80 registers).  Measured per 10 M cfg2 records (serialised):
+                              // 6.2 / 7.3 / 4.85 / 4.55 / 7.25 ms -- the restructured kernel needs ~86 registers to keep its loads in flight
     int tune_cov_bps = 6;                                // BQC_COV_BPS: k_cov_tiles CTAs per SM
     uint64_t records_seen = 0, frames_repaired = 0;
     std::atomic<uint64_t> launches{0};   // kernels launched (commit thread, anchor thread, caller)
@@ -433,6 +435,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     if (const char* v = getenv("BQC_HOST_FRAMING")) e->device_framing = atoi(v) == 0;
     if (const char* v = getenv("BQC_TRACE")) e->trace = atoi(v) != 0;
     if (const char* v = getenv("BQC_FRAME_FORCE_REPAIR")) e->force_bad_frames = atoi(v) != 0;
+    if (const char* v = getenv("BQC_SKETCH_V2")) e->tune_sketch_v2 = atoi(v);
     if (const char* v = getenv("BQC_SKETCH_THREADS")) e->tune_sketch_threads = std::max(32, std::min(1024, atoi(v) & ~31));
     e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     if (e->host_threads > 1) e->pool.reset(new HostPool(e->host_threads - 1));
@@ -485,6 +488,10 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         CU(cudaFuncSetAttribute(k_cov_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCovBlockSmem));
         CU(cudaFuncSetAttribute(k_cov_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCovCodesSmem));
         CU(cudaFuncSetAttribute(k_sketch32, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024 + (int)sizeof(HashPairTable) + (int)(kSketchThreads / 32 * kSketchQueue * 8)));
+        CU(cudaFuncSetAttribute(k_sketch32v2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sketch32v2_smem(32768u, 1024)));
+        CU(cudaFuncSetAttribute(k_sketch32v2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sketch32v2_smem(32768u, 512)));
+        CU(cudaFuncSetAttribute(k_sketch32v2<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sketch32v2_smem(32768u, 640)));
+        CU(cudaFuncSetAttribute(k_sketch32v2<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sketch32v2_smem(32768u, 768)));
         return 0;
     }();
     if (rc) { g_last_error = e->last_error; bqc_destroy(e); return rc; }
@@ -919,7 +926,14 @@ static int launch_tables(bqc_engine* e, const DeviceBatch& d, const BatchLaunch&
                 SP.qk = qi * (uint32_t)e->klist.size() + ki;
                 int gs = (int)std::min<uint64_t>((n + kSketchThreads - 1) / kSketchThreads, (uint64_t)e->n_sm);
                 ProfScope prof(e, 2);
-                if (SP.k == 32u && e->L.f2size <= 32768u)
+                if (SP.k == 32u && e->L.f2size <= 32768u && e->tune_sketch_v2 && SP.q_thresh >= 33 && SP.q_thresh <= 127)
+                {
+                    if (e->tune_sketch_v2 == 2) k_sketch32v2<512><<<(int)std::min<uint64_t>((n + 511) / 512, (uint64_t)e->n_sm), 512, sketch32v2_smem(e->L.f2size, 512), e->compute>>>(E, B, lane, SP, e->d_hash + ki);
+                    else if (e->tune_sketch_v2 == 3) k_sketch32v2<640><<<(int)std::min<uint64_t>((n + 639) / 640, (uint64_t)e->n_sm), 640, sketch32v2_smem(e->L.f2size, 640), e->compute>>>(E, B, lane, SP, e->d_hash + ki);
+                    else if (e->tune_sketch_v2 == 4) k_sketch32v2<768><<<(int)std::min<uint64_t>((n + 767) / 768, (uint64_t)e->n_sm), 768, sketch32v2_smem(e->L.f2size, 768), e->compute>>>(E, B, lane, SP, e->d_hash + ki);
+                    else k_sketch32v2<1024><<<gs, 1024, sketch32v2_smem(e->L.f2size, 1024), e->compute>>>(E, B, lane, SP, e->d_hash + ki);
+                }
+                else if (SP.k == 32u && e->L.f2size <= 32768u)
                     k_sketch32<<<gs, e->tune_sketch_threads, e->L.f2size * 4 + sizeof(HashPairTable) + kSketchThreads / 32 * kSketchQueue * 8, e->compute>>>(E, B, lane, SP, e->d_hash + ki);
                 else if (e->L.f2size <= 32768u)
                     k_sketch<true><<<gs, kSketchThreads, e->L.f2size * 4, e->compute>>>(E, B, lane, SP, e->d_hash + ki);

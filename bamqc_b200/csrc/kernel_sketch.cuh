@@ -177,4 +177,191 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, Ba
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_sketch32v2 -- same arithmetic, restructured around what ncu showed in k_sketch32 (profiles/r1, profiles/r2):
+//   * one __ballot_sync per base for the queue append, an `i < Ls` guard around every base and a signed-char quality
+//     test + run counter in front of it (56 of ~80 warp instructions per base);
+//   * the (in, out) pair table: a warp's lanes read different 32-byte rows that fall on the same banks -- 14 shared
+//     memory wavefronts per 16-byte load where 4 are the minimum, i.e. the LSU pipe busy half of the kernel's time
+//     and every hash step waiting ~3x longer for its row.
+// Here a read is processed in sub-chunks of 8 bases in two passes:
+//   pass 1  validity of the 8 bases (quality in [q, 94] as one unsigned range test, base != N; bases past the end of
+//           the read get quality 255) shifted into a 32-bit history: a base ends a window iff the history is all ones
+//           -> 8 emit bits; ONE warp prefix sum of the emit counts gives every lane its place in the warp's hash queue;
+//   pass 2  the 8 hash updates, unconditional; an emitted hash is one predicated 8-byte store at the lane's next slot.
+// The hash tables are split by linearity -- row(in, out) = row_in(in) ^ row_out(out) -- into two 16-row tables that
+// are REPLICATED across the banks: a row holds 8 copies of its 16-byte part and 16 copies of its 8-byte part, lane l
+// reads copy l mod 8 (l mod 16), so the lanes of a quarter (half) warp never share a bank whatever they look up:
+// 4 + 4 + 2 wavefronts per base instead of ~28.  The first 32 bases of a read look up an all-zero `out` table.
+// Then the warp probes the sketch for 32 queued hashes at a time with every lane busy, as before.  Taken when the
+// quality threshold is an ordinary one ((char)(33 + q) in 33..127); k_sketch32 stays for the others.
+// ------------------------------------------------------------------------------------------------
+static const uint32_t kSketchSub = 8;                                  // bases per sub-chunk
+static const uint32_t kSketchQueue2 = 31 + 32 * kSketchSub + 1;        // queue entries per warp: leftover + one sub-chunk of every lane
+// shared memory: [F2 table][in tables: 2 strands x 16 rows x 256 B][out tables: 2 strands x 16 rows x 128 B][zero: 16 x 128 B][queues]
+static const uint32_t kSkIn = 2 * 16 * 256, kSkOut = 2 * 16 * 128, kSkZero = 16 * 128;
+__host__ __device__ inline uint32_t sketch32v2_smem(uint32_t f2size, uint32_t threads) { return f2size * 4u + kSkIn + kSkOut + kSkZero + (threads / 32u) * kSketchQueue2 * 8u; }
+
+// exclusive prefix sum over the warp of a count in 0..8 without a dependent shuffle chain: one ballot per bit
+__device__ __forceinline__ uint32_t warp_prefix_small(uint32_t cnt, uint32_t lt_mask, uint32_t& total) {
+    const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, cnt & 1u), b1 = __ballot_sync(0xFFFFFFFFu, cnt & 2u);
+    const uint32_t b2 = __ballot_sync(0xFFFFFFFFu, cnt & 4u), b3 = __ballot_sync(0xFFFFFFFFu, cnt & 8u);
+    total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2) + 8u * __popc(b3);
+    return __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask) + 4u * __popc(b2 & lt_mask) + 8u * __popc(b3 & lt_mask);
+}
+
+template <uint32_t THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_sketch32v2(EngineView E, BatchView B, uint32_t lane, SketchParams SP, const HashTables* __restrict__ HT) {
+    extern __shared__ __align__(16) uint32_t sm[];
+    const Layout& L = E.L;
+    uint8_t* tin = reinterpret_cast<uint8_t*>(sm + L.f2size);
+    uint8_t* tout = tin + kSkIn;
+    uint8_t* tzero = tout + kSkOut;
+    uint64_t* queue = reinterpret_cast<uint64_t*>(tzero + kSkZero) + (threadIdx.x >> 5) * kSketchQueue2;
+    for (uint32_t i = threadIdx.x; i < L.f2size; i += blockDim.x) sm[i] = 0;
+    // in row (strand s, nibble n): copies of {a_lo = H[in].lo, b_lo = rotl_k(Ht''[in]).lo} then of {a_hi, b_hi} (see k_sketch32);
+    // out row: copies of {rotl_k(H[out]).lo, Ht[out].lo}
+    for (uint32_t i = threadIdx.x; i < 2 * 16 * 8; i += blockDim.x) {
+        const uint32_t s = i / 128, n = (i / 8) % 16, c = i % 8;
+        uint64_t* pi = reinterpret_cast<uint64_t*>(tin + (s * 16 + n) * 256 + c * 16);
+        pi[0] = HT->t[s][0][n][1];
+        pi[1] = HT->t[s][2][n][1] & ~1ULL;
+        uint64_t* po = reinterpret_cast<uint64_t*>(tout + (s * 16 + n) * 128 + c * 16);
+        po[0] = HT->t[s][1][n][1];
+        po[1] = HT->t[s][3][n][1];
+    }
+    for (uint32_t i = threadIdx.x; i < 2 * 16 * 16; i += blockDim.x) {
+        const uint32_t s = i / 256, n = (i / 16) % 16, c = i % 16;
+        uint32_t* ph = reinterpret_cast<uint32_t*>(tin + (s * 16 + n) * 256 + 128 + c * 8);
+        ph[0] = (uint32_t)(HT->t[s][0][n][0] >> 32);
+        ph[1] = (uint32_t)HT->t[s][2][n][0];
+    }
+    for (uint32_t i = threadIdx.x; i < kSkZero / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tzero)[i] = 0;
+    __syncthreads();
+    uint64_t* G = E.counters + (uint64_t)lane * L.lane_stride + L.o_qk + (uint64_t)SP.qk * L.qk_stride;
+    uint32_t* sk = E.sketch + ((uint64_t)lane * L.n_qk + SP.qk) * 32ull * (L.sk_size * 2ull);
+    const uint32_t words_per_level = L.sk_size * 2u;
+    const uint64_t idx_mask = (uint64_t)L.sk_size * 16ull - 1ull;
+    const uint32_t f2mask = L.f2size - 1u;
+    // valid(q) <=> (signed char)(q + 33) >= (signed char)thr with thr in 33..127  <=>  thr - 33 <= q <= 94
+    const uint32_t q_lo_ok = (uint32_t)SP.q_thresh - 33u, q_span = 94u - q_lo_ok;
+    unsigned long long warp_count = 0;               // k-mers hashed by this warp (same value in every lane)
+    const uint32_t lane_id = threadIdx.x & 31u;
+    const uint32_t sm_in = (uint32_t)__cvta_generic_to_shared(tin), sm_out = (uint32_t)__cvta_generic_to_shared(tout);
+    const uint32_t zero_lo = (uint32_t)__cvta_generic_to_shared(tzero) + (lane_id & 7u) * 16u;
+    const uint32_t lt_mask = (1u << lane_id) - 1u;
+    const uint32_t queue_s = (uint32_t)__cvta_generic_to_shared(queue);
+    uint32_t qn = 0;                                 // queued hashes of this warp (uniform, < 32 between sub-chunks)
+    SketchProbe probe = {kNone, 0u, 0u};
+
+    auto probe_issue = [&](uint64_t hv) {            // StreamCounter::operator() (src/kmerstream/StreamCounter.hpp:67-93)
+        probe.finish(sk);
+        atomicAdd(sm + ((uint32_t)hv & f2mask), 1u);
+        uint32_t w = hv ? (uint32_t)(__ffsll((long long)hv) - 1) : 63u;  // bitScanForward, 63 for 0
+        if (w > 31u) w = 31u;
+        const uint64_t index = (hv >> (w + 1u)) & idx_mask;
+        probe.word = w * words_per_level + (uint32_t)(index >> 3);
+        probe.sh = ((uint32_t)index & 7u) * 4u;
+        probe.old = __ldcg(sk + probe.word);
+    };
+
+    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < B.n_records; r0 += gridDim.x * blockDim.x) {
+        const uint32_t rec = r0 + lane_id;
+        RecHdr h;
+        bool act = rec < B.n_records && !(B.rec_lane && B.rec_lane[rec] != lane);
+        if (act) {
+            const uint32_t off = B.offsets[rec];
+            act = decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h);
+        }
+        act = act && !(h.flag & 0xF00u) && (h.flag & 0xC0u) && (uint32_t)h.lseq >= 32u;
+        const uint32_t Ls = act ? (uint32_t)h.lseq : 0u;
+        const uint32_t maxL = __reduce_max_sync(0xFFFFFFFFu, Ls);
+        const uint32_t s = act ? ((h.flag >> 4) & 1u) : 0u;
+        const uint8_t* seqp = act ? h.p + h.o_seq : B.bytes;
+        const uint8_t* qualp = act ? h.p + h.o_qual : B.bytes;
+        // this lane's copies: the row offset (nibble << 8, nibble << 7) is added to these shared-memory addresses
+        const uint32_t in_lo = sm_in + s * 4096u + (lane_id & 7u) * 16u, in_hi = sm_in + s * 4096u + 128u + (lane_id & 15u) * 8u;
+        const uint32_t out_lo = sm_out + s * 2048u + (lane_id & 7u) * 16u;
+        uint64_t hlo = 0, tlo = 0;
+        uint32_t hhi = 0, thi = 0;                    // top 32 bits of h.hi, low 32 bits of ht.hi
+        uint32_t seq_cur = ldu32(seqp), seq_next = ldu32(seqp + 4);   // 8 bases each; loads run two sub-chunks ahead
+        uint64_t q_cur = ldu64(qualp), q_next = ldu64(qualp + 8);
+        uint32_t lag0 = 0, lag1 = 0, lag2 = 0, lag3 = 0;  // SEQ words of the last 4 sub-chunks, oldest first (the base leaving a 32-window sits 4 words back)
+        uint32_t vh = 0;                              // validity of the last 32 bases, newest in bit 0
+        const uint32_t nsub = (maxL + kSketchSub - 1u) / kSketchSub;
+        for (uint32_t c = 0; c < nsub; ++c) {
+            const uint32_t seq_next2 = ldu32(seqp + 4u * (c + 2u));         // reads past a short record stay inside the padded batch
+            const uint64_t q_next2 = ldu64(qualp + 8u * (c + 2u));
+            // ---- pass 1: which of the 8 bases end a window of 32 valid bases
+            const uint32_t left = Ls > 8u * c ? Ls - 8u * c : 0u;           // bases of the read from here on
+            if (left < 8u) q_cur |= ~0ULL << (8u * left);                   // past the end: quality 255 = not valid
+            uint32_t emit = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {
+                const uint32_t nin = (seq_cur >> (4u * (j ^ 1u))) & 15u;
+                const uint32_t q = (uint32_t)(q_cur >> (8u * j)) & 255u;
+                const bool valid = (q - q_lo_ok) <= q_span && nin != 15u;
+                vh += vh;
+                if (valid) vh |= 1u;
+                if (vh == 0xFFFFFFFFu) emit |= 1u << j;
+            }
+            uint32_t total;
+            const uint32_t excl = warp_prefix_small(__popc(emit), lt_mask, total);
+            uint32_t qp = queue_s + 8u * (qn + excl);                       // this lane's next queue slot
+            // ---- pass 2: the hash updates; h = rotl1(h) ^ H[in] ^ rotl_k(H[out]), ht = rotr1(ht ^ rotl_k(Ht[in]) ^ Ht[out])
+            const uint32_t outw = lag0;
+            const uint32_t o_base = c >= 4u ? out_lo : zero_lo;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {
+                const uint32_t sh = 4u * (j ^ 1u);
+                const uint32_t ni = sh >= 8u ? (seq_cur >> (sh - 8u)) & 0xF00u : (seq_cur << (8u - sh)) & 0xF00u;   // nibble << 8
+                const uint32_t no = sh >= 7u ? (outw >> (sh - 7u)) & 0x780u : (outw << (7u - sh)) & 0x780u;         // nibble << 7
+                uint64_t a_lo, b_lo, oa_lo, ob_lo;
+                uint32_t a_hi, b_hi;
+                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a_lo), "=l"(b_lo) : "r"(in_lo + ni));
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a_hi), "=r"(b_hi) : "r"(in_hi + ni));
+                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(oa_lo), "=l"(ob_lo) : "r"(o_base + no));
+                hlo = ((hlo << 1) | (uint64_t)(hhi >> 31)) ^ a_lo ^ oa_lo;
+                hhi = (hhi << 1) ^ a_hi;
+                const uint64_t xl = tlo ^ b_lo ^ ob_lo;
+                const uint32_t xh = thi ^ b_hi;
+                tlo = (xl >> 1) | ((uint64_t)xh << 63);
+                thi = xh >> 1;
+                if ((emit >> j) & 1u) {
+                    const uint64_t hv = hlo ^ tlo;
+                    asm volatile("st.shared.u64 [%0], %1;" ::"r"(qp), "l"(hv) : "memory");
+                    qp += 8u;
+                }
+            }
+            lag0 = lag1; lag1 = lag2; lag2 = lag3; lag3 = seq_cur;
+            seq_cur = seq_next; seq_next = seq_next2;
+            q_cur = q_next; q_next = q_next2;
+            if (total) {  // warp-uniform
+                __syncwarp();
+                warp_count += total;
+                const uint32_t have = qn + total;
+                uint32_t done = 0;
+                for (; done + 32u <= have; done += 32u) probe_issue(queue[done + lane_id]);
+                const uint32_t rest = have - done;
+                if (done && rest) {                                         // what is left moves to the front of the queue
+                    const uint64_t v = lane_id < rest ? queue[done + lane_id] : 0ull;
+                    __syncwarp();
+                    if (lane_id < rest) queue[lane_id] = v;
+                }
+                qn = rest;
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    if (lane_id < qn) probe_issue(queue[lane_id]);  // what is left in the queue
+    probe.finish(sk);
+    if (lane_id == 0 && warp_count) atomicAdd((unsigned long long*)G, warp_count);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < L.f2size; i += blockDim.x) {
+        uint32_t v = sm[i];
+        if (v) atomicAdd((unsigned long long*)(G + 8 + i), (unsigned long long)v);
+    }
+}
+
 }  // namespace bqc
