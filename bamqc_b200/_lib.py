@@ -87,6 +87,8 @@ PROTOTYPES = {
     "bqc_submit": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, _u64]),
     "bqc_submit_stream": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_int]),
     "bqc_submit_bgzf": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]),
+    "bqc_stream_unknown_start": (ctypes.c_int, [_vp]),
+    "bqc_stream_skipped": (ctypes.c_int, [_vp, _P(_u64)]),
     "bqc_frames_repaired": (_u64, [_vp]),
     "bqc_records_seen": (_u64, [_vp]),
     "bqc_batch_prepare": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, _u64, _P(_vp)]),

@@ -193,10 +193,13 @@ struct bqc_engine {
         int mode;          // 0: framed by the host (offsets + meta in the slot), 1: raw stream bytes, framed on the device,
                            // 2: BGZF blocks, inflated and framed on the device
         uint32_t n_blocks = 0, inflated = 0, skip = 0;  // mode 2: BGZF blocks, their total inflated size, leading non-record bytes
+        bool seek = false;  // the stream starts inside a record: find the first record boundary (k_frame_seek)
         bool must_align;   // the bytes must end on a record boundary (whole-record submissions, last stream chunk)
     };
     std::deque<Task> ingest;       // stream tasks whose H2D copy + framing kernels are enqueued, not yet launched
     int last_stream_slot = -1;     // slot of the previous stream submission (source of the carried partial record)
+    bool stream_seek = false;      // bqc_stream_unknown_start: the next stream submission starts inside a record
+    std::atomic<int64_t> stream_skipped{-1};   // bytes in front of the first record boundary that was found (-1: not known yet)
     bool device_framing = true;    // BQC_HOST_FRAMING=1 turns it off (A/B tests)
     bool trace = false;            // BQC_TRACE=1: per-buffer timings of the commit thread on stderr
     bool force_bad_frames = false; // BQC_FRAME_FORCE_REPAIR=1: every speculation is treated as failed (tests the repair path)
@@ -353,8 +356,10 @@ extern "C" const char* bqc_last_error(bqc_engine* e) { return e ? e->last_error.
 
 static int alloc_device_batch(bqc_engine* e, DeviceBatch& d, uint64_t bytes_cap, uint64_t rec_cap) {
     d.owns = true;
-    CU(cudaMalloc(&d.bytes, kFrameHead + bytes_cap + 256));
-    CU(cudaMemset(d.bytes, 0, kFrameHead + bytes_cap + 256));
+    // head room in front (a carried partial record) and the same slack behind: the host-framed stream path puts the
+    // carried bytes in front of a full chunk and copies both to bytes + kFrameHead
+    CU(cudaMalloc(&d.bytes, kFrameHead + bytes_cap + kFrameHead + 256));
+    CU(cudaMemset(d.bytes, 0, kFrameHead + bytes_cap + kFrameHead + 256));
     d.base = d.bytes + kFrameHead;
     CU(cudaMalloc(&d.offsets, (rec_cap + 1) * sizeof(uint32_t)));
     if (e->n_lanes > 1) CU(cudaMalloc(&d.rec_lane, rec_cap + 1));
@@ -371,6 +376,8 @@ extern "C" int bqc_reset(bqc_engine* e) {
     CU(cudaStreamSynchronize(e->covs));
     CU(cudaStreamSynchronize(e->frames));
     e->last_stream_slot = -1;
+    e->stream_seek = false;
+    e->stream_skipped = -1;
     e->host_carry.clear();
     CU(cudaMemsetAsync(e->d_counters, 0, e->n_lanes * e->L.lane_stride * 8, e->compute));
     CU(cudaMemsetAsync(e->d_sketch, 0, e->n_lanes * e->n_qk * e->sketch_words_per_qk * 4, e->compute));
@@ -1040,6 +1047,7 @@ static int stream_stage_a(bqc_engine* e, const bqc_engine::Task& t) {
         CU(cudaStreamWaitEvent(e->frames, e->copied, 0));
     }
     ProfScope prof_frame(e, 9, e->frames);
+    if (t.seek) { k_frame_seek<<<1, 256, 0, e->frames>>>(d.bytes, s.d_frame, std::max(1, e->cfg.n_ref)); e->launches += 1; }
     const uint32_t nwin = (uint32_t)((kFrameHead + (uint64_t)n_new + kFrameWindow - 1) / kFrameWindow);
     const uint32_t nblk = (nwin + kFrameThreads - 1) / kFrameThreads;
     const uint32_t rec_cap = (uint32_t)e->max_records_per_slot;
@@ -1090,6 +1098,7 @@ static int stream_stage_b(bqc_engine* e, const bqc_engine::Task& t) {
         return BQC_ERR_BAD_RECORD;
     }
     if (fr.repaired) e->frames_repaired += 1;
+    if (t.seek) e->stream_skipped = (int64_t)fr.start - (int64_t)kFrameHead - (int64_t)t.skip;
     const uint64_t n = fr.n_records;
     d.max_lseq = fr.max_lseq;
     d.n_records = n;
@@ -1265,6 +1274,8 @@ static int submit_common(bqc_engine* e, const void* data, size_t n_bytes, const 
         t.n_records = 0;
         t.max_lseq = 0;
         t.mode = 1;
+        t.seek = e->stream_seek;
+        e->stream_seek = false;
         t.must_align = !stream || last;
         t.span = n_bytes;
         t.h2d_src = n_bytes ? h2d_source(e, s, src, n_bytes) : s.pinned + kFrameHead;
@@ -1374,6 +1385,8 @@ extern "C" int bqc_submit_bgzf(bqc_engine* e, const void* data, size_t n_bytes, 
             t.n_records = 0;
             t.max_lseq = 0;
             t.mode = 2;
+            t.seek = e->stream_seek;
+            e->stream_seek = false;
             t.must_align = final_chunk;
             t.span = (size_t)used;
             t.n_blocks = nb;
@@ -1384,7 +1397,13 @@ extern "C" int bqc_submit_bgzf(bqc_engine* e, const void* data, size_t n_bytes, 
         } else {
             // several read groups / BQC_HOST_FRAMING=1: zlib on the host threads, then the host-framed stream path
             uint8_t* buf = s.pinned + kFrameHead;
-            if (inflated && bqc_bgzf_inflate(src + p, used, buf, e->staging_bytes, e->host_threads) != inflated) {
+            const uint8_t* cin = src + p;
+            std::vector<uint8_t> moved;
+            if (cin < s.pinned + kFrameHead + e->staging_bytes + 256 && cin + used > s.pinned) {  // the caller filled this very staging buffer
+                moved.assign(cin, cin + used);
+                cin = moved.data();
+            }
+            if (inflated && bqc_bgzf_inflate(cin, used, buf, e->staging_bytes, e->host_threads) != inflated) {
                 e->host_error.code = BQC_ERR_BAD_RECORD;
                 e->host_error.record = e->records_seen;
                 snprintf(e->host_error.message, sizeof(e->host_error.message), "ERROR: Could not read record from BAM File (BGZF block does not inflate)");
@@ -1401,6 +1420,19 @@ extern "C" int bqc_submit_bgzf(bqc_engine* e, const void* data, size_t n_bytes, 
     return 0;
 }
 
+extern "C" int bqc_stream_unknown_start(bqc_engine* e) {
+    if (!(e->device_framing && e->n_lanes == 1)) { set_error(e, "bqc_stream_unknown_start needs device framing (single read group)"); return BQC_ERR_ARG; }
+    if (e->records_seen || e->last_stream_slot >= 0) { set_error(e, "bqc_stream_unknown_start: call it before the first submission"); return BQC_ERR_ARG; }
+    e->stream_seek = true;
+    e->stream_skipped = -1;
+    return 0;
+}
+extern "C" int bqc_stream_skipped(bqc_engine* e, uint64_t* skipped) {
+    const int64_t v = e->stream_skipped.load();
+    if (v < 0) return e->async_rc ? e->async_rc : -1;   // -1: the first submission has not been framed yet (poll again)
+    *skipped = (uint64_t)v;
+    return 0;
+}
 extern "C" uint64_t bqc_frames_repaired(bqc_engine* e) { drain_commits(e); return e->frames_repaired; }
 extern "C" uint64_t bqc_records_seen(bqc_engine* e) { drain_commits(e); return e->records_seen; }
 

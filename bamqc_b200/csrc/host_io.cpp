@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <map>
 #include <set>
@@ -489,20 +490,11 @@ struct Cli {
     std::vector<int32_t> klist;
     std::vector<uint64_t> qlist;
     double e = 0.01;
-    int seed = 1, isize = 1000, device = 0, threads = 0;
+    int seed = 1, isize = 1000, threads = 0, max_read_len = 0;
+    std::vector<int> devices = {0};
+    uint64_t staging_mb = 0;
     bool timing = false;
 };
-bool read_file(const std::string& path, std::vector<uint8_t>& out) {
-    FILE* f = fopen(path.c_str(), "rb");
-    if (!f) return false;
-    fseek(f, 0, SEEK_END);
-    long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    out.resize((size_t)n);
-    size_t got = n ? fread(out.data(), 1, (size_t)n, f) : 0;
-    fclose(f);
-    return got == (size_t)n;
-}
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -659,6 +651,486 @@ bool sam_line_to_bam(const std::string& line, const std::map<std::string, int32_
 }
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// the command: helpers shared by the SAM and the file path
+// ------------------------------------------------------------------------------------------------
+namespace {
+typedef std::chrono::steady_clock::time_point TimePoint;
+
+bool probe_output(const Cli& c) {
+    std::ofstream probe(c.out.c_str(), std::ios::out | std::ios::binary);
+    if (!probe.good()) {
+        std::cerr << "ERROR: Could not open output file " << c.out << '\n';
+        return false;
+    }
+    return true;
+}
+
+int report_submit_error(bqc_engine* eng, const Cli& c) {
+    bqc_error_info ei;
+    bqc_get_error(eng, &ei);
+    if (ei.code == BQC_ERR_BAD_RECORD) std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
+    else std::cerr << "ERROR: " << bqc_last_error(eng) << std::endl;
+    return 1;
+}
+
+// the reference's messages for the fatal records (src/bamqualcheck.cpp:91,308,387; src/TripletCounting.hpp:116-127)
+int report_finish_error(bqc_engine* eng, const Cli& c) {
+    bqc_error_info ei;
+    bqc_get_error(eng, &ei);
+    if (ei.code == BQC_ERR_RG_NOT_Z) std::cout << "Read does not have Z" << "\n";
+    else if (ei.code == BQC_ERR_BAD_RECORD) std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
+    else if (ei.code == BQC_ERR_NO_MATE_FLAG) std::cerr << "ERROR: No first or second flag in read in:  " << c.bam << "\n";
+    else std::cerr << (ei.code ? ei.message : bqc_last_error(eng)) << std::endl;
+    return ei.code ? ei.code : 1;
+}
+
+bqc_engine* make_engine(const Cli& c, const bqc_bam_header& hdr, int device, std::vector<uint8_t>& main_chrom) {
+    main_chrom.assign((size_t)std::max(1, hdr.n_ref), 0);
+    {   // initChroms (src/bamqualcheck.cpp:106-123): the -c names that exist in the BAM header
+        std::istringstream cs(c.chroms);
+        std::string name;
+        while (std::getline(cs, name, ','))
+            for (int i = 0; i < hdr.n_ref; ++i)
+                if (name == hdr.ref_names[i]) { main_chrom[i] = 1; break; }
+    }
+    if (hdr.n_lanes == 0) {
+        std::cerr << "ERROR: BAM header declares no read group (@RG); bamqualcheck needs at least one.\n";
+        return nullptr;
+    }
+    bqc_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.device = device;
+    cfg.isize = c.isize;
+    cfg.n_lanes = hdr.n_lanes;
+    cfg.lane_ids = hdr.lane_ids;
+    cfg.n_ref = hdr.n_ref;
+    cfg.main_chrom = main_chrom.data();
+    cfg.n_k = (int32_t)c.klist.size();
+    cfg.klist = c.klist.data();
+    cfg.n_q = (int32_t)c.qlist.size();
+    cfg.q_cutoff = c.qlist.data();
+    cfg.q_base = 33;
+    cfg.e = c.e;
+    cfg.seed = c.seed;
+    cfg.max_read_len = c.max_read_len;
+    cfg.staging_bytes = c.staging_mb << 20;
+    cfg.host_threads = c.threads;
+    bqc_engine* eng = nullptr;
+    if (bqc_create(&cfg, &eng)) {
+        std::cerr << "ERROR: " << bqc_last_error(nullptr) << std::endl;
+        return nullptr;
+    }
+    return eng;
+}
+
+// reference genome: every BAM reference that the FASTA holds goes to HBM
+bool load_reference(bqc_engine* eng, bqc_fasta* fa, const bqc_bam_header& hdr) {
+    for (int i = 0; i < hdr.n_ref; ++i) {
+        const uint8_t* packed = nullptr;
+        int64_t len = bqc_fasta_contig(fa, hdr.ref_names[i], &packed);
+        if (len >= 0 && bqc_set_reference(eng, i, packed, (uint64_t)len)) {
+            std::cerr << "ERROR: " << bqc_last_error(eng) << std::endl;
+            return false;
+        }
+    }
+    return true;
+}
+
+// ---- streaming file input ----------------------------------------------------------------------------------
+struct RangeReader {  // sequential pread over [pos, end) of a file (end == ~0: to the end of the file / pipe)
+    int fd = -1;
+    bool seekable = true;
+    uint64_t pos = 0, end = ~0ull;
+    size_t read(uint8_t* buf, size_t n) {
+        size_t got = 0;
+        while (got < n && pos < end) {
+            const size_t want = (size_t)std::min<uint64_t>(n - got, end - pos);
+            const ssize_t r = seekable ? pread(fd, buf + got, want, (off_t)pos) : ::read(fd, buf + got, want);
+            if (r <= 0) break;
+            got += (size_t)r;
+            pos += (uint64_t)r;
+        }
+        return got;
+    }
+};
+
+// whole BGZF blocks at the front of buf[0..n): bytes and inflated size, stopping before `max_out` inflated bytes are
+// exceeded; bad = not a BGZF block header (SAM/BAM specification 4.1)
+size_t bgzf_whole_prefix(const uint8_t* buf, size_t n, uint64_t max_out, uint64_t& inflated, bool& bad) {
+    size_t p = 0;
+    inflated = 0;
+    bad = false;
+    while (p + 18 <= n) {
+        if (buf[p] != 0x1f || buf[p + 1] != 0x8b || buf[p + 2] != 8 || !(buf[p + 3] & 4)) { bad = true; break; }
+        const uint32_t xlen = buf[p + 10] | (buf[p + 11] << 8);
+        if (p + 12 + xlen > n) break;
+        size_t x = p + 12, xend = x + xlen;
+        int bsize = -1;
+        while (x + 4 <= xend) {
+            const uint32_t slen = buf[x + 2] | (buf[x + 3] << 8);
+            if (buf[x] == 'B' && buf[x + 1] == 'C' && slen == 2 && x + 6 <= xend) bsize = buf[x + 4] | (buf[x + 5] << 8);
+            x += 4 + slen;
+        }
+        if (bsize < 0) { bad = true; break; }
+        const size_t blen = (size_t)bsize + 1;
+        if (p + blen > n) break;
+        uint32_t isize;
+        memcpy(&isize, buf + p + blen - 4, 4);
+        if (isize > 65536u) { bad = true; break; }
+        if (inflated + isize > max_out) break;
+        inflated += isize;
+        p += blen;
+    }
+    return p;
+}
+
+// A BGZF block boundary at or after `from`: the 16-byte member header with the BC subfield, confirmed by three hops.
+// Returns ~0 if none is found within 1 MiB (then the file is not cut there).
+uint64_t find_bgzf_block(int fd, uint64_t from, uint64_t file_size) {
+    std::vector<uint8_t> buf((size_t)std::min<uint64_t>(file_size - from, (1u << 20) + (4u << 16)));
+    RangeReader rr;
+    rr.fd = fd; rr.pos = from; rr.end = file_size;
+    const size_t n = rr.read(buf.data(), buf.size());
+    for (size_t p = 0; p + 18 <= n && p < (1u << 20); ++p) {
+        size_t q = p;
+        int hops = 0;
+        while (hops < 4 && q + 18 <= n) {
+            if (!(buf[q] == 0x1f && buf[q + 1] == 0x8b && buf[q + 2] == 8 && buf[q + 3] == 4 && buf[q + 10] == 6 && buf[q + 11] == 0 && buf[q + 12] == 'B' &&
+                  buf[q + 13] == 'C' && buf[q + 14] == 2 && buf[q + 15] == 0))
+                break;
+            q += (size_t)(buf[q + 16] | (buf[q + 17] << 8)) + 1;
+            ++hops;
+        }
+        if (hops == 4 || (hops >= 1 && from + q == file_size)) return from + p;
+    }
+    return ~0ull;
+}
+
+struct Piece {  // one engine and the byte range of the file it reads
+    bqc_engine* eng = nullptr;
+    std::vector<uint8_t> main_chrom;
+    uint64_t beg = 0, end = 0;
+    size_t skip = 0;           // piece 0: inflated bytes of the BAM header in its first block
+    std::atomic<int> rc{0};
+    Piece() {}
+    Piece(const Piece&) {}
+};
+
+// Piece k of a BGZF file: whole blocks go to the device as they are.  Pieces after the first begin inside a record:
+// the engine finds the first record boundary, the bytes in front of it are inflated here and handed to the piece
+// before (get_head), whose last record they complete.
+int stream_bgzf_piece(const Cli& c, int fd, Piece& P, bool unknown_start, bool is_last, const std::function<bool(std::vector<uint8_t>&)>& get_next_head) {
+    bqc_engine* eng = P.eng;
+    if (unknown_start && bqc_stream_unknown_start(eng)) return report_submit_error(eng, c);
+    RangeReader rr;
+    rr.fd = fd; rr.pos = P.beg; rr.end = P.end;
+    std::vector<uint8_t> carry;
+    size_t skip = P.skip;
+    bool eof = false, any = false;
+    while (!eof || !carry.empty() || !any) {
+        void* pin;
+        size_t cap;
+        if (bqc_acquire_staging(eng, &pin, &cap)) return report_submit_error(eng, c);
+        uint8_t* buf = (uint8_t*)pin;
+        size_t filled = carry.size();
+        memcpy(buf, carry.data(), filled);
+        carry.clear();
+        const size_t target = std::max<size_t>(1u << 20, cap / 4);   // ~4x compression: the inflated bytes have to fit the same buffer
+        if (!eof && filled < target) {
+            const size_t got = rr.read(buf + filled, target - filled);
+            if (got < target - filled) eof = true;
+            filled += got;
+        }
+        uint64_t inflated = 0;
+        bool bad = false;
+        const size_t used = bgzf_whole_prefix(buf, filled, cap, inflated, bad);
+        if (bad || (used == 0 && filled > 0 && (eof || filled >= target))) {
+            std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
+            return 1;
+        }
+        carry.assign(buf + used, buf + filled);
+        const bool final_chunk = eof && carry.empty();
+        if (used || final_chunk) {
+            if (bqc_submit_bgzf(eng, buf, used, skip, (final_chunk && is_last) ? 1 : 0)) return report_submit_error(eng, c);
+            skip = 0;
+            any = true;
+        }
+        if (final_chunk) break;
+    }
+    if (!is_last) {  // the end of this piece's last record lies in the next piece
+        std::vector<uint8_t> head;
+        if (!get_next_head(head)) return 1;
+        if (bqc_submit_stream(eng, head.empty() ? nullptr : head.data(), head.size(), 1)) return report_submit_error(eng, c);
+    }
+    return 0;
+}
+
+// the first `want` inflated bytes of the BGZF stream that starts at file offset `from`
+bool inflate_head(int fd, uint64_t from, uint64_t file_size, uint64_t want, std::vector<uint8_t>& out) {
+    out.clear();
+    if (!want) return true;
+    std::vector<uint8_t> buf((size_t)std::min<uint64_t>(file_size - from, want + (4u << 20)));
+    RangeReader rr;
+    rr.fd = fd; rr.pos = from; rr.end = file_size;
+    const size_t n = rr.read(buf.data(), buf.size());
+    std::vector<BgzfBlock> blocks;
+    bool bad = false;
+    bgzf_index(buf.data(), n, blocks, ~0ull, bad);
+    if (bad || blocks.empty()) return false;
+    size_t nb = 0;
+    while (nb < blocks.size() && blocks[nb].obeg < want) ++nb;
+    blocks.resize(nb);
+    if (blocks.empty() || blocks.back().obeg + blocks.back().isize < want) return false;
+    out.resize((size_t)(blocks.back().obeg + blocks.back().isize));
+    if (!inflate_blocks(buf.data(), blocks, out.data(), 1)) return false;
+    out.resize((size_t)want);
+    return true;
+}
+
+int finish_and_write(const Cli& c, std::vector<Piece>& pieces, const bqc_bam_header& hdr, TimePoint t_start, TimePoint t_setup) {
+    const int N = (int)pieces.size();
+    for (Piece& P : pieces)
+        if (bqc_finish(P.eng)) {
+            bqc_error_info ei;
+            bqc_get_error(P.eng, &ei);
+            // a piece that does not end on a record boundary: the guessed start of the next piece was wrong (or the file is
+            // damaged, which the single-stream pass then reports)
+            if (N > 1 && ei.code == BQC_ERR_BAD_RECORD) return 2;
+            report_finish_error(P.eng, c);
+            return 1;
+        }
+    if (N > 1) {
+        // the coverage windows across the cuts (include/bamqc_b200.h: bqc_cov_shard_*), then everything is summed
+        std::vector<bqc_cov_shard> sh((size_t)N);
+        for (int k = 0; k < N; ++k)
+            if (bqc_cov_shard_boundary(pieces[k].eng, &sh[k])) return report_submit_error(pieces[k].eng, c);
+        std::vector<int> have_prev(N, 0);
+        std::vector<int32_t> prid(N, 0);
+        std::vector<uint32_t> pb(N, 0);
+        for (int k = 1; k < N; ++k) {
+            have_prev[k] = have_prev[k - 1]; prid[k] = prid[k - 1]; pb[k] = pb[k - 1];
+            if (sh[k - 1].n) { have_prev[k] = 1; prid[k] = sh[k - 1].last_rid; pb[k] = sh[k - 1].last_b; }
+        }
+        std::vector<std::vector<uint16_t>> fn((size_t)N, std::vector<uint16_t>(1002));
+        for (int k = 0; k < N; ++k)
+            if (bqc_cov_shard_function(pieces[k].eng, have_prev[k], prid[k], pb[k], fn[k].data())) return report_submit_error(pieces[k].eng, c);
+        uint32_t p = 0;
+        for (int k = 0; k < N; ++k) {
+            if (bqc_cov_shard_run(pieces[k].eng, have_prev[k], prid[k], pb[k], p, &sh[k])) return report_submit_error(pieces[k].eng, c);
+            if (sh[k].n) p = bqc_cov_apply(fn[k].data(), p);
+        }
+        int64_t delta[101];
+        bqc_cov_shards_combine(sh.data(), N, delta);
+        for (int k = 1; k < N; ++k)
+            if (bqc_merge_from(pieces[0].eng, pieces[k].eng)) return report_submit_error(pieces[0].eng, c);
+        if (bqc_poscov_adjust(pieces[0].eng, 0, delta)) return report_submit_error(pieces[0].eng, c);
+    }
+    auto t_stats = std::chrono::steady_clock::now();
+    if (bqc_write_bamqc(pieces[0].eng, hdr.sample_id, c.out.c_str())) {
+        std::cerr << "ERROR: Could not open output file " << c.out << '\n';
+        return 1;
+    }
+    auto t_end = std::chrono::steady_clock::now();
+    if (c.timing) {
+        auto sec = [](TimePoint a, TimePoint b) { return std::chrono::duration<double>(b - a).count(); };
+        unsigned long long recs = 0;
+        for (Piece& P : pieces) recs += bqc_records_seen(P.eng);
+        fprintf(stderr, "BAMQC_TIMING records=%llu setup_s=%.4f stats_s=%.4f write_s=%.4f total_s=%.4f threads=%d devices=%d\n", recs, sec(t_start, t_setup), sec(t_setup, t_stats),
+                sec(t_stats, t_end), sec(t_start, t_end), c.threads, N);
+    }
+    return 0;
+}
+
+// A .bam file (BGZF, or the raw uncompressed BAM stream the tests use): read in staging-sized pieces, never as a
+// whole (src/bamqualcheck.cpp:303-306 streams too).  With several devices the file is cut into contiguous byte
+// ranges at BGZF block boundaries, one engine per range, all reading concurrently.
+int run_file(Cli& c, TimePoint t_start) {
+    const int fd = open(c.bam.c_str(), O_RDONLY);
+    if (fd < 0) {
+        std::cerr << "ERROR: Could not open " << c.bam << " for reading.\n";
+        return 1;
+    }
+    struct stat st;
+    const bool seekable = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
+    const uint64_t file_size = seekable ? (uint64_t)st.st_size : ~0ull;
+    if (!probe_output(c)) { close(fd); return 1; }
+    // ---- header: read (and inflate) a prefix large enough to hold it ------------------------------------
+    std::vector<uint8_t> front;          // the first bytes of the file as read
+    RangeReader rr;
+    rr.fd = fd; rr.seekable = seekable; rr.end = file_size;
+    auto grow_front = [&](size_t more) { const size_t o = front.size(); front.resize(o + more); front.resize(o + rr.read(front.data() + o, more)); return front.size() > o; };
+    grow_front(1u << 20);
+    const bool raw = front.size() >= 4 && memcmp(front.data(), "BAM\1", 4) == 0;
+    bqc_bam_header hdr;
+    size_t hdr_bytes = 0;
+    std::vector<BgzfBlock> blocks;       // BGZF blocks of `front`
+    std::vector<uint8_t> head;
+    for (;;) {
+        if (raw) hdr_bytes = bqc_parse_bam_header(front.data(), front.size(), &hdr);
+        else {
+            blocks.clear();
+            bool bad = false;
+            bgzf_index(front.data(), front.size(), blocks, ~0ull, bad);
+            if (bad || (blocks.empty() && front.size() >= (1u << 17))) break;
+            if (!blocks.empty()) {
+                head.resize((size_t)(blocks.back().obeg + blocks.back().isize));
+                if (!inflate_blocks(front.data(), blocks, head.data(), c.threads)) break;
+                hdr_bytes = bqc_parse_bam_header(head.data(), head.size(), &hdr);
+            }
+        }
+        if (hdr_bytes) break;
+        if (!grow_front(std::max<size_t>(front.size(), 1u << 20))) break;   // the header did not fit: read on
+    }
+    if (!hdr_bytes) {
+        std::cerr << "ERROR: Could not open " << c.bam << " for reading.\n";
+        close(fd);
+        return 1;
+    }
+    // ---- engines: one per device; with several, the record stream is cut into contiguous pieces -----------
+    uint64_t rec_beg = 0;   // file offset of the first BGZF block that holds records
+    size_t skip = 0;
+    if (!raw) {
+        size_t k = 0;
+        while (k < blocks.size() && blocks[k].obeg + blocks[k].isize <= hdr_bytes) ++k;
+        if (k < blocks.size()) { rec_beg = blocks[k].bbeg; skip = hdr_bytes - (size_t)blocks[k].obeg; }
+        else { rec_beg = blocks.empty() ? 0 : blocks.back().bbeg + (blocks.back().cbeg - blocks.back().bbeg) + blocks.back().clen + 8; skip = 0; }
+    }
+    std::vector<int> devices = c.devices;
+    if (raw || !seekable || hdr.n_lanes != 1) devices.resize(1);   // pieces need BGZF block boundaries and device-side framing
+    std::vector<uint64_t> cut(1, rec_beg);
+    if (devices.size() > 1) {
+        const uint64_t span = file_size - rec_beg;
+        const size_t n = (size_t)std::min<uint64_t>(devices.size(), std::max<uint64_t>(1, span >> 22));   // at least 4 MB of file per piece
+        for (size_t k = 1; k < n; ++k) {
+            const uint64_t at = find_bgzf_block(fd, rec_beg + span * k / n, file_size);
+            if (at != ~0ull && at > cut.back() && at < file_size) cut.push_back(at);
+        }
+        devices.resize(cut.size());
+    }
+    const int N = (int)devices.size();
+    int rc = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        std::vector<Piece> pieces((size_t)(attempt ? 1 : N));
+        const int M = (int)pieces.size();
+        for (int k = 0; k < M && !rc; ++k) {
+            pieces[k].eng = make_engine(c, hdr, devices[k], pieces[k].main_chrom);
+            if (!pieces[k].eng) rc = 1;
+            pieces[k].beg = k ? cut[k] : rec_beg;
+            pieces[k].end = k + 1 < M ? cut[k + 1] : file_size;
+        }
+        bqc_fasta* fa = rc ? nullptr : bqc_fasta_open(c.ref.c_str());
+        if (!rc && !fa) std::cerr << "ERROR: Could not open fasta file " << c.ref << std::endl;  // the reference continues too (:291)
+        if (fa) {
+            std::vector<std::thread> th;
+            std::atomic<int> bad(0);
+            for (int k = 0; k < M; ++k) th.emplace_back([&, k] { if (!load_reference(pieces[k].eng, fa, hdr)) bad = 1; });
+            for (auto& t : th) t.join();
+            bqc_fasta_close(fa);
+            if (bad) rc = 1;
+        }
+        auto t_setup = std::chrono::steady_clock::now();
+        if (!rc && raw) {
+            // the uncompressed stream: the engine frames it on the device
+            bqc_engine* eng = pieces[0].eng;
+            std::vector<uint8_t> pending(front.begin() + (ptrdiff_t)hdr_bytes, front.end());
+            bool eof = false, first = true;
+            while ((!eof || !pending.empty() || first) && !rc) {
+                first = false;
+                void* pin;
+                size_t cap;
+                if (bqc_acquire_staging(eng, &pin, &cap)) { rc = report_submit_error(eng, c); break; }
+                uint8_t* buf = (uint8_t*)pin;
+                size_t filled = std::min(cap, pending.size());
+                memcpy(buf, pending.data(), filled);
+                pending.erase(pending.begin(), pending.begin() + (ptrdiff_t)filled);
+                if (pending.empty() && !eof && filled < cap) {
+                    const size_t got = rr.read(buf + filled, cap - filled);
+                    if (got < cap - filled) eof = true;
+                    filled += got;
+                }
+                if (bqc_submit_stream(eng, buf, filled, (eof && pending.empty()) ? 1 : 0)) rc = report_submit_error(eng, c);
+            }
+        } else if (!rc) {
+            if (M > 1)
+                for (int k = 0; k < M; ++k) bqc_cov_defer(pieces[k].eng, k == 0 ? 2 : 1);
+            pieces[0].skip = skip;
+            if (!seekable) {  // a pipe: what was read for the header is replayed from memory first
+                // (single piece) the front bytes from rec_beg on are fed through a temporary reader below
+            }
+            std::vector<std::thread> th;
+            std::vector<int> prc((size_t)M, 0);
+            for (int k = 0; k < M; ++k)
+                th.emplace_back([&, k] {
+                    auto next_head = [&](std::vector<uint8_t>& out) -> bool {
+                        uint64_t skipped = 0;
+                        for (;;) {   // until piece k+1 has framed its first buffer
+                            const int r = bqc_stream_skipped(pieces[k + 1].eng, &skipped);
+                            if (r == 0) break;
+                            if (r > 0 || pieces[k + 1].rc.load()) return false;
+                            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+                        }
+                        return inflate_head(fd, pieces[k + 1].beg, file_size, skipped, out);
+                    };
+                    prc[k] = seekable ? stream_bgzf_piece(c, fd, pieces[k], k > 0, k + 1 == M, next_head) : 0;
+                    if (prc[k]) pieces[k].rc = 1;
+                });
+            for (auto& t : th) t.join();
+            if (!seekable) {
+                // BGZF from a pipe: the bytes already read (from the first record block on), then the rest of the pipe
+                bqc_engine* eng = pieces[0].eng;
+                std::vector<uint8_t> carry(front.begin() + (ptrdiff_t)rec_beg, front.end());
+                size_t sk = skip;
+                bool eof = false, any = false;
+                while ((!eof || !carry.empty() || !any) && !rc) {
+                    void* pin;
+                    size_t cap;
+                    if (bqc_acquire_staging(eng, &pin, &cap)) { rc = report_submit_error(eng, c); break; }
+                    uint8_t* buf = (uint8_t*)pin;
+                    const size_t target = std::max<size_t>(1u << 20, cap / 4);
+                    size_t filled = std::min(carry.size(), target);
+                    memcpy(buf, carry.data(), filled);
+                    carry.erase(carry.begin(), carry.begin() + (ptrdiff_t)filled);
+                    if (carry.empty() && !eof && filled < target) {
+                        const size_t got = rr.read(buf + filled, target - filled);
+                        if (got < target - filled) eof = true;
+                        filled += got;
+                    }
+                    uint64_t inflated = 0;
+                    bool bad = false;
+                    const size_t used = bgzf_whole_prefix(buf, filled, cap, inflated, bad);
+                    if (bad || (used == 0 && filled > 0 && eof && carry.empty())) { std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n"; rc = 1; break; }
+                    carry.insert(carry.begin(), buf + used, buf + filled);
+                    const bool final_chunk = eof && carry.empty();
+                    if (used || final_chunk) {
+                        if (bqc_submit_bgzf(eng, buf, used, sk, final_chunk ? 1 : 0)) { rc = report_submit_error(eng, c); break; }
+                        sk = 0;
+                        any = true;
+                    }
+                    if (final_chunk) break;
+                }
+            }
+            for (int k = 0; k < M; ++k)
+                if (prc[k]) rc = 1;
+        }
+        if (!rc) rc = finish_and_write(c, pieces, hdr, t_start, t_setup);
+        if (rc == 2 && attempt == 0) {  // a piece did not begin where its predecessor ended: one stream on one device
+            std::cerr << "note: the file could not be cut at the guessed record boundaries; reading it as one stream\n";
+            for (Piece& P : pieces) bqc_destroy(P.eng);
+            rc = 0;
+            continue;
+        }
+        if (rc == 2) rc = 1;
+        for (Piece& P : pieces)
+            if (P.eng) bqc_destroy(P.eng);
+        break;
+    }
+    bqc_free_bam_header(&hdr);
+    close(fd);
+    return rc;
+}
+}  // namespace
+
 extern "C" int bqc_main(int argc, const char* const* argv) {
     Cli c;
     std::string kmer = "32", qcut = "17";
@@ -680,7 +1152,8 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
                          "  -o, --output-file OUT      Output filename.\n  -k, --kmer-size STRING     Comma-separated list of k-mer sizes. Default: 32.\n"
                          "  -q, --quality-cutoff STRING Comma-separated list of PHRED quality thresholds. Default: 17.\n"
                          "  -e, --error-rate DOUBLE    Error rate guaranteed. Default: 0.01.\n  -s, --seed INT             Seed value for the randomness. Default: 1.\n"
-                         "  --device INT, --threads INT, --timing   (engine options)\n";
+                         "  --device INT | --devices LIST (e.g. 0-7: the BAM file is cut into one piece per GPU), --threads INT,\n"
+                         "  --max-read-len INT, --staging-mb INT, --timing   (engine options)\n";
             return 0;
         }
         if (a == "--version") { std::cout << "bamqualcheck version: dev (bamqc-b200)\n"; return 0; }
@@ -692,7 +1165,20 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
         else if (a == "-q" || a == "--quality-cutoff") qcut = need("q");
         else if (a == "-e" || a == "--error-rate") c.e = atof(need("e").c_str());
         else if (a == "-s" || a == "--seed") c.seed = atoi(need("s").c_str());
-        else if (a == "--device") c.device = atoi(need("device").c_str());
+        else if (a == "--device") c.devices = {atoi(need("device").c_str())};
+        else if (a == "--devices") {   // 0,1,2 or 0-7: the file is cut into one contiguous piece per device
+            c.devices.clear();
+            std::stringstream ds(need("devices"));
+            std::string item;
+            while (std::getline(ds, item, ',')) {
+                const size_t dash = item.find('-');
+                if (dash != std::string::npos && dash > 0) for (int d = atoi(item.substr(0, dash).c_str()); d <= atoi(item.substr(dash + 1).c_str()); ++d) c.devices.push_back(d);
+                else if (!item.empty()) c.devices.push_back(atoi(item.c_str()));
+            }
+            if (c.devices.empty()) c.devices = {0};
+        }
+        else if (a == "--max-read-len") c.max_read_len = atoi(need("max-read-len").c_str());
+        else if (a == "--staging-mb") c.staging_mb = (uint64_t)atoll(need("staging-mb").c_str());
         else if (a == "--threads") c.threads = atoi(need("threads").c_str());
         else if (a == "--timing") c.timing = true;
         else positional.push_back(a);
@@ -713,10 +1199,12 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
     const bool sam = c.bam == "-";
     if (c.threads <= 0) c.threads = (int)std::max(1u, std::thread::hardware_concurrency());
     auto t_start = std::chrono::steady_clock::now();
+    if (!sam) return run_file(c, t_start);
+    // ---- SAM text on stdin (src/bamqualcheck.cpp:252-260): one device ------------------------------------
     std::vector<uint8_t> file;
     std::string sam_pending;  // first alignment line, read while looking for the end of the header
     bool sam_have_pending = false;
-    if (sam) {
+    {
         std::cerr << "Reading from stdin" << std::endl;  // src/CommandLineParser.hpp:96
         std::string text, line;
         while (std::getline(std::cin, line)) {
@@ -727,116 +1215,22 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
             break;
         }
         file = sam_header_to_bam(text);
-    } else if (!read_file(c.bam, file)) {
-        std::cerr << "ERROR: Could not open " << c.bam << " for reading.\n";
-        return 1;
     }
-    std::ofstream probe(c.out.c_str(), std::ios::out | std::ios::binary);
-    if (!probe.good()) {
-        std::cerr << "ERROR: Could not open output file " << c.out << '\n';
-        return 1;
-    }
-    probe.close();
-    const bool raw = file.size() >= 4 && memcmp(file.data(), "BAM\1", 4) == 0;
-
-    // ---- header: inflate a prefix large enough to hold it --------------------------------------------
-    std::vector<BgzfBlock> blocks;
-    std::vector<uint8_t> head;
-    size_t next_block = 0;
-    if (!raw) {
-        bool bad = false;
-        uint64_t used = bgzf_index(file.data(), file.size(), blocks, ~0ull, bad);
-        if (bad || used != file.size() || blocks.empty()) {
-            std::cerr << "ERROR: Could not open " << c.bam << " for reading.\n";
-            return 1;
-        }
-    }
+    if (!probe_output(c)) return 1;
     bqc_bam_header hdr;
-    size_t hdr_bytes = 0;
-    if (raw) {
-        hdr_bytes = bqc_parse_bam_header(file.data(), file.size(), &hdr);
-    } else {
-        // grow the inflated prefix until the header parses
-        size_t nb = 0;
-        while (nb < blocks.size()) {
-            size_t take = std::min(blocks.size(), nb ? nb * 2 : (size_t)4);
-            std::vector<BgzfBlock> part(blocks.begin(), blocks.begin() + take);
-            head.resize(part.back().obeg + part.back().isize);
-            if (!inflate_blocks(file.data(), part, head.data(), c.threads)) {
-                std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
-                return 1;
-            }
-            nb = take;
-            hdr_bytes = bqc_parse_bam_header(head.data(), head.size(), &hdr);
-            if (hdr_bytes) break;
-        }
-        next_block = nb;
-    }
-    if (!hdr_bytes) {
+    if (!bqc_parse_bam_header(file.data(), file.size(), &hdr)) {
         std::cerr << "ERROR: Could not open " << c.bam << " for reading.\n";
         return 1;
     }
-
-    // ---- engine --------------------------------------------------------------------------------------
-    std::vector<uint8_t> main_chrom((size_t)std::max(1, hdr.n_ref), 0);
-    {
-        std::istringstream cs(c.chroms);
-        std::string name;
-        while (std::getline(cs, name, ','))
-            for (int i = 0; i < hdr.n_ref; ++i)
-                if (name == hdr.ref_names[i]) { main_chrom[i] = 1; break; }
-    }
-    if (hdr.n_lanes == 0) {
-        std::cerr << "ERROR: BAM header declares no read group (@RG); bamqualcheck needs at least one.\n";
-        return 1;
-    }
-    bqc_config cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.device = c.device;
-    cfg.isize = c.isize;
-    cfg.n_lanes = hdr.n_lanes;
-    cfg.lane_ids = hdr.lane_ids;
-    cfg.n_ref = hdr.n_ref;
-    cfg.main_chrom = main_chrom.data();
-    cfg.n_k = (int32_t)c.klist.size();
-    cfg.klist = c.klist.data();
-    cfg.n_q = (int32_t)c.qlist.size();
-    cfg.q_cutoff = c.qlist.data();
-    cfg.q_base = 33;
-    cfg.e = c.e;
-    cfg.seed = c.seed;
-    bqc_engine* eng = nullptr;
-    if (bqc_create(&cfg, &eng)) {
-        std::cerr << "ERROR: " << bqc_last_error(nullptr) << std::endl;
-        return 1;
-    }
-    // reference genome: every BAM reference that the FASTA holds goes to HBM
+    std::vector<uint8_t> main_chrom;
+    bqc_engine* eng = make_engine(c, hdr, c.devices[0], main_chrom);
+    if (!eng) return 1;
     bqc_fasta* fa = bqc_fasta_open(c.ref.c_str());
     if (!fa) std::cerr << "ERROR: Could not open fasta file " << c.ref << std::endl;  // the reference continues too (:291)
-    if (fa)
-        for (int i = 0; i < hdr.n_ref; ++i) {
-            const uint8_t* packed = nullptr;
-            int64_t len = bqc_fasta_contig(fa, hdr.ref_names[i], &packed);
-            if (len >= 0 && bqc_set_reference(eng, i, packed, (uint64_t)len)) {
-                std::cerr << "ERROR: " << bqc_last_error(eng) << std::endl;
-                return 1;
-            }
-        }
+    if (fa && !load_reference(eng, fa, hdr)) return 1;
     auto t_setup = std::chrono::steady_clock::now();
-
-    // ---- stream the inflated bytes through the pinned staging buffers; the engine frames the records --------
     int rc = 0;
-    auto report_submit_error = [&]() -> int {
-        bqc_error_info ei;
-        bqc_get_error(eng, &ei);
-        if (ei.code == BQC_ERR_BAD_RECORD) std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
-        else std::cerr << "ERROR: " << bqc_last_error(eng) << std::endl;
-        return 1;
-    };
-    auto submit_chunk = [&](uint8_t* buf, size_t filled, bool last) -> int {
-        return bqc_submit_stream(eng, buf, filled, last ? 1 : 0) ? report_submit_error() : 0;
-    };
-    if (sam) {
+    {
         std::map<std::string, int32_t> ref_id;
         for (int i = 0; i < hdr.n_ref; ++i) ref_id.insert({hdr.ref_names[i], i});  // first of duplicate names wins
         std::vector<uint8_t> enc;
@@ -862,46 +1256,10 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
             if (rc) break;
             if (enc.size() > cap) { std::cerr << "ERROR: SAM record larger than the staging buffer\n"; rc = 1; break; }
             memcpy(pin, enc.data(), enc.size());
-            rc = submit_chunk((uint8_t*)pin, enc.size(), eof);
-        }
-    } else if (raw) {
-        size_t p = hdr_bytes;
-        bool first = true;
-        while ((p < file.size() || first) && !rc) {
-            first = false;
-            void* pin;
-            size_t cap;
-            if (bqc_acquire_staging(eng, &pin, &cap)) { rc = 1; break; }
-            uint8_t* buf = (uint8_t*)pin;
-            size_t take = std::min(cap, file.size() - p);
-            memcpy(buf, file.data() + p, take);
-            p += take;
-            rc = submit_chunk(buf, take, p >= file.size());
-        }
-    } else {
-        // the compressed blocks go to the device as they are (inflated and framed there); the first block that
-        // holds records may start with the end of the header
-        size_t k = 0;
-        while (k < blocks.size() && blocks[k].obeg + blocks[k].isize <= hdr_bytes) ++k;
-        if (k < blocks.size()) {
-            const size_t skip = hdr_bytes - (size_t)blocks[k].obeg;
-            if (bqc_submit_bgzf(eng, file.data() + blocks[k].bbeg, file.size() - (size_t)blocks[k].bbeg, skip, 1)) rc = report_submit_error();
-        } else {
-            rc = submit_chunk(nullptr, 0, true);
+            if (bqc_submit_stream(eng, pin, enc.size(), eof ? 1 : 0)) rc = report_submit_error(eng, c);
         }
     }
-    if (!rc) {
-        int code = bqc_finish(eng);
-        if (code) {
-            bqc_error_info ei;
-            bqc_get_error(eng, &ei);
-            if (ei.code == BQC_ERR_RG_NOT_Z) std::cout << "Read does not have Z" << "\n";
-            else if (ei.code == BQC_ERR_BAD_RECORD) std::cerr << "ERROR: Could not read record from BAM File " << c.bam << "\n";
-            else if (ei.code == BQC_ERR_NO_MATE_FLAG) std::cerr << "ERROR: No first or second flag in read in:  " << c.bam << "\n";
-            else std::cerr << (ei.code ? ei.message : bqc_last_error(eng)) << std::endl;
-            rc = 1;
-        }
-    }
+    if (!rc && bqc_finish(eng)) { report_finish_error(eng, c); rc = 1; }
     auto t_stats = std::chrono::steady_clock::now();
     if (!rc && bqc_write_bamqc(eng, hdr.sample_id, c.out.c_str())) {
         std::cerr << "ERROR: Could not open output file " << c.out << '\n';
@@ -910,7 +1268,7 @@ extern "C" int bqc_main(int argc, const char* const* argv) {
     auto t_end = std::chrono::steady_clock::now();
     if (c.timing) {
         auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
-        fprintf(stderr, "BAMQC_TIMING records=%llu setup_s=%.4f stats_s=%.4f write_s=%.4f total_s=%.4f threads=%d\n", (unsigned long long)bqc_records_seen(eng), sec(t_start, t_setup), sec(t_setup, t_stats), sec(t_stats, t_end), sec(t_start, t_end), c.threads);
+        fprintf(stderr, "BAMQC_TIMING records=%llu setup_s=%.4f stats_s=%.4f write_s=%.4f total_s=%.4f threads=%d devices=1\n", (unsigned long long)bqc_records_seen(eng), sec(t_start, t_setup), sec(t_setup, t_stats), sec(t_stats, t_end), sec(t_start, t_end), c.threads);
     }
     if (fa) bqc_fasta_close(fa);
     bqc_destroy(eng);

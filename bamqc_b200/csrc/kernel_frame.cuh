@@ -89,6 +89,28 @@ __device__ __forceinline__ void frame_walk(const uint8_t* d, uint64_t n, uint64_
     exit_pos = (uint32_t)p;
 }
 
+// A stream that begins somewhere inside a record (a later piece of a file cut at BGZF block boundaries): the first
+// position from which six records in a row look plausible becomes the stream position.  The caller verifies the guess
+// from the other side: the piece before it must end exactly there (include/bamqc_b200.h, bqc_stream_unknown_start).
+static const uint32_t kFrameSeekSpan = 1u << 20;   // a record is smaller than the head room (1 MiB)
+__global__ void __launch_bounds__(256) k_frame_seek(const uint8_t* __restrict__ d, FrameResult* fr, int32_t n_ref) {
+    __shared__ uint32_t s_best;
+    const uint64_t start = fr->start, n = fr->total;
+    if (threadIdx.x == 0) s_best = kNone;
+    __syncthreads();
+    for (uint64_t base = start; base < n && base < start + kFrameSeekSpan; base += blockDim.x) {
+        const uint64_t p = base + threadIdx.x;
+        if (p + 36 <= n && frame_chain_plausible(d, n, p, n_ref)) atomicMin(&s_best, (uint32_t)p);
+        __syncthreads();
+        if (s_best != kNone) break;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (s_best != kNone) fr->start = s_best;
+        else { fr->start = (uint32_t)n; fr->tail_overflow = 1u; }   // no record boundary in sight: reported as an unreadable stream
+    }
+}
+
 __global__ void __launch_bounds__(kFrameThreads) k_frame_speculate(const uint8_t* __restrict__ d, const FrameResult* __restrict__ fr, int32_t n_ref, uint32_t nwin,
                                                                    uint32_t* __restrict__ ws, uint32_t* __restrict__ we, uint32_t* __restrict__ wc) {
     const uint32_t w = blockIdx.x * kFrameThreads + threadIdx.x;

@@ -99,6 +99,15 @@ int bqc_submit_stream(bqc_engine* e, const void* data, size_t n_bytes, int last)
  * (the BAM header, for the first call of a file).  With several read groups or BQC_HOST_FRAMING=1 the blocks are
  * inflated with zlib on the host threads instead (same results). */
 int bqc_submit_bgzf(bqc_engine* e, const void* data, size_t n_bytes, size_t skip_bytes, int last);
+/* A later piece of a file that was cut at BGZF block boundaries begins somewhere inside a record.  Called before the
+ * first submission, bqc_stream_unknown_start makes the engine look for the first record boundary itself (the first
+ * position from which six records in a row are plausible); bqc_stream_skipped then tells how many inflated bytes lie in
+ * front of it -- they are the end of the previous piece's last record and have to be submitted there
+ * (bqc_submit_stream(..., last = 1)); that piece ending exactly on a record boundary is the proof that the guess was
+ * right (otherwise it reports BQC_ERR_BAD_RECORD and the caller falls back to a single stream). */
+int bqc_stream_unknown_start(bqc_engine* e);
+int bqc_stream_skipped(bqc_engine* e, uint64_t* skipped);   /* 0: known; -1: the first submission has not been framed yet (poll; may be
+                                                               called from another thread); > 0: the engine's error code */
 /* Number of stream buffers whose speculative framing failed verification and were re-framed sequentially. */
 uint64_t bqc_frames_repaired(bqc_engine* e);
 /* Records submitted so far (waits for the submissions in flight to be framed). */

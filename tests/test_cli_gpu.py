@@ -222,3 +222,52 @@ def test_records_larger_than_a_framing_window(tmp_path):
     g = util.run_cli(["-r", fasta, "-c", "chr1,chr2", "-o", tmp_path / "g2.bamqc", tmp_path / "in.bam"])
     assert g.returncode == 0, g.stderr
     assert not util.diff_bamqc(tmp_path / "g.bamqc", tmp_path / "g2.bamqc")
+
+
+# ---- streaming file input and several devices (the file is cut into one contiguous piece per engine) -----------------
+@pytest.fixture(scope="module")
+def big_bgzf(tmp_path_factory):
+    """~600 k records as a level-1 BGZF BAM (~60 MB of file) + FASTA + the oracle's .bamqc."""
+    from bamqc_b200 import synth
+    d = tmp_path_factory.mktemp("big")
+    genome = util.small_genome(seed=41, lengths=(3000000, 1500000, 200000))
+    lib_ = synth.Library(seed=4100, n_pairs=300000)
+    records, offsets = synth.generate(genome, lib_)
+    fasta, bam = d / "g.fa", d / "big.bam"
+    genome.write_fasta(fasta)
+    synth.write_bam(bam, genome, lib_, records, int(offsets[-1]), level=1)
+    r = util.run_oracle(bam, fasta, d / "oracle.bamqc", chroms="chr1,chr2")
+    assert r.returncode == 0, r.stderr
+    return d
+
+
+@pytest.mark.parametrize("opts", [["--staging-mb", "8"], ["--devices", "0,0", "--staging-mb", "32"], ["--devices", "0,0,0", "--staging-mb", "16"]],
+                         ids=["one_device_small_staging", "two_pieces", "three_pieces"])
+def test_cli_streams_the_file_and_cuts_it_across_devices(big_bgzf, tmp_path, opts):
+    """The command never holds the whole file: it reads staging-sized pieces (8 MB here: dozens of submissions with
+    carried partial BGZF blocks).  With --devices the file is cut at BGZF block boundaries found by signature; the
+    engines of the later pieces find their first record boundary themselves, the piece before completes its last
+    record from the next piece's first bytes, and the coverage windows are resolved across the cuts.  Two or three
+    engines share GPU 0 here; the output must be byte-identical to the oracle's on the whole file."""
+    d = big_bgzf
+    out = tmp_path / "gpu.bamqc"
+    r = util.run_cli(["-r", d / "g.fa", "-c", "chr1,chr2", "-o", out, "--timing"] + opts + [d / "big.bam"])
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "could not be cut" not in r.stderr
+    if "--devices" in opts:
+        assert "devices=%d" % len(opts[1].split(",")) in r.stderr, r.stderr
+    diffs = util.diff_bamqc(d / "oracle.bamqc", out)
+    assert not diffs, "\n".join(diffs)
+
+
+def test_cli_reads_bgzf_from_a_pipe(big_bgzf, tmp_path):
+    d = big_bgzf
+    out = tmp_path / "gpu.bamqc"
+    exe = os.path.join(util.ROOT, "bamqc_b200", "bin", "bamqualcheck")
+    with open(d / "big.bam", "rb") as f:
+        p1 = subprocess.Popen(["cat"], stdin=f, stdout=subprocess.PIPE)
+        r = subprocess.run([exe, "-r", str(d / "g.fa"), "-c", "chr1,chr2", "-o", str(out), "--staging-mb", "16", "/dev/stdin"], stdin=p1.stdout, capture_output=True, text=True)
+        p1.wait()
+    assert r.returncode == 0, r.stderr + r.stdout
+    diffs = util.diff_bamqc(d / "oracle.bamqc", out)
+    assert not diffs, "\n".join(diffs)
