@@ -103,6 +103,8 @@ PROTOTYPES = {
     "bqc_finish": (ctypes.c_int, [_vp]),
     "bqc_profile_enable": (None, [_vp, ctypes.c_int]),
     "bqc_profile_read": (ctypes.c_int, [_vp, _P(ctypes.c_double), _P(_u64)]),
+    "bqc_read_len_capacity": (_u32, [_vp]),
+    "bqc_reserve_read_len": (ctypes.c_int, [_vp, _u32]),
     "bqc_counters_len": (_u64, [_vp]),
     "bqc_counters_export": (ctypes.c_int, [_vp, _vp]),
     "bqc_counters_import": (ctypes.c_int, [_vp, _vp]),

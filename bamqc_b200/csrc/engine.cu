@@ -407,6 +407,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     }
     if (cfg->device < 0 || cfg->device >= ndev) { set_error(nullptr, "bqc_create: bad device %d", cfg->device); return BQC_ERR_ARG; }
     if (cfg->n_lanes < 1 || cfg->n_k < 0 || cfg->n_q < 0 || cfg->isize < 0) { set_error(nullptr, "bqc_create: bad configuration"); return BQC_ERR_ARG; }
+    if (cfg->n_lanes > 255) { set_error(nullptr, "bqc_create: more than 255 read groups (the per-record lane index is one byte)"); return BQC_ERR_ARG; }
     if (cfg->seed == 0) { set_error(nullptr, "bqc_create: seed 0 (time-based hash seed, src/kmerstream/RepHash.cpp:5-7) is not reproducible and is rejected"); return BQC_ERR_ARG; }
     for (int i = 0; i < cfg->n_k; ++i)
         if (cfg->klist[i] < 1 || cfg->klist[i] > 63) { set_error(nullptr, "bqc_create: k must be in 1..63 (src/kmerstream/RepHash.hpp:34-35)"); return BQC_ERR_ARG; }
@@ -488,8 +489,8 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         CU(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kInflateStreams * sizeof(InflateTabs))));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->inflate_bps, k_inflate, (int)kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs)));
         if (e->inflate_bps < 1) e->inflate_bps = 1;
-        CU(cudaFuncSetAttribute(k_stats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CU(cudaFuncSetAttribute(k_stats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(k_stats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(k_stats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CU(cudaFuncSetAttribute(k_eightmer, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CU(cudaFuncSetAttribute(k_sketch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CU(cudaFuncSetAttribute(k_cov_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCovBlockSmem));
@@ -828,17 +829,80 @@ struct BatchLaunch {  // launch geometry shared by the coverage and the table ke
     uint32_t cycb;
     size_t stats_smem;
     int bps;
+    bool staged;
 };
+
+// The reference's per-cycle String<>s grow with the longest read seen (src/QualityCheck.hpp:85-109); here the result
+// block has a per-cycle capacity, and a batch with a longer read moves every table to a larger layout before its
+// kernels are launched.  The limit is what k_stats can keep in shared memory (per-cycle rows of both mates).
+static const uint32_t kMaxReadLen = 1800;   // 2 mates x 9 padded per-cycle rows + 6 per-read histograms of that length: 216 KB of the 227 KB
+static int grow_read_len(bqc_engine* e, uint32_t need) {
+    if (need <= e->L.cyc || need > kMaxReadLen) return 0;   // longer: the kernel reports BQC_ERR_UNSUPPORTED
+    const uint32_t cyc2 = std::min<uint32_t>(pad8(kMaxReadLen), pad8(std::max<uint32_t>(need, e->L.cyc + e->L.cyc / 2)));
+    const Layout A = e->L, Bn = make_layout(cyc2, A.isize1 - 1, A.n_qk, A.f2size, A.sk_size);
+    std::vector<uint3> segs;
+    auto seg = [&](uint32_t so, uint32_t d_o, uint32_t n) { segs.push_back(make_uint3(so, d_o, n)); };
+    seg(A.o_scalars, Bn.o_scalars, S_COUNT);
+    seg(A.o_poscov, Bn.o_poscov, kPoscov);
+    seg(A.o_insert, Bn.o_insert, pad8(A.isize1));
+    seg(A.o_eightmer, Bn.o_eightmer, kEightmer);
+    seg(A.o_triplet, Bn.o_triplet, kTriplet);
+    for (uint32_t m = 0; m < 2; ++m) {
+        const uint32_t a = A.o_mate0 + m * A.mate_stride, b = Bn.o_mate0 + m * Bn.mate_stride;
+        seg(a + A.m_readlen, b + Bn.m_readlen, pad8(A.cyc + 1));
+        seg(a + A.m_ncount, b + Bn.m_ncount, pad8(A.cyc + 1));
+        seg(a + A.m_gccount, b + Bn.m_gccount, pad8(A.cyc + 1));
+        seg(a + A.m_avgq, b + Bn.m_avgq, kQCap);
+        seg(a + A.m_ceilq, b + Bn.m_ceilq, kQCap);
+        seg(a + A.m_mapq, b + Bn.m_mapq, kMapqCap);
+        seg(a + A.m_mismatch, b + Bn.m_mismatch, A.mmcap);
+        seg(a + A.m_del, b + Bn.m_del, A.delcap);
+        seg(a + A.m_ins, b + Bn.m_ins, A.mmcap);
+        for (uint32_t r = 0; r < PC_ROWS; ++r) seg(a + A.m_pc + r * pad8(A.cyc), b + Bn.m_pc + r * pad8(Bn.cyc), pad8(A.cyc));
+        seg(a + A.m_readnr, b + Bn.m_readnr, 8);
+    }
+    seg(A.o_qk, Bn.o_qk, A.n_qk * A.qk_stride);
+    uint64_t* d2 = nullptr;
+    uint3* dseg = nullptr;
+    CU(cudaStreamSynchronize(e->covs));      // the coverage kernels add to poscov in the old block
+    CU(cudaStreamSynchronize(e->compute));
+    CU(cudaMalloc(&d2, e->n_lanes * Bn.lane_stride * 8));
+    CU(cudaMemset(d2, 0, e->n_lanes * Bn.lane_stride * 8));
+    CU(cudaMalloc(&dseg, segs.size() * sizeof(uint3)));
+    CU(cudaMemcpy(dseg, segs.data(), segs.size() * sizeof(uint3), cudaMemcpyHostToDevice));
+    k_relayout<<<dim3(64, (unsigned)segs.size()), 256, 0, e->compute>>>((const unsigned long long*)e->d_counters, (unsigned long long*)d2, dseg, (uint32_t)segs.size(), A.lane_stride,
+                                                                        Bn.lane_stride, e->n_lanes);
+    e->launches += 1;
+    CU(cudaStreamSynchronize(e->compute));
+    cudaFree(dseg);
+    cudaFree(e->d_counters);
+    e->d_counters = d2;
+    e->L = Bn;
+    e->have_results = false;
+    return 0;
+}
+
 static int batch_launch_setup(bqc_engine* e, const DeviceBatch& d, BatchLaunch& BL) {
+    if (d.max_lseq > e->L.cyc) { int rc = grow_read_len(e, d.max_lseq); if (rc) return rc; }
     BL.E = make_view(e);
     uint32_t cycb = pad8(std::max<uint32_t>(d.max_lseq, 8u));
     if (cycb > e->L.cyc) cycb = e->L.cyc;  // longer reads are reported as unsupported by the kernel
     BL.cycb = cycb;
     StatsSmem S = stats_smem_layout(cycb, BL.E.insert_smem);
-    BL.stats_smem = e->tune_stats_stage ? (size_t)S.stage * 4 + (size_t)(kStatsThreads / 32) * kStatsStage : (size_t)S.total * 4;
     int bps = 0;
-    if (e->tune_stats_stage) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats<true>, (int)kStatsThreads, BL.stats_smem));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats<false>, (int)kStatsThreads, BL.stats_smem));
+    BL.staged = e->tune_stats_stage != 0;
+    if (BL.staged) {  // the per-warp staging areas on top of the tables: only while both fit
+        BL.stats_smem = (size_t)S.stage * 4 + (size_t)(kStatsThreads / 32) * kStatsStage;
+        if (BL.stats_smem > 227u * 1024u || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats<true>, (int)kStatsThreads, BL.stats_smem) != cudaSuccess || bps < 1) {
+            cudaGetLastError();
+            BL.staged = false;
+            bps = 0;
+        }
+    }
+    if (!BL.staged) {
+        BL.stats_smem = (size_t)S.total * 4;
+        if (BL.stats_smem <= 227u * 1024u) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats<false>, (int)kStatsThreads, BL.stats_smem));
+    }
     if (bps < 1) { set_error(e, "k_stats does not fit: %zu bytes of shared memory", BL.stats_smem); return BQC_ERR_ARG; }
     if (e->tune_stats_bps > 0 && e->tune_stats_bps < bps) bps = e->tune_stats_bps;
     BL.bps = bps;
@@ -918,7 +982,7 @@ static int launch_tables(bqc_engine* e, const DeviceBatch& d, const BatchLaunch&
         int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * BL.bps);
         {
             ProfScope prof(e, 0);
-            if (e->tune_stats_stage) k_stats<true><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
+            if (BL.staged) k_stats<true><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
             else k_stats<false><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
         }
         int g8 = (int)std::min<uint64_t>((n + kEightThreads - 1) / kEightThreads, (uint64_t)e->n_sm);
@@ -1708,6 +1772,14 @@ extern "C" int bqc_poscov_adjust(bqc_engine* e, int32_t lane, const int64_t delt
 // ------------------------------------------------------------------------------------------------
 // multi-GPU merge helpers
 // ------------------------------------------------------------------------------------------------
+extern "C" uint32_t bqc_read_len_capacity(bqc_engine* e) { return e->L.cyc; }
+extern "C" int bqc_reserve_read_len(bqc_engine* e, uint32_t n) {
+    CU(cudaSetDevice(e->cfg.device));
+    { int arc = drain_commits(e); if (arc) return arc; }
+    if (n > kMaxReadLen) { set_error(e, "bqc_reserve_read_len: reads longer than %u are not supported", kMaxReadLen); return BQC_ERR_ARG; }
+    while (e->L.cyc < n) { const uint32_t before = e->L.cyc; int rc = grow_read_len(e, n); if (rc) return rc; if (e->L.cyc == before) break; }
+    return 0;
+}
 extern "C" uint64_t bqc_counters_len(bqc_engine* e) { return (uint64_t)e->n_lanes * e->L.lane_stride; }
 extern "C" int bqc_counters_export(bqc_engine* e, void* dev) {
     CU(cudaSetDevice(e->cfg.device));
@@ -1746,6 +1818,10 @@ extern "C" int bqc_sketch_import_u8(bqc_engine* e, const void* dev) {
 }
 extern "C" int bqc_merge_from(bqc_engine* dst, bqc_engine* src) {
     bqc_engine* e = dst;
+    if (dst->L.cyc != src->L.cyc) {  // one of them met a longer read: same layout first
+        int rc = dst->L.cyc < src->L.cyc ? grow_read_len(dst, src->L.cyc) : grow_read_len(src, dst->L.cyc);
+        if (rc) return rc;
+    }
     if (bqc_counters_len(dst) != bqc_counters_len(src) || bqc_sketch_len(dst) != bqc_sketch_len(src)) { set_error(e, "bqc_merge_from: engines differ in configuration"); return BQC_ERR_ARG; }
     CU(cudaSetDevice(src->cfg.device));
     CU(cudaStreamSynchronize(src->compute));

@@ -530,6 +530,15 @@ __global__ void k_sketch_merge(uint32_t* dst, const uint32_t* src, uint64_t nwor
         dst[i] = w;
     }
 }
+// move the tables of a result block to a layout with a larger per-cycle capacity: segs = {src offset, dst offset, length}
+__global__ void k_relayout(const unsigned long long* src, unsigned long long* dst, const uint3* __restrict__ segs, uint32_t nseg, uint64_t stride_src, uint64_t stride_dst, uint32_t n_lanes) {
+    for (uint32_t lane = 0; lane < n_lanes; ++lane)
+        for (uint32_t sgi = blockIdx.y; sgi < nseg; sgi += gridDim.y) {
+            const uint3 sg = segs[sgi];
+            for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.z; i += gridDim.x * blockDim.x)
+                dst[lane * stride_dst + sg.y + i] = src[lane * stride_src + sg.x + i];
+        }
+}
 __global__ void k_counters_add(unsigned long long* dst, const unsigned long long* src, uint64_t n) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] += src[i];
 }

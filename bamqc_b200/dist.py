@@ -38,8 +38,16 @@ def reduce_engine(engine, bufs=None, group=None):
     """Export this GPU's tables, all-reduce them over NCCL, import the merged tables back (every rank ends
     with the whole-job result).  `bufs` lets the caller reuse the two device tensors across steps."""
     import torch
+    import torch.distributed as dist
     dev = torch.device("cuda", engine.device)
-    if bufs is None:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        # the layout of the block depends on the longest read a rank has seen: same capacity everywhere first
+        cap = torch.tensor([engine.lib.bqc_read_len_capacity(engine.handle)], dtype=torch.int64, device=dev)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)
+        if int(cap.item()) != engine.lib.bqc_read_len_capacity(engine.handle):
+            engine._check(engine.lib.bqc_reserve_read_len(engine.handle, int(cap.item())))
+            bufs = None
+    if bufs is None or bufs[0].numel() != engine.counters_len():
         bufs = (torch.empty(engine.counters_len(), dtype=torch.int64, device=dev),
                 torch.empty(max(1, engine.sketch_len()), dtype=torch.uint8, device=dev))
     c, s = bufs

@@ -51,7 +51,8 @@ typedef struct bqc_config {
     uint32_t q_base;              /* 33 */
     double e;                     /* -e (sketch geometry, src/kmerstream/StreamCounter.hpp:25-43) */
     int32_t seed;                 /* -s (RepHash table, src/kmerstream/RepHash.cpp:4-17); 0 is rejected */
-    int32_t max_read_len;         /* per-cycle table capacity; 0 => 512.  Longer reads => BQC_ERR_UNSUPPORTED */
+    int32_t max_read_len;         /* initial per-cycle table capacity; 0 => 512.  The tables grow with the longest read seen, like
+                                     the reference's String<>s (src/QualityCheck.hpp:85-109), up to 1800 (what k_stats can keep in shared memory); beyond => BQC_ERR_UNSUPPORTED */
     uint64_t staging_bytes;       /* capacity of each pinned staging buffer; 0 => 256 MiB */
     uint32_t cov_ring_log2;       /* unused (the coverage statistic no longer keeps a depth ring); kept for ABI stability */
     int32_t host_threads;         /* host threads of the framing pre-pass of host-framed submissions; 0 => min(16, cores) */
@@ -143,6 +144,10 @@ int bqc_finish(bqc_engine* e);
 /* The additive part of the result: one flat uint64 array (all lanes).  Sum across GPUs, import on the
  * root.  dev_* pointers are device pointers on this engine's GPU. */
 uint64_t bqc_counters_len(bqc_engine* e);                 /* number of uint64 */
+/* The layout of the block depends on the per-cycle capacity, which grows with the longest read an engine has seen:
+ * before exporting, bring every engine to the largest capacity of the group (all-reduce max of the capacities). */
+uint32_t bqc_read_len_capacity(bqc_engine* e);
+int bqc_reserve_read_len(bqc_engine* e, uint32_t n);
 int bqc_counters_export(bqc_engine* e, void* dev_u64);    /* device -> device copy */
 int bqc_counters_import(bqc_engine* e, const void* dev_u64);
 /* The sketch: one uint8 per 4-bit counter (so that 8 GPUs x 15 fits); import clamps to 15. */

@@ -102,6 +102,20 @@ def test_long_reads_split_the_staging_span(tmp_path):
     _roundtrip(tmp_path, synth.Library(seed=32, n_pairs=4000, read_len=251, ins_mean=450))
 
 
+def test_tables_grow_with_the_longest_read(tmp_path):
+    """2 x 700 bp with the default per-cycle capacity of 512: the result block is moved to a larger layout when the first
+    batch with longer reads arrives (the reference's String<>s grow the same way, src/QualityCheck.hpp:85-109); the
+    second half of the records comes in a later batch."""
+    from bamqc_b200 import synth
+    _roundtrip(tmp_path, synth.Library(seed=33, n_pairs=1500, read_len=700, ins_mean=1200, ins_sd=100, ins_min=800, ins_max=2000), n_batches=2)
+
+
+def test_very_long_reads_without_staging(tmp_path):
+    """2 x 1500 bp: the per-cycle rows leave no room for the per-warp staging areas; k_stats reads the records from global memory."""
+    from bamqc_b200 import synth
+    _roundtrip(tmp_path, synth.Library(seed=34, n_pairs=400, read_len=1500, ins_mean=2500, ins_sd=100, ins_min=1800, ins_max=4000), isize=3000)
+
+
 def test_device_framing_whole_record_slices(tmp_path):
     from bamqc_b200 import synth
     _roundtrip(tmp_path, synth.Library(seed=21, n_pairs=20000), n_batches=3, mode="whole", expect_repaired=False)
