@@ -904,9 +904,166 @@ static inline int32_t rdI32(const uint8_t* p) {
     memcpy(&v, p, 4);
     return v;
 }
+// SAM text (`bamqualcheck ... -` or a .sam file: src/bamqualcheck.cpp:252-260, src/CommandLineParser.hpp:88-107).  The
+// reference hands the text to SeqAn's BamStream, which fills the same BamAlignmentRecord as for BAM; this reader is an
+// independent restatement of that (SAM specification sections 1.3-1.5): the text is turned into the inflated BAM
+// stream that readRecord() below decodes, so both formats meet the statistics through one decoder.
+template <typename T> static void putLE(std::vector<uint8_t>& v, T x) {
+    uint8_t b[sizeof(T)];
+    memcpy(b, &x, sizeof(T));
+    v.insert(v.end(), b, b + sizeof(T));
+}
+static bool samToBam(std::istream& in, std::vector<uint8_t>& out) {
+    std::string text, line;
+    std::vector<std::string> names;
+    std::vector<int32_t> lens;
+    std::vector<std::string> body;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line[line.size() - 1] == '\r') line.erase(line.size() - 1);
+        if (line.empty()) continue;
+        if (line[0] == '@' && body.empty()) {
+            text += line + "\n";
+            if (line.compare(0, 3, "@SQ") == 0) {
+                std::string sn;
+                long ln = 0;
+                std::istringstream ls(line);
+                std::string f;
+                while (std::getline(ls, f, '\t')) {
+                    if (f.compare(0, 3, "SN:") == 0) sn = f.substr(3);
+                    if (f.compare(0, 3, "LN:") == 0) ln = atol(f.c_str() + 3);
+                }
+                names.push_back(sn);
+                lens.push_back((int32_t)ln);
+            }
+        } else body.push_back(line);
+    }
+    out.clear();
+    out.insert(out.end(), {'B', 'A', 'M', 1});
+    putLE<int32_t>(out, (int32_t)text.size());
+    out.insert(out.end(), text.begin(), text.end());
+    putLE<int32_t>(out, (int32_t)names.size());
+    for (size_t i = 0; i < names.size(); ++i) {
+        putLE<int32_t>(out, (int32_t)names[i].size() + 1);
+        out.insert(out.end(), names[i].begin(), names[i].end());
+        out.push_back(0);
+        putLE<int32_t>(out, lens[i]);
+    }
+    auto refId = [&](const std::string& n) -> int32_t {
+        for (size_t i = 0; i < names.size(); ++i)
+            if (names[i] == n) return (int32_t)i;
+        return -1;
+    };
+    for (const std::string& l : body) {
+        std::vector<std::string> f;
+        size_t p = 0;
+        for (;;) {
+            size_t q = l.find('\t', p);
+            f.push_back(l.substr(p, q == std::string::npos ? std::string::npos : q - p));
+            if (q == std::string::npos) break;
+            p = q + 1;
+        }
+        if (f.size() < 11) return false;
+        const int32_t rid = f[2] == "*" ? -1 : refId(f[2]);
+        const int32_t nrid = f[6] == "*" ? -1 : (f[6] == "=" ? rid : refId(f[6]));
+        std::vector<uint32_t> cig;
+        if (f[5] != "*") {
+            uint32_t n = 0;
+            for (char ch : f[5]) {
+                if (ch >= '0' && ch <= '9') { n = n * 10 + (uint32_t)(ch - '0'); continue; }
+                const char* ops = "MIDNSHP=X";
+                const char* w = strchr(ops, ch);
+                if (!w) return false;
+                cig.push_back((n << 4) | (uint32_t)(w - ops));
+                n = 0;
+            }
+        }
+        const std::string seq = f[9] == "*" ? std::string() : f[9];
+        std::vector<uint8_t> rec;
+        putLE<int32_t>(rec, rid);
+        putLE<int32_t>(rec, atoi(f[3].c_str()) - 1);
+        rec.push_back((uint8_t)(f[0].size() + 1));
+        rec.push_back((uint8_t)atoi(f[4].c_str()));
+        putLE<uint16_t>(rec, 4680);
+        putLE<uint16_t>(rec, (uint16_t)cig.size());
+        putLE<uint16_t>(rec, (uint16_t)atoi(f[1].c_str()));
+        putLE<int32_t>(rec, (int32_t)seq.size());
+        putLE<int32_t>(rec, nrid);
+        putLE<int32_t>(rec, atoi(f[7].c_str()) - 1);
+        putLE<int32_t>(rec, atoi(f[8].c_str()));
+        rec.insert(rec.end(), f[0].begin(), f[0].end());
+        rec.push_back(0);
+        for (uint32_t c : cig) putLE<uint32_t>(rec, c);
+        static const char nt16[] = "=ACMGRSVTWYHKDBN";
+        for (size_t i = 0; i < seq.size(); i += 2) {
+            auto code = [&](char ch) -> uint8_t {
+                const char* w = strchr(nt16, toupper((unsigned char)ch));
+                return (uint8_t)(w && *w ? w - nt16 : 15);
+            };
+            rec.push_back((uint8_t)((code(seq[i]) << 4) | (i + 1 < seq.size() ? code(seq[i + 1]) : 0)));
+        }
+        if (f[10] == "*") rec.insert(rec.end(), seq.size(), 0xFF);
+        else {
+            if (f[10].size() != seq.size()) return false;
+            for (char ch : f[10]) rec.push_back((uint8_t)(ch - 33));
+        }
+        for (size_t t = 11; t < f.size(); ++t) {
+            const std::string& g = f[t];
+            if (g.size() < 5 || g[2] != ':' || g[4] != ':') return false;
+            const char ty = g[3];
+            const std::string val = g.substr(5);
+            rec.push_back((uint8_t)g[0]);
+            rec.push_back((uint8_t)g[1]);
+            if (ty == 'A') { rec.push_back('A'); rec.push_back((uint8_t)(val.empty() ? 0 : val[0])); }
+            else if (ty == 'i') {  // the smallest BAM integer type that holds the value
+                const long long v = atoll(val.c_str());
+                if (v >= 0) {
+                    if (v <= 255) { rec.push_back('C'); rec.push_back((uint8_t)v); }
+                    else if (v <= 65535) { rec.push_back('S'); putLE<uint16_t>(rec, (uint16_t)v); }
+                    else { rec.push_back('I'); putLE<uint32_t>(rec, (uint32_t)v); }
+                } else {
+                    if (v >= -128) { rec.push_back('c'); rec.push_back((uint8_t)(int8_t)v); }
+                    else if (v >= -32768) { rec.push_back('s'); putLE<int16_t>(rec, (int16_t)v); }
+                    else { rec.push_back('i'); putLE<int32_t>(rec, (int32_t)v); }
+                }
+            } else if (ty == 'f') { rec.push_back('f'); putLE<float>(rec, (float)atof(val.c_str())); }
+            else if (ty == 'Z' || ty == 'H') { rec.push_back((uint8_t)ty); rec.insert(rec.end(), val.begin(), val.end()); rec.push_back(0); }
+            else if (ty == 'B') {
+                if (val.empty()) return false;
+                const char sub = val[0];
+                std::vector<std::string> items;
+                std::istringstream vs(val.size() > 2 ? val.substr(2) : std::string());
+                std::string it;
+                while (std::getline(vs, it, ',')) items.push_back(it);
+                rec.push_back('B');
+                rec.push_back((uint8_t)sub);
+                putLE<int32_t>(rec, (int32_t)items.size());
+                for (const std::string& x : items) {
+                    switch (sub) {
+                        case 'c': rec.push_back((uint8_t)(int8_t)atoi(x.c_str())); break;
+                        case 'C': rec.push_back((uint8_t)atoi(x.c_str())); break;
+                        case 's': putLE<int16_t>(rec, (int16_t)atoi(x.c_str())); break;
+                        case 'S': putLE<uint16_t>(rec, (uint16_t)atoi(x.c_str())); break;
+                        case 'i': putLE<int32_t>(rec, (int32_t)atoll(x.c_str())); break;
+                        case 'I': putLE<uint32_t>(rec, (uint32_t)atoll(x.c_str())); break;
+                        case 'f': putLE<float>(rec, (float)atof(x.c_str())); break;
+                        default: return false;
+                    }
+                }
+            } else return false;
+        }
+        putLE<int32_t>(out, (int32_t)rec.size());
+        out.insert(out.end(), rec.begin(), rec.end());
+    }
+    return true;
+}
+
 static bool openBam(const std::string& path, BamInput& b) {
     std::vector<uint8_t> raw;
-    if (!readFile(path, raw)) return false;
+    const bool sam = path == "-" || (path.size() > 4 && path.compare(path.size() - 4, 4, ".sam") == 0);
+    if (sam) {
+        if (path == "-") { std::cerr << "Reading from stdin" << std::endl; if (!samToBam(std::cin, raw)) return false; }
+        else { std::ifstream f(path.c_str()); if (!f.good() || !samToBam(f, raw)) return false; }
+    } else if (!readFile(path, raw)) return false;
     if (raw.size() >= 4 && memcmp(raw.data(), "BAM\1", 4) == 0) b.data.swap(raw);
     else if (!inflateBgzf(raw, b.data)) return false;
     const std::vector<uint8_t>& d = b.data;

@@ -183,6 +183,11 @@ def test_sam_on_stdin_gives_the_same_bamqc_as_the_bam_file(tmp_path):
     assert "Reading from stdin" in g2.stderr
     diffs = util.diff_bamqc(tmp_path / "bam.bamqc", tmp_path / "sam.bamqc")
     assert not diffs, "\n".join(diffs)
+    # ... and as the CPU oracle reading the same SAM text with its own, independent SAM reader (oracle/bamqc_oracle.cpp: samToBam)
+    o = subprocess.run([util.ensure_oracle(), "-r", str(fasta), "-c", "chr1,chr2", "-o", str(tmp_path / "oracle_sam.bamqc"), "-"], input=sam, capture_output=True, text=True)
+    assert o.returncode == 0, o.stderr
+    diffs = util.diff_bamqc(tmp_path / "oracle_sam.bamqc", tmp_path / "sam.bamqc")
+    assert not diffs, "\n".join(diffs)
     # the odd tag types of the hand-made records survive the text round trip too
     recs = [util.bam_record(name=f"s{i}", flag=0x63 if i % 2 == 0 else 0x93, pos=1000 + 3 * i, npos=1200, tlen=350,
                             tags=(("RG", "Z", "L1"), ("XB", "B", ("S", [1, 2, 3])), ("NM", "i", i % 4), ("XF", "f", 1.5), ("AS", "s", 120), ("XA", "A", "q")))
@@ -194,6 +199,10 @@ def test_sam_on_stdin_gives_the_same_bamqc_as_the_bam_file(tmp_path):
                         capture_output=True, text=True)
     assert g3.returncode == 0 and g4.returncode == 0, g3.stderr + g4.stderr
     assert not util.diff_bamqc(tmp_path / "h_bam.bamqc", tmp_path / "h_sam.bamqc")
+    o2 = subprocess.run([util.ensure_oracle(), "-r", str(fasta), "-c", "chr1", "-o", str(tmp_path / "h_oracle.bamqc"), "-"], input=util.bam_records_to_sam(stream),
+                        capture_output=True, text=True)
+    assert o2.returncode == 0, o2.stderr
+    assert not util.diff_bamqc(tmp_path / "h_oracle.bamqc", tmp_path / "h_sam.bamqc")
 
 
 def test_records_larger_than_a_framing_window(tmp_path):

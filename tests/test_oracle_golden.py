@@ -37,6 +37,26 @@ def test_oracle_reproduces_reference_bamqc(case, tmp_path, oracle_bin):
     assert not diffs, "\n".join(diffs)
 
 
+@pytest.mark.parametrize("case", ["stress", "two_lanes_kq"])
+def test_oracle_sam_reader_reproduces_reference_bamqc(case, tmp_path, oracle_bin):
+    """The oracle's own SAM reader (samToBam; `bamqualcheck ... -`, src/bamqualcheck.cpp:252-260): the golden BAM as SAM
+    text on stdin gives the golden .bamqc that the reference's code wrote for the BAM file."""
+    import zlib
+    raw = bytearray()
+    b = open(os.path.join(GOLD, case + ".bam"), "rb").read()
+    for p in util.bgzf_block_starts(b):
+        xlen = int.from_bytes(b[p + 10:p + 12], "little")
+        bsize = int.from_bytes(b[p + 16:p + 18], "little") + 1
+        raw += zlib.decompress(b[p + 12 + xlen:p + bsize - 8], -15)
+    sam = util.bam_records_to_sam(bytes(raw))
+    out = tmp_path / "o.bamqc"
+    r = subprocess.run([oracle_bin, "-r", os.path.join(GOLD, "genome.fa"), "-o", str(out)] + CASES[case] + ["-"], input=sam, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Reading from stdin" in r.stderr
+    diffs = util.diff_bamqc(os.path.join(GOLD, case + ".bamqc"), out)
+    assert not diffs, "\n".join(diffs)
+
+
 def test_bamqc_shape():
     """80 lines per lane at defaults."""
     lines = open(os.path.join(GOLD, "standard.bamqc")).read().strip().split("\n")
