@@ -172,6 +172,8 @@ struct bqc_engine {
     uint64_t* d_ref_len = nullptr;
     uint8_t* d_main_chrom = nullptr;
     HashTables* d_hash = nullptr;  // one per k
+    char* d_lane_names = nullptr;      // @RG IDs back to back + their offsets (k_frame_lanes)
+    uint32_t* d_lane_off = nullptr;
     std::vector<uint32_t*> ref_bufs;
     std::vector<uint64_t> ref_len;
     cudaStream_t compute = nullptr, copy = nullptr, covs = nullptr;  // covs: coverage scatter + flush (HBM bound) overlaps the table kernels
@@ -342,6 +344,8 @@ extern "C" void bqc_destroy(bqc_engine* e) {
     cudaFree(e->d_ref_len);
     cudaFree(e->d_main_chrom);
     cudaFree(e->d_hash);
+    cudaFree(e->d_lane_names);
+    cudaFree(e->d_lane_off);
     if (e->copied) cudaEventDestroy(e->copied);
     if (e->cov_done) cudaEventDestroy(e->cov_done);
     if (e->cov_go) cudaEventDestroy(e->cov_go);
@@ -475,6 +479,15 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         if (cfg->n_ref) CU(cudaMemcpy(e->d_main_chrom, e->main_chrom.data(), cfg->n_ref, cudaMemcpyHostToDevice));
         e->ref_bufs.assign(nref, nullptr);
         e->ref_len.assign(nref, 0);
+        if (e->n_lanes > 1) {
+            std::string cat;
+            std::vector<uint32_t> off(1, 0);
+            for (const std::string& id : e->lane_ids) { cat += id; off.push_back((uint32_t)cat.size()); }
+            CU(cudaMalloc(&e->d_lane_names, std::max<size_t>(1, cat.size())));
+            CU(cudaMemcpy(e->d_lane_names, cat.data(), cat.size(), cudaMemcpyHostToDevice));
+            CU(cudaMalloc(&e->d_lane_off, off.size() * 4));
+            CU(cudaMemcpy(e->d_lane_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+        }
         if (cfg->n_k) {
             std::vector<HashTables> ht(cfg->n_k);
             for (int i = 0; i < cfg->n_k; ++i) build_hash_tables(cfg->seed, cfg->klist[i], ht[i]);
@@ -489,8 +502,9 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         CU(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kInflateStreams * sizeof(InflateTabs))));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->inflate_bps, k_inflate, (int)kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs)));
         if (e->inflate_bps < 1) e->inflate_bps = 1;
-        CU(cudaFuncSetAttribute(k_stats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CU(cudaFuncSetAttribute(k_stats<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(k_stats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(k_stats<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(k_stats<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CU(cudaFuncSetAttribute(k_eightmer, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CU(cudaFuncSetAttribute(k_sketch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CU(cudaFuncSetAttribute(k_cov_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCovBlockSmem));
@@ -892,8 +906,8 @@ static int batch_launch_setup(bqc_engine* e, const DeviceBatch& d, BatchLaunch& 
     int bps = 0;
     BL.staged = e->tune_stats_stage != 0;
     if (BL.staged) {  // the per-warp staging areas on top of the tables: only while both fit
-        BL.stats_smem = (size_t)S.stage * 4 + (size_t)(kStatsThreads / 32) * kStatsStage;
-        if (BL.stats_smem > 227u * 1024u || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats<true>, (int)kStatsThreads, BL.stats_smem) != cudaSuccess || bps < 1) {
+        BL.stats_smem = (size_t)S.stage * 4 + (size_t)(kStatsThreads / 32) * kStatsStage + kStatsMbarBytes;
+        if (BL.stats_smem > 227u * 1024u || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats<1>, (int)kStatsThreads, BL.stats_smem) != cudaSuccess || bps < 1) {
             cudaGetLastError();
             BL.staged = false;
             bps = 0;
@@ -901,7 +915,7 @@ static int batch_launch_setup(bqc_engine* e, const DeviceBatch& d, BatchLaunch& 
     }
     if (!BL.staged) {
         BL.stats_smem = (size_t)S.total * 4;
-        if (BL.stats_smem <= 227u * 1024u) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats<false>, (int)kStatsThreads, BL.stats_smem));
+        if (BL.stats_smem <= 227u * 1024u) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats<0>, (int)kStatsThreads, BL.stats_smem));
     }
     if (bps < 1) { set_error(e, "k_stats does not fit: %zu bytes of shared memory", BL.stats_smem); return BQC_ERR_ARG; }
     if (e->tune_stats_bps > 0 && e->tune_stats_bps < bps) bps = e->tune_stats_bps;
@@ -952,7 +966,7 @@ static int launch_cov(bqc_engine* e, const DeviceBatch& d, const BatchLaunch& BL
         for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
             CovCarry* carry = e->d_cov_carry + lane;
             CU(cudaMemsetAsync(e->d_cov_scratch, 0, e->cov_ctl_bytes, cs));
-            k_cov_prep<<<(int)std::min<uint32_t>(nprep, (uint32_t)e->n_sm * 8u), 256, 0, cs>>>(BL.E, B, lane, S, carry, e->cov_deferred ? 1u : 0u);
+            k_cov_prep<<<(int)std::min<uint32_t>(nprep, (uint32_t)e->n_sm * 2u), kCovPrepThreads, 0, cs>>>(BL.E, B, lane, S, carry, e->cov_deferred ? 1u : 0u);
             e->launches += 1;
             if (e->cov_deferred) continue;
             rc = launch_cov_resolve(e, lane, B, n, false);
@@ -982,8 +996,9 @@ static int launch_tables(bqc_engine* e, const DeviceBatch& d, const BatchLaunch&
         int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * BL.bps);
         {
             ProfScope prof(e, 0);
-            if (BL.staged) k_stats<true><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
-            else k_stats<false><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
+            if (BL.staged && e->tune_stats_stage == 2) k_stats<2><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
+            else if (BL.staged) k_stats<1><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
+            else k_stats<0><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
         }
         int g8 = (int)std::min<uint64_t>((n + kEightThreads - 1) / kEightThreads, (uint64_t)e->n_sm);
         if (g8 < 1) g8 = 1;
@@ -1125,6 +1140,10 @@ static int stream_stage_a(bqc_engine* e, const bqc_engine::Task& t) {
     k_frame_repair<<<1, 32, 0, e->frames>>>(d.bytes, s.d_frame, e->cfg.n_ref, e->d_main_chrom, d.offsets, nullptr, rec_cap);
     k_frame_emit<<<nblk, kFrameThreads, 0, e->frames>>>(d.bytes, s.d_frame, e->cfg.n_ref, e->d_main_chrom, nwin, s.d_ws, s.d_wc, s.d_bbase, d.offsets, nullptr);
     e->launches += 10;
+    if (e->n_lanes > 1) {  // several read groups: the lane of every record, from its RG tag
+        k_frame_lanes<<<e->n_sm * 4, 256, 0, e->frames>>>(d.bytes, s.d_frame, d.offsets, e->d_lane_names, e->d_lane_off, e->n_lanes, d.rec_lane);
+        e->launches += 1;
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(s.h_frame, s.d_frame, sizeof(FrameResult), cudaMemcpyDeviceToHost, e->frames));
     CU(cudaEventRecord(s.framed, e->frames));
@@ -1330,7 +1349,7 @@ static int submit_common(bqc_engine* e, const void* data, size_t n_bytes, const 
     rc = wait_slot(e, s);
     if (rc) return rc;
     const uint8_t* src = (const uint8_t*)data;
-    const bool on_device = !record_offsets && e->device_framing && e->n_lanes == 1;
+    const bool on_device = !record_offsets && e->device_framing;
     if (on_device) {
         if (n_bytes == 0 && !(stream && last)) return 0;
         bqc_engine::Task t;
@@ -1421,7 +1440,7 @@ extern "C" int bqc_submit_bgzf(bqc_engine* e, const void* data, size_t n_bytes, 
     if (e->async_rc) return e->async_rc;
     CU(cudaSetDevice(e->cfg.device));
     const uint8_t* src = (const uint8_t*)data;
-    const bool on_device = e->device_framing && e->n_lanes == 1;
+    const bool on_device = e->device_framing;
     size_t p = 0;
     bool any = false;
     while (p < n_bytes || (last && !any)) {
@@ -1485,7 +1504,7 @@ extern "C" int bqc_submit_bgzf(bqc_engine* e, const void* data, size_t n_bytes, 
 }
 
 extern "C" int bqc_stream_unknown_start(bqc_engine* e) {
-    if (!(e->device_framing && e->n_lanes == 1)) { set_error(e, "bqc_stream_unknown_start needs device framing (single read group)"); return BQC_ERR_ARG; }
+    if (!e->device_framing) { set_error(e, "bqc_stream_unknown_start needs device framing"); return BQC_ERR_ARG; }
     if (e->records_seen || e->last_stream_slot >= 0) { set_error(e, "bqc_stream_unknown_start: call it before the first submission"); return BQC_ERR_ARG; }
     e->stream_seek = true;
     e->stream_skipped = -1;

@@ -12,11 +12,12 @@
 //   k_cov_codes   with the state at block entry known: state of every record in closed form, its virtual
 //                 coordinate X = 1000 * window + pos as a prefix sum (look-back across blocks), covered interval
 //                 [X + a, X + b) clipped where the reference's writes leave its two windows;
-//   k_cov_tiles   depth histogram: the virtual axis is cut into tiles of 8192 positions, a CTA builds the tile's
-//                 difference array in shared memory from the records that overlap it (a record only writes into its
-//                 two windows and window starts never decrease, even for unsorted input, so those are the records
-//                 whose window start lies in the tile or in the one before), prefix-sums it and adds run lengths of
-//                 equal depth to poscov[min(depth, 100)];
+//   k_cov_tiles   depth histogram: the virtual axis is cut into tiles of 1024 positions, one warp per tile; the warp
+//                 builds the tile's difference array in shared memory from the records that overlap it (a record only
+//                 writes into its two windows and window starts never decrease, even for unsorted input, so those
+//                 are the records whose window start lies in the tile or in the two before), marks the positions that
+//                 hold an event in a bitmap, prefix-sums the events and adds run lengths of equal depth to
+//                 poscov[min(depth, 100)] -- it touches the events, not the positions;
 //   k_cov_carry   the two windows that are still open after the batch's last record (the reference's v1 | v2)
 //                 become a 2001-entry difference array that the next batch (or k_cov_final) starts from.
 // There is no depth array in global memory and no host work: cost is proportional to the records plus 1/32 of the
@@ -32,6 +33,8 @@ static const uint32_t kCovTile = 1024;      // virtual positions per tile: one w
 static const uint32_t kCovTileThreads = 256;
 static const uint32_t kCovD = 2048;         // entries of a carry difference array (2001 used)
 static const uint32_t kCovPrepTile = 1024;  // records per compaction tile
+static const uint32_t kCovPrepPer = 1;      // records per thread (one: every header is its own dependent load chain)
+static const uint32_t kCovPrepThreads = kCovPrepTile / kCovPrepPer;
 enum { COV_CLOSED = 0, COV_CONST = 1, COV_TABLE = 2 };
 
 struct CovCarry {  // per lane
@@ -167,7 +170,7 @@ __device__ __forceinline__ void cov_walk_cigar(const uint8_t* p, F emit) {
 // not duplicate, rID in the -c set) and their (rid, begin, interval), compacted in file order.
 // ------------------------------------------------------------------------------------------------
 // append != 0 (shard mode): the records are added behind the carry->nq already collected instead of replacing them.
-__global__ void __launch_bounds__(256) k_cov_prep(EngineView E, BatchView B, uint32_t lane, CovScratch S, CovCarry* carry, uint32_t append) {
+__global__ void __launch_bounds__(kCovPrepThreads) k_cov_prep(EngineView E, BatchView B, uint32_t lane, CovScratch S, CovCarry* carry, uint32_t append) {
     __shared__ uint32_t ws[33];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
@@ -178,11 +181,11 @@ __global__ void __launch_bounds__(256) k_cov_prep(EngineView E, BatchView B, uin
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= ntile) break;
-        int32_t rid[4];
-        uint32_t b[4], iv[4], flags = 0;
-        const uint32_t r0 = tile * kCovPrepTile + 4u * threadIdx.x;
+        int32_t rid[kCovPrepPer];
+        uint32_t b[kCovPrepPer], iv[kCovPrepPer], flags = 0;
+        const uint32_t r0 = tile * kCovPrepTile + kCovPrepPer * threadIdx.x;
 #pragma unroll
-        for (uint32_t k = 0; k < 4; ++k) {
+        for (uint32_t k = 0; k < kCovPrepPer; ++k) {
             const uint32_t r = r0 + k;
             rid[k] = -1; b[k] = 0; iv[k] = 0;
             if (r >= B.n_records) continue;
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(256) k_cov_prep(EngineView E, BatchView B, uin
         __syncthreads();
         uint32_t o = (uint32_t)s_base + excl;
 #pragma unroll
-        for (uint32_t k = 0; k < 4; ++k)
+        for (uint32_t k = 0; k < kCovPrepPer; ++k)
             if (flags & (1u << k)) {
                 S.q_rid[o] = rid[k]; S.q_b[o] = b[k]; S.q_iv[o] = iv[k]; S.q_rec[o] = r0 + k;
                 ++o;
@@ -552,24 +555,26 @@ __device__ __forceinline__ int32_t cov_warp_tile(int32_t* diff, const uint32_t* 
 // adds the covered interval(s) of compact record j, clipped to [T0, T1), to a difference array over [T0, T1] and marks
 // the positions in the bitmap (bm may be NULL)
 __device__ __forceinline__ void cov_tile_add(const CovScratch& S, const BatchView& B, uint32_t j, unsigned long long T0, unsigned long long T1, int32_t* diff, uint32_t* bm) {
-    const unsigned long long X = S.base[j];
+    const long long rel = (long long)(S.base[j] - T0);        // begin of the record relative to the range (may be negative)
+    const int32_t len = (int32_t)(T1 - T0);
+    if (rel >= (long long)len || rel < -4096) return;           // an interval reaches at most 2000 positions
+    const int32_t r = (int32_t)rel;
     const uint32_t code = S.ab[j];
-    auto add = [&](unsigned long long A, unsigned long long Bv) {
-        if (Bv <= T0 || A >= T1 || A >= Bv) return;
-        const uint32_t s = (uint32_t)((A > T0 ? A : T0) - T0);
+    auto add = [&](int32_t a, int32_t b) {                     // [a, b) relative to the range
+        if (b <= 0 || a >= len || a >= b) return;
+        const uint32_t s = (uint32_t)max(a, 0);
         atomicAdd(diff + s, 1);
         if (bm) atomicOr(bm + (s >> 5), 1u << (s & 31u));
-        if (Bv < T1) {
-            const uint32_t e = (uint32_t)(Bv - T0);
-            atomicAdd(diff + e, -1);
-            if (bm) atomicOr(bm + (e >> 5), 1u << (e & 31u));
+        if (b < len) {
+            atomicAdd(diff + b, -1);
+            if (bm) atomicOr(bm + ((uint32_t)b >> 5), 1u << ((uint32_t)b & 31u));
         }
     };
     if (!(code & kCovComplex)) {
-        add(X + (code & 2047u), X + ((code >> 11) & 2047u));
+        add(r + (int32_t)(code & 2047u), r + (int32_t)((code >> 11) & 2047u));
     } else {
         const uint32_t lim = 2u * kCovV - (code & 2047u);
-        cov_walk_cigar(B.bytes + B.offsets[S.q_rec[j]], [&](uint32_t s, uint32_t e) { add(X + min(s, lim), X + min(e, lim)); });
+        cov_walk_cigar(B.bytes + B.offsets[S.q_rec[j]], [&](uint32_t s, uint32_t e) { add(r + (int32_t)min(s, lim), r + (int32_t)min(e, lim)); });
     }
 }
 
@@ -590,13 +595,19 @@ __global__ void __launch_bounds__(kCovTileThreads) k_cov_tiles(BatchView B, CovS
     for (uint32_t i = threadIdx.x; i < 104u; i += blockDim.x) hist[i] = 0;
     for (uint32_t i = lane; i < kCovTile; i += 32u) diff[i] = 0;
     __syncthreads();
-    for (uint32_t t = blockIdx.x * (kCovTileThreads / 32u) + w; t < ntiles; t += gridDim.x * (kCovTileThreads / 32u)) {
+    const uint32_t tstep = gridDim.x * (kCovTileThreads / 32u);
+    uint32_t t = blockIdx.x * (kCovTileThreads / 32u) + w;
+    uint32_t jlo = 0, jhi = 0;
+    if (t < ntiles) { jlo = t >= 2u ? S.first_rec[t - 2u] : 0u; jhi = t + 1u <= vt_last ? S.first_rec[t + 1u] : nq; }
+    for (; t < ntiles; t += tstep) {
         const unsigned long long T0 = xc + (unsigned long long)t * kCovTile;
         const unsigned long long T1 = min(T0 + kCovTile, xl);
         const uint32_t len = (uint32_t)(T1 - T0);
         bm[lane] = 0;
-        const uint32_t jlo = t >= 2u ? S.first_rec[t - 2u] : 0u;
-        const uint32_t jhi = t + 1u <= vt_last ? S.first_rec[t + 1u] : nq;
+        // the record range of this warp's next tile is fetched while this one is worked on
+        const uint32_t tn = t + tstep;
+        uint32_t njlo = 0, njhi = 0;
+        if (tn < ntiles) { njlo = S.first_rec[tn - 2u]; njhi = tn + 1u <= vt_last ? S.first_rec[tn + 1u] : nq; }
         __syncwarp();
         for (uint32_t j = jlo + lane; j < jhi; j += 32u) cov_tile_add(S, B, j, T0, T1, diff, bm);
         int32_t d0 = 0;
@@ -613,6 +624,7 @@ __global__ void __launch_bounds__(kCovTileThreads) k_cov_tiles(BatchView B, CovS
         }
         __syncwarp();
         cov_warp_tile(diff, bm, len, d0, hist);
+        jlo = njlo; jhi = njhi;
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < 101u; i += blockDim.x)

@@ -317,6 +317,56 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame_emit(const uint8_t* __r
     if (threadIdx.x == 0 && s_max) atomicMax(&fr->max_lseq, s_max);
 }
 
+// Lane (read group) of every framed record: the value of the first RG tag is looked up in the table of @RG IDs
+// (getLane, src/bamqualcheck.cpp:72-100; a value that is not in the header maps to lane 0, like the reference's
+// laneNames[...] which default-inserts 0; a record without RG:Z keeps lane 0 and k_stats reports it).  names: the lane
+// ids back to back, name_off[l] .. name_off[l + 1] delimits id l; later duplicates win like the map assignment.
+__global__ void __launch_bounds__(256) k_frame_lanes(const uint8_t* __restrict__ d, const FrameResult* __restrict__ fr, const uint32_t* __restrict__ offsets,
+                                                     const char* __restrict__ names, const uint32_t* __restrict__ name_off, uint32_t n_lanes, uint8_t* __restrict__ lane_out) {
+    const uint32_t n = fr->n_records;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const uint32_t off = offsets[r], end = offsets[r + 1];
+        const uint8_t* p = d + off;
+        uint32_t lane = 0;
+        if (end - off >= 36u) {
+            const uint32_t lname = ldu32(p + 12) & 255u, ncig = ldu32(p + 16) & 0xFFFFu;
+            const int32_t lseq = (int32_t)ldu32(p + 20);
+            const uint32_t ls = lseq > 0 ? (uint32_t)lseq : 0u;
+            uint64_t q = 36ull + lname + 4ull * ncig + (ls + 1u) / 2u + ls;
+            const uint64_t avail = end - off;
+            while (q + 3 <= avail) {
+                const uint32_t k0 = ldg8(p + q), k1 = ldg8(p + q + 1), ty = ldg8(p + q + 2);
+                q += 3;
+                uint64_t sz;
+                if (ty == 'A' || ty == 'c' || ty == 'C') sz = 1;
+                else if (ty == 's' || ty == 'S') sz = 2;
+                else if (ty == 'i' || ty == 'I' || ty == 'f') sz = 4;
+                else if (ty == 'Z' || ty == 'H') { uint64_t z = q; while (z < avail && ldg8(p + z) != 0) ++z; sz = z - q + 1; }
+                else if (ty == 'B') {
+                    if (q + 5 > avail) break;
+                    const uint32_t sub = ldg8(p + q), cnt = ldu32(p + q + 1);
+                    sz = 5ull + (uint64_t)cnt * ((sub == 'c' || sub == 'C') ? 1u : (sub == 's' || sub == 'S') ? 2u : 4u);
+                } else break;
+                if (k0 == 'R' && k1 == 'G') {
+                    if (ty == 'Z') {
+                        const uint32_t vlen = (uint32_t)(sz - 1);   // without the NUL
+                        for (uint32_t l = 0; l < n_lanes; ++l) {
+                            const uint32_t a = name_off[l], m = name_off[l + 1] - a;
+                            if (m != vlen) continue;
+                            uint32_t i = 0;
+                            while (i < m && (uint32_t)(uint8_t)names[a + i] == ldg8(p + q + i)) ++i;
+                            if (i == m) lane = l;
+                        }
+                    }
+                    break;   // the first RG tag decides (:86)
+                }
+                q += sz;
+            }
+        }
+        lane_out[r] = (uint8_t)lane;
+    }
+}
+
 // Prepare the frame header of the next buffer: carry the partial record [end, total) of the previous buffer (if
 // any) in front of kFrameHead and set start/total.  One CTA.
 // `skip`: bytes at the front of the new data that are not records (the BAM header in the first buffer of a file).

@@ -287,15 +287,41 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
+// Bulk asynchronous copy global -> shared (the TMA unit's 1-D mode: cp.async.bulk, SASS UBLKCP) that signals an mbarrier
+// with the number of bytes it delivered.  One lane issues the copy of the warp's whole record span; it replaces ~580
+// 16-byte cp.async (LDGSTS) per span, 18 per lane plus their address arithmetic.  (STAGE == 2; measured SLOWER than the
+// LDGSTS form here, 4.7 vs 4.15 ms per 10 M records: the span cannot be double-buffered within the shared memory that
+// two CTAs per SM leave, and one bulk copy per warp has a longer latency than 18 independent 16-byte copies per lane.)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
 static const uint32_t kStatsStage = 10240;   // bytes of staging per warp: 32 standard 2x150 bp records are 9280 bytes
 static const uint32_t kStatsStageTail = 64;  // the decoders read up to a few words past the end of a record
+static const uint32_t kStatsMbarBytes = (kStatsThreads / 32) * 8;   // one mbarrier per warp, behind the staging areas
 
 // The 32 records of a warp are one contiguous byte span of the batch.  The warp copies the span into its staging area
-// with coalesced 16-byte async copies (one round trip to HBM with ~18 copies in flight per lane) and every phase then
-// reads record bytes from shared memory; without this the kernel waited on dependent, unaligned global loads (ncu:
-// half of all stall samples).  A span larger than the stage is processed in pieces; a single record larger than the
-// stage is read straight from global memory.
-template <bool STAGE>
+// -- STAGE 1: coalesced 16-byte async copies (LDGSTS, ~18 in flight per lane, one round trip to HBM); STAGE 2: one bulk
+// copy by the TMA unit (cp.async.bulk + mbarrier) -- and every phase then reads record bytes from shared memory;
+// without staging (STAGE 0) the kernel waits on dependent, unaligned global loads (ncu: half of all stall samples).  A
+// span larger than the stage is processed in pieces; a single record larger than the stage is read straight from
+// global memory.
+template <int STAGE>
 __global__ void __launch_bounds__(kStatsThreads, STAGE ? 2 : 4) __maxnreg__(STAGE ? 96 : 64) k_stats(EngineView E, BatchView B, uint32_t lane) {
     extern __shared__ __align__(16) uint32_t sm[];
     const StatsSmem S = stats_smem_layout(B.cycb, E.insert_smem);
@@ -305,6 +331,12 @@ __global__ void __launch_bounds__(kStatsThreads, STAGE ? 2 : 4) __maxnreg__(STAG
     uint64_t* G = E.counters + (uint64_t)lane * L.lane_stride;
     const uint32_t cycb = B.cycb;
     const uint32_t lane_id = threadIdx.x & 31u;
+    uint32_t phase = 0;   // parity of this warp's mbarrier
+    if (STAGE == 2) {
+        if (lane_id == 0) mbar_init((uint32_t)__cvta_generic_to_shared((uint8_t*)(sm + S.stage) + (kStatsThreads / 32) * kStatsStage) + (threadIdx.x >> 5) * 8u, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
 
     for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < B.n_records; r0 += gridDim.x * blockDim.x) {
         const uint32_t n_here = min(32u, B.n_records - r0);
@@ -316,6 +348,7 @@ __global__ void __launch_bounds__(kStatsThreads, STAGE ? 2 : 4) __maxnreg__(STAG
         }
         uint8_t* stage = (uint8_t*)(sm + S.stage) + (threadIdx.x >> 5) * kStatsStage;
         const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+        const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared((uint8_t*)(sm + S.stage) + (kStatsThreads / 32) * kStatsStage) + (threadIdx.x >> 5) * 8u;
         uint32_t sub = 0;
         while (sub < n_here) {
             const uint32_t lo = __shfl_sync(0xFFFFFFFFu, off, sub) & ~15u;
@@ -328,9 +361,18 @@ __global__ void __launch_bounds__(kStatsThreads, STAGE ? 2 : 4) __maxnreg__(STAG
             }
             const uint32_t hi = __shfl_sync(0xFFFFFFFFu, end, sub + m - 1);
             const uint32_t nvec = (hi + 48u - lo + 15u) >> 4;
-            for (uint32_t v = lane_id; v < nvec; v += 32u) cp_async16(stage_s + 16u * v, B.bytes + lo + 16u * v);
-            cp_async_wait_all();
-            __syncwarp();
+            if (STAGE == 2) {
+                if (lane_id == 0) {
+                    mbar_expect_tx(bar_s, nvec << 4);
+                    bulk_copy_g2s(stage_s, B.bytes + lo, nvec << 4, bar_s);
+                }
+                mbar_wait(bar_s, phase);
+                phase ^= 1u;
+            } else {
+                for (uint32_t v = lane_id; v < nvec; v += 32u) cp_async16(stage_s + 16u * v, B.bytes + lo + 16u * v);
+                cp_async_wait_all();
+                __syncwarp();
+            }
             stats_records<SMem>(E, B, lane, sm, S, r0 + lane_id, fits, stage + (off - lo), end - off);
             __syncwarp();  // every lane is done with the stage before it is refilled
             sub += m;

@@ -90,14 +90,15 @@ int bqc_submit(bqc_engine* e, const void* data, size_t n_bytes, const uint64_t* 
  * readRecord() hides at src/bamqualcheck.cpp:306).  The partial record at the end of a chunk is carried into the
  * next one on the device; the records are framed on the device (speculated window starts, verified against the
  * sequential chain; kernel_frame.cuh).  `last` != 0 marks the end of the stream: a trailing partial record is then
- * the reference's "Could not read record" error (BQC_ERR_BAD_RECORD).  With several read groups, or with
- * BQC_HOST_FRAMING=1 in the environment, the host framer is used instead (same results). */
+ * the reference's "Could not read record" error (BQC_ERR_BAD_RECORD).  With several read groups the lane of every
+ * record is looked up from its RG tag on the device as well.  BQC_HOST_FRAMING=1 in the environment switches to the
+ * host framer (same results). */
 int bqc_submit_stream(bqc_engine* e, const void* data, size_t n_bytes, int last);
 /* Submit whole BGZF blocks (the compressed bytes of a .bam file) -- SURVEY section 8f rank 1: the blocks are copied
  * to the device as they are, inflated there (one warp per block, kernel_inflate.cuh) and the inflated stream then
  * takes the bqc_submit_stream path on the device.  data must start at a block boundary and hold whole blocks; any
  * size (the call splits it to the staging capacity).  skip_bytes: inflated bytes at the front that are not records
- * (the BAM header, for the first call of a file).  With several read groups or BQC_HOST_FRAMING=1 the blocks are
+ * (the BAM header, for the first call of a file).  With BQC_HOST_FRAMING=1 the blocks are
  * inflated with zlib on the host threads instead (same results). */
 int bqc_submit_bgzf(bqc_engine* e, const void* data, size_t n_bytes, size_t skip_bytes, int last);
 /* A later piece of a file that was cut at BGZF block boundaries begins somewhere inside a record.  Called before the

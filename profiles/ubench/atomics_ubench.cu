@@ -28,6 +28,23 @@ __global__ void k_smem(uint32_t* out, int iters, int bins){
   if(acc==0xdeadbeef) out[0]=acc;
 }
 
+// 64-bit shared-memory REDs (one word carries two 32-bit counters): spread random / conflict-free 8-byte banks
+template<int MODE>
+__global__ void k_smem64(uint32_t* out, int iters, int bins){
+  extern __shared__ unsigned long long sm64[];
+  for(int i=threadIdx.x;i<bins;i+=blockDim.x) sm64[i]=0;
+  __syncthreads();
+  uint32_t s = (blockIdx.x*blockDim.x+threadIdx.x)*2654435761u+12345u;
+  for(int i=0;i<iters;i++){
+    uint32_t r = xs(s);
+    uint32_t idx = MODE==0 ? r % bins : (threadIdx.x&31) + 32*((r>>5)%(bins/32));
+    atomicAdd(&sm64[idx],(1ull<<32)|(r&63));
+  }
+  __syncthreads();
+  unsigned long long acc=0; for(int i=threadIdx.x;i<bins;i+=blockDim.x) acc+=sm64[i];
+  if(acc==0xdeadbeef) out[0]=(uint32_t)acc;
+}
+
 template<typename T, int MODE>
 __global__ void k_glob(T* tab, int iters, uint32_t mask){
   uint32_t s = (blockIdx.x*blockDim.x+threadIdx.x)*2654435761u+777u;
@@ -81,6 +98,8 @@ int main(){
     ms=timeit([&]{k_smem<0><<<blocks,tpb,4096*4>>>(d,iters,1024);}); printf("smem atomic spread 1024 bins  tpb=%d: %.1f Gops/s\n",tpb,ops/ms/1e6);
     ms=timeit([&]{k_smem<0><<<blocks,tpb,4096*4>>>(d,iters,4096);}); printf("smem atomic spread 4096 bins  tpb=%d: %.1f Gops/s\n",tpb,ops/ms/1e6);
     ms=timeit([&]{k_smem<3><<<blocks,tpb,4096*4>>>(d,iters,4096);}); printf("smem atomic conflict-free     tpb=%d: %.1f Gops/s\n",tpb,ops/ms/1e6);
+    ms=timeit([&]{k_smem64<0><<<blocks,tpb,4096*8>>>(d,iters,4096);}); printf("smem atomic u64 spread 4096    tpb=%d: %.1f Gops/s\n",tpb,ops/ms/1e6);
+    ms=timeit([&]{k_smem64<1><<<blocks,tpb,4096*8>>>(d,iters,4096);}); printf("smem atomic u64 conflict-free  tpb=%d: %.1f Gops/s\n",tpb,ops/ms/1e6);
     ms=timeit([&]{k_smem<1><<<blocks,tpb,4096*4>>>(d,iters,1024);}); printf("smem atomic 1 hot bin         tpb=%d: %.1f Gops/s\n",tpb,ops/ms/1e6);
     ms=timeit([&]{k_smem<2><<<blocks,tpb,4096*4>>>(d,iters,1024);}); printf("smem atomic 4 hot bins        tpb=%d: %.1f Gops/s\n",tpb,ops/ms/1e6);
     ms=timeit([&]{k_glob<uint32_t,0><<<blocks,tpb>>>(d,iters,65535);}); printf("global RED u32 random 64K bins tpb=%d: %.1f Gops/s\n",tpb,ops/ms/1e6);

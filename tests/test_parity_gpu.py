@@ -151,9 +151,18 @@ def test_stream_host_framing_switch(tmp_path, monkeypatch):
     _roundtrip(tmp_path, synth.Library(seed=26, n_pairs=5000), mode="stream", chunk_bytes=300007, expect_repaired=False)
 
 
-def test_stream_two_lanes_uses_host_framer(tmp_path):
+def test_stream_two_lanes_on_the_device_framer(tmp_path):
+    """Several read groups: the lane of every record comes from its RG tag on the device (k_frame_lanes), so the
+    stream keeps device-side framing."""
     from bamqc_b200 import synth
-    _roundtrip(tmp_path, synth.Library(seed=27, n_pairs=5000, n_lanes=2), mode="stream", chunk_bytes=400009)
+    _roundtrip(tmp_path, synth.Library(seed=27, n_pairs=5000, n_lanes=2), mode="stream", chunk_bytes=400009, expect_repaired=False)
+
+
+def test_stream_three_lanes_with_host_framing_switch(tmp_path, monkeypatch):
+    """BQC_HOST_FRAMING=1: the host framer and the host RG lookup (same results)."""
+    from bamqc_b200 import synth
+    monkeypatch.setenv("BQC_HOST_FRAMING", "1")
+    _roundtrip(tmp_path, synth.Library(seed=29, n_pairs=4000, n_lanes=3), mode="stream", chunk_bytes=500009)
 
 
 def test_stream_truncated_record_is_an_error(tmp_path):
