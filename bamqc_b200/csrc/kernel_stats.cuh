@@ -212,8 +212,10 @@ __device__ __forceinline__ void stats_records(const EngineView& E, const BatchVi
                     for (uint32_t j = 0; j < 8u; ++j) {
                         const uint32_t d = (D >> (4u * j)) & 15u;
                         const uint32_t q = ((j < 4u ? qlo : qhi) >> (8u * (j & 3u))) & 255u;
-                        red_shared_inc(ca + d * rowb + 4u * j);
-                        red_shared_add(ca + PC_QUAL * rowb + 4u * j, q);
+                        // ONE shared atomic per base: the count of (base, cycle) in the low 12 bits of the cell, the quality of the
+                        // same base in the 20 bits above (qualcount[cycle] is the sum over the five base rows).  The cells are
+                        // emptied every kStatsUnpackEvery CTA iterations, before either field can run over (k_stats, unpack).
+                        red_shared_add(ca + d * rowb + 4u * j, (q << 12) | 1u);
                     }
                 }
             }
@@ -311,6 +313,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// Packed per-cycle cells (count : 12 | quality sum : 20): a CTA looks at 256 records per iteration of its loop, so a cell
+// gains at most 256 counts and 256 x 255 of quality per iteration; 15 iterations stay below 4096 and 2^20.
+static const uint32_t kStatsUnpackEvery = 4095u / kStatsThreads;
 static const uint32_t kStatsStage = 10240;   // bytes of staging per warp: 32 standard 2x150 bp records are 9280 bytes
 static const uint32_t kStatsStageTail = 64;  // the decoders read up to a few words past the end of a record
 static const uint32_t kStatsMbarBytes = (kStatsThreads / 32) * 8;   // one mbarrier per warp, behind the staging areas
@@ -322,7 +327,7 @@ static const uint32_t kStatsMbarBytes = (kStatsThreads / 32) * 8;   // one mbarr
 // span larger than the stage is processed in pieces; a single record larger than the stage is read straight from
 // global memory.
 template <int STAGE>
-__global__ void __launch_bounds__(kStatsThreads, STAGE ? 2 : 4) __maxnreg__(STAGE ? 96 : 64) k_stats(EngineView E, BatchView B, uint32_t lane) {
+__global__ void __launch_bounds__(kStatsThreads, kStatsThreads > 256 ? 1 : (STAGE ? 2 : 4)) __maxnreg__(kStatsThreads > 256 ? 96 : (STAGE ? 96 : 64)) k_stats(EngineView E, BatchView B, uint32_t lane) {
     extern __shared__ __align__(16) uint32_t sm[];
     const StatsSmem S = stats_smem_layout(B.cycb, E.insert_smem);
     for (uint32_t i = threadIdx.x; i < S.total; i += blockDim.x) sm[i] = 0;
@@ -338,7 +343,38 @@ __global__ void __launch_bounds__(kStatsThreads, STAGE ? 2 : 4) __maxnreg__(STAG
         __syncthreads();
     }
 
-    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < B.n_records; r0 += gridDim.x * blockDim.x) {
+    // the packed per-cycle cells -> counts to the global rows, quality to the CTA's 32-bit quality row; cells zeroed
+    auto unpack = [&]() {
+        const uint32_t rowp = stats_row_words(cycb);
+        for (uint32_t m = 0; m < 2; ++m) {
+            uint64_t* GMm = G + L.o_mate0 + m * L.mate_stride;
+            uint32_t* base = sm + S.pc + m * (PC_ROWS + 1u) * rowp;
+            for (uint32_t c = threadIdx.x; c < cycb; c += blockDim.x) {
+                const uint32_t cc = c + (c >> 3);
+                uint32_t qs = 0;
+#pragma unroll
+                for (uint32_t r = PC_A; r <= PC_N; ++r) {
+                    const uint32_t v = base[r * rowp + cc];
+                    if (v) {
+                        base[r * rowp + cc] = 0;
+                        qs += v >> 12;
+                        atomicAdd((unsigned long long*)(GMm + L.m_pc + r * pad8(L.cyc) + c), (unsigned long long)(v & 0xFFFu));
+                    }
+                }
+                if (qs) base[PC_QUAL * rowp + cc] += qs;   // this thread owns the column
+            }
+        }
+    };
+    uint32_t iters = 0;
+    for (uint32_t cta0 = blockIdx.x * blockDim.x; cta0 < B.n_records; cta0 += gridDim.x * blockDim.x) {
+        if (++iters == kStatsUnpackEvery) {   // (uniform over the CTA: cta0 is)
+            __syncthreads();
+            unpack();
+            __syncthreads();
+            iters = 0;
+        }
+        const uint32_t r0 = cta0 + threadIdx.x - lane_id;
+        if (r0 >= B.n_records) continue;
         const uint32_t n_here = min(32u, B.n_records - r0);
         uint32_t off = 0, end = 0;
         if (lane_id < n_here) { off = B.offsets[r0 + lane_id]; end = B.offsets[r0 + lane_id + 1]; }
@@ -378,6 +414,8 @@ __global__ void __launch_bounds__(kStatsThreads, STAGE ? 2 : 4) __maxnreg__(STAG
             sub += m;
         }
     }
+    __syncthreads();
+    unpack();
     __syncthreads();
     // ---- flush the CTA-private tables (skip zeros) ---------------------------------------------------
     auto flush = [&](uint32_t smo, uint32_t n, uint64_t* g) {

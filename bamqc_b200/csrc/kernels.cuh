@@ -244,7 +244,10 @@ __device__ __forceinline__ AuxInfo aux_walk(const RecHdr& h, OnNM on_nm) {
 // ------------------------------------------------------------------------------------------------
 static const uint32_t kQS = 64;    // smem bins of the average-quality histograms (rest -> global)
 static const uint32_t kHS = 32;    // smem bins of mismatch / del / ins histograms
-static const uint32_t kStatsThreads = 256;
+#ifndef BQC_STATS_THREADS
+#define BQC_STATS_THREADS 256
+#endif
+static const uint32_t kStatsThreads = BQC_STATS_THREADS;
 
 struct StatsSmem {  // word offsets into the dynamic shared array
     uint32_t pc, rl, nc, gc, aq, cq, mq, mm, dl, in, isz, tri, sc, total, stage;
