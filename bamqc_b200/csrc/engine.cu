@@ -107,6 +107,10 @@ struct DeviceBatch {
     const uint8_t* base = nullptr;   // what the record offsets are relative to (bytes + kFrameHead when the host framed, bytes when the device did)
     uint32_t* offsets = nullptr;
     uint8_t* rec_lane = nullptr;
+    uint32_t* lane_index = nullptr;  // several read groups: record indices grouped by lane + where each lane's list starts
+    uint32_t* lane_range = nullptr;
+    unsigned long long* lane_lb = nullptr;   // look-back states + ticket of k_lane_partition
+    uint64_t lane_lb_bytes = 0;
     uint64_t n_records = 0, n_bytes = 0;
     uint32_t max_lseq = 0;
     uint64_t first_record = 0;
@@ -216,6 +220,7 @@ struct bqc_engine {
     int tune_sketch_v2 = 3;   // BQC_SKETCH_V2: 0 = k_sketch32 of round 1 (per-base ballot, pair table), 1/2/3/4 = k_sketch32v2 with
                               // 1024/512/640/768 threads per CTA (64/88/86/80 registers).  Measured per 10 M cfg2 records (serialised):
                               // 6.2 / 7.3 / 4.85 / 4.55 / 7.25 ms -- the restructured kernel needs ~86 registers to keep its loads in flight
+    int tune_lane_index = 1;  // BQC_LANE_INDEX=0: every lane's pass filters the whole batch (round 1 behaviour, A/B)
     int tune_cov_bps = 6;                                // BQC_COV_BPS: k_cov_tiles CTAs per SM
     uint64_t records_seen = 0, frames_repaired = 0;
     std::atomic<uint64_t> launches{0};   // kernels launched (commit thread, anchor thread, caller)
@@ -304,6 +309,9 @@ static void free_device_batch(DeviceBatch& d) {
     cudaFree(d.bytes);
     cudaFree(d.offsets);
     cudaFree(d.rec_lane);
+    cudaFree(d.lane_index);
+    cudaFree(d.lane_range);
+    cudaFree(d.lane_lb);
     d = DeviceBatch();
 }
 
@@ -366,7 +374,13 @@ static int alloc_device_batch(bqc_engine* e, DeviceBatch& d, uint64_t bytes_cap,
     CU(cudaMemset(d.bytes, 0, kFrameHead + bytes_cap + kFrameHead + 256));
     d.base = d.bytes + kFrameHead;
     CU(cudaMalloc(&d.offsets, (rec_cap + 1) * sizeof(uint32_t)));
-    if (e->n_lanes > 1) CU(cudaMalloc(&d.rec_lane, rec_cap + 1));
+    if (e->n_lanes > 1) {
+        CU(cudaMalloc(&d.rec_lane, rec_cap + 1));
+        CU(cudaMalloc(&d.lane_index, (rec_cap + 1) * 4));
+        CU(cudaMalloc(&d.lane_range, (e->n_lanes + 1) * 4));
+        d.lane_lb_bytes = (rec_cap / 1024 + 4) * 8;
+        CU(cudaMalloc(&d.lane_lb, d.lane_lb_bytes));
+    }
     return 0;
 }
 
@@ -448,6 +462,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     if (const char* v = getenv("BQC_TRACE")) e->trace = atoi(v) != 0;
     if (const char* v = getenv("BQC_FRAME_FORCE_REPAIR")) e->force_bad_frames = atoi(v) != 0;
     if (const char* v = getenv("BQC_SKETCH_V2")) e->tune_sketch_v2 = atoi(v);
+    if (const char* v = getenv("BQC_LANE_INDEX")) e->tune_lane_index = atoi(v);
     if (const char* v = getenv("BQC_SKETCH_THREADS")) e->tune_sketch_threads = std::max(32, std::min(1024, atoi(v) & ~31));
     e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     if (e->host_threads > 1) e->pool.reset(new HostPool(e->host_threads - 1));
@@ -844,6 +859,7 @@ struct BatchLaunch {  // launch geometry shared by the coverage and the table ke
     size_t stats_smem;
     int bps;
     bool staged;
+    size_t stats_smem0;   // shared memory of the unstaged kernel (lane-indexed batches)
 };
 
 // The reference's per-cycle String<>s grow with the longest read seen (src/QualityCheck.hpp:85-109); here the result
@@ -904,7 +920,8 @@ static int batch_launch_setup(bqc_engine* e, const DeviceBatch& d, BatchLaunch& 
     BL.cycb = cycb;
     StatsSmem S = stats_smem_layout(cycb, BL.E.insert_smem);
     int bps = 0;
-    BL.staged = e->tune_stats_stage != 0;
+    BL.stats_smem0 = (size_t)S.total * 4;
+    BL.staged = e->tune_stats_stage != 0 && !(e->n_lanes > 1 && e->tune_lane_index);
     if (BL.staged) {  // the per-warp staging areas on top of the tables: only while both fit
         BL.stats_smem = (size_t)S.stage * 4 + (size_t)(kStatsThreads / 32) * kStatsStage + kStatsMbarBytes;
         if (BL.stats_smem > 227u * 1024u || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_stats<1>, (int)kStatsThreads, BL.stats_smem) != cudaSuccess || bps < 1) {
@@ -958,6 +975,8 @@ static int launch_cov(bqc_engine* e, const DeviceBatch& d, const BatchLaunch& BL
         B.bytes = d.base;
         B.offsets = d.offsets;
         B.rec_lane = d.rec_lane;
+        B.index = (e->n_lanes > 1 && e->tune_lane_index) ? d.lane_index : nullptr;
+        B.index_range = d.lane_range;
         B.n_records = (uint32_t)n;
         B.cycb = BL.cycb;
         B.first_record = d.first_record;
@@ -990,13 +1009,16 @@ static int launch_tables(bqc_engine* e, const DeviceBatch& d, const BatchLaunch&
         B.bytes = d.base;
         B.offsets = d.offsets;
         B.rec_lane = d.rec_lane;
+        B.index = (e->n_lanes > 1 && e->tune_lane_index) ? d.lane_index : nullptr;
+        B.index_range = d.lane_range;
         B.n_records = (uint32_t)n;
         B.cycb = BL.cycb;
         B.first_record = d.first_record;
         int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * BL.bps);
         {
             ProfScope prof(e, 0);
-            if (BL.staged && e->tune_stats_stage == 2) k_stats<2><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
+            if (B.index) k_stats<0><<<grid, kStatsThreads, BL.stats_smem0, e->compute>>>(E, B, lane);   // a lane's records are not contiguous: no span to stage
+            else if (BL.staged && e->tune_stats_stage == 2) k_stats<2><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
             else if (BL.staged) k_stats<1><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
             else k_stats<0><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
         }
@@ -1078,6 +1100,21 @@ static int ensure_slot(bqc_engine* e, Slot& s) {
     return alloc_device_batch(e, s.dev, e->staging_bytes, rc_);
 }
 
+// Several read groups: group the record indices by lane (k_lane_partition, one cheap pass over the lane bytes per
+// lane) on `st`, after rec_lane is there.  n_ptr: device-side record count of a device-framed buffer, or NULL.
+static int launch_lane_partition(bqc_engine* e, DeviceBatch& d, const uint32_t* n_ptr, uint64_t n, cudaStream_t st) {
+    if (e->n_lanes <= 1 || !e->tune_lane_index) return 0;
+    const uint64_t nb = n_ptr ? e->max_records_per_slot : n;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((nb + 1023) / 1024, (uint64_t)e->n_sm * 2));
+    for (uint32_t lane = 0; lane < e->n_lanes; ++lane) {
+        CU(cudaMemsetAsync(d.lane_lb, 0, d.lane_lb_bytes, st));
+        k_lane_partition<<<grid, 1024, 0, st>>>(d.rec_lane, n_ptr, (uint32_t)n, lane, d.lane_index, d.lane_range, d.lane_lb + 1, (uint32_t*)d.lane_lb);
+        e->launches += 1;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // host-framed task: copies and launches
 static int commit_task(bqc_engine* e, const bqc_engine::Task& t) {
     Slot& s = e->slots[t.slot];
@@ -1090,7 +1127,11 @@ static int commit_task(bqc_engine* e, const bqc_engine::Task& t) {
     d.base = d.bytes + kFrameHead;
     CU(cudaMemcpyAsync(d.bytes + kFrameHead, t.h2d_src, t.span, cudaMemcpyHostToDevice, e->copy));
     CU(cudaMemcpyAsync(d.offsets, s.h_offsets, (n_records + 1) * 4, cudaMemcpyHostToDevice, e->copy));
-    if (e->n_lanes > 1) CU(cudaMemcpyAsync(d.rec_lane, s.h_lane, n_records, cudaMemcpyHostToDevice, e->copy));
+    if (e->n_lanes > 1) {
+        CU(cudaMemcpyAsync(d.rec_lane, s.h_lane, n_records, cudaMemcpyHostToDevice, e->copy));
+        int rcp = launch_lane_partition(e, d, nullptr, n_records, e->copy);
+        if (rcp) return rcp;
+    }
     CU(cudaEventRecord(e->copied, e->copy));
     CU(cudaStreamWaitEvent(e->compute, e->copied, 0));
     int rc = run_device_batch(e, d);
@@ -1140,9 +1181,11 @@ static int stream_stage_a(bqc_engine* e, const bqc_engine::Task& t) {
     k_frame_repair<<<1, 32, 0, e->frames>>>(d.bytes, s.d_frame, e->cfg.n_ref, e->d_main_chrom, d.offsets, nullptr, rec_cap);
     k_frame_emit<<<nblk, kFrameThreads, 0, e->frames>>>(d.bytes, s.d_frame, e->cfg.n_ref, e->d_main_chrom, nwin, s.d_ws, s.d_wc, s.d_bbase, d.offsets, nullptr);
     e->launches += 10;
-    if (e->n_lanes > 1) {  // several read groups: the lane of every record, from its RG tag
+    if (e->n_lanes > 1) {  // several read groups: the lane of every record, from its RG tag, then the records grouped by lane
         k_frame_lanes<<<e->n_sm * 4, 256, 0, e->frames>>>(d.bytes, s.d_frame, d.offsets, e->d_lane_names, e->d_lane_off, e->n_lanes, d.rec_lane);
         e->launches += 1;
+        int rcp = launch_lane_partition(e, d, &s.d_frame->n_records, 0, e->frames);
+        if (rcp) return rcp;
     }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(s.h_frame, s.d_frame, sizeof(FrameResult), cudaMemcpyDeviceToHost, e->frames));
@@ -1550,7 +1593,12 @@ extern "C" int bqc_batch_prepare(bqc_engine* e, const void* data, size_t n_bytes
     if (n_records) {
         CU(cudaMemcpy(d.bytes + kFrameHead, src + record_offsets[0], span, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.offsets, o32.data(), (n_records + 1) * 4, cudaMemcpyHostToDevice));
-        if (e->n_lanes > 1) CU(cudaMemcpy(d.rec_lane, lanes.data(), n_records, cudaMemcpyHostToDevice));
+        if (e->n_lanes > 1) {
+            CU(cudaMemcpy(d.rec_lane, lanes.data(), n_records, cudaMemcpyHostToDevice));
+            rc = launch_lane_partition(e, d, nullptr, n_records, e->compute);
+            if (rc) return rc;
+            CU(cudaStreamSynchronize(e->compute));
+        }
     }
     *out = b;
     return 0;

@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(kCovPrepThreads) k_cov_prep(EngineView E, Batc
     __shared__ uint32_t ws[33];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
-    const uint32_t ntile = (B.n_records + kCovPrepTile - 1u) / kCovPrepTile;
+    const LaneRecords LR = lane_records(B, lane);
+    const uint32_t ntile = (LR.n + kCovPrepTile - 1u) / kCovPrepTile;
     const uint32_t have = append ? carry->nq : 0u;   // only tile 0 uses it, and the last tile overwrites it after tile 0 has published
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(S.tickets + 0, 1u);
@@ -182,14 +183,15 @@ __global__ void __launch_bounds__(kCovPrepThreads) k_cov_prep(EngineView E, Batc
         const uint32_t tile = s_tile;
         if (tile >= ntile) break;
         int32_t rid[kCovPrepPer];
-        uint32_t b[kCovPrepPer], iv[kCovPrepPer], flags = 0;
+        uint32_t b[kCovPrepPer], iv[kCovPrepPer], recno[kCovPrepPer], flags = 0;
         const uint32_t r0 = tile * kCovPrepTile + kCovPrepPer * threadIdx.x;
 #pragma unroll
         for (uint32_t k = 0; k < kCovPrepPer; ++k) {
-            const uint32_t r = r0 + k;
-            rid[k] = -1; b[k] = 0; iv[k] = 0;
-            if (r >= B.n_records) continue;
-            if (B.rec_lane && B.rec_lane[r] != lane) continue;
+            rid[k] = -1; b[k] = 0; iv[k] = 0; recno[k] = 0;
+            if (r0 + k >= LR.n) continue;
+            const uint32_t r = LR[r0 + k];
+            recno[k] = r;
+            if (!lane_match(B, r, lane)) continue;
             const uint32_t off = B.offsets[r], avail = B.offsets[r + 1] - off;
             if (avail < 36u) continue;
             const uint8_t* p = B.bytes + off;
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(kCovPrepThreads) k_cov_prep(EngineView E, Batc
 #pragma unroll
         for (uint32_t k = 0; k < kCovPrepPer; ++k)
             if (flags & (1u << k)) {
-                S.q_rid[o] = rid[k]; S.q_b[o] = b[k]; S.q_iv[o] = iv[k]; S.q_rec[o] = r0 + k;
+                S.q_rid[o] = rid[k]; S.q_b[o] = b[k]; S.q_iv[o] = iv[k]; S.q_rec[o] = recno[k];
                 ++o;
             }
         __syncthreads();

@@ -367,6 +367,41 @@ __global__ void __launch_bounds__(256) k_frame_lanes(const uint8_t* __restrict__
     }
 }
 
+// Several read groups: the record indices of one lane, in file order (stable compaction, decoupled look-back), so that
+// the lane's pass of every table kernel touches its own records only.  Launched once per lane in lane order:
+// range[lane] is where the lane's list starts in `index`, range[lane + 1] is written by the last tile.
+// n_ptr: the record count on the device (FrameResult::n_records of a device-framed buffer) or NULL (then n).
+__global__ void __launch_bounds__(1024) k_lane_partition(const uint8_t* __restrict__ rec_lane, const uint32_t* __restrict__ n_ptr, uint32_t n, uint32_t lane,
+                                                         uint32_t* __restrict__ index, uint32_t* range, unsigned long long* lb, uint32_t* ticket) {
+    __shared__ uint32_t ws[33];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base;
+    if (n_ptr) n = *n_ptr;
+    const uint32_t ntile = (n + 1023u) / 1024u;
+    const uint32_t start = lane ? range[lane] : 0u;
+    if (ntile == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) { if (!lane) range[0] = 0; range[lane + 1] = start; } return; }
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntile) break;
+        const uint32_t r = tile * 1024u + threadIdx.x;
+        const uint32_t f = (r < n && rec_lane[r] == lane) ? 1u : 0u;
+        uint32_t total;
+        const uint32_t excl = cov_block_scan(f, ws, total) - f;
+        if (threadIdx.x < 32) {
+            const unsigned long long pre = cov_lookback(lb, tile, total, (unsigned long long)start);
+            if (threadIdx.x == 0) {
+                s_base = pre;
+                if (tile == ntile - 1u) { if (!lane) range[0] = 0; range[lane + 1] = (uint32_t)(pre + total); }
+            }
+        }
+        __syncthreads();
+        if (f) index[(uint32_t)s_base + excl] = r;
+        __syncthreads();
+    }
+}
+
 // Prepare the frame header of the next buffer: carry the partial record [end, total) of the previous buffer (if
 // any) in front of kFrameHead and set start/total.  One CTA.
 // `skip`: bytes at the front of the new data that are not records (the BAM header in the first buffer of a file).

@@ -96,10 +96,12 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, Ba
         probe.old = __ldcg(sk + probe.word);   // tested one drain later: the L2 latency overlaps the hashing in between
     };
 
-    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < B.n_records; r0 += gridDim.x * blockDim.x) {
-        const uint32_t rec = r0 + lane_id;
+    const LaneRecords LR = lane_records(B, lane);
+    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < LR.n; r0 += gridDim.x * blockDim.x) {
+        const uint32_t ri = r0 + lane_id;
+        const uint32_t rec = ri < LR.n ? LR[ri] : 0u;
         RecHdr h;
-        bool act = rec < B.n_records && !(B.rec_lane && B.rec_lane[rec] != lane);
+        bool act = ri < LR.n && lane_match(B, rec, lane);
         if (act) {
             const uint32_t off = B.offsets[rec];
             act = decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h);
@@ -265,10 +267,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_sketch32v2(EngineView E, BatchVi
         probe.old = __ldcg(sk + probe.word);
     };
 
-    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < B.n_records; r0 += gridDim.x * blockDim.x) {
-        const uint32_t rec = r0 + lane_id;
+    const LaneRecords LR = lane_records(B, lane);
+    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < LR.n; r0 += gridDim.x * blockDim.x) {
+        const uint32_t ri = r0 + lane_id;
+        const uint32_t rec = ri < LR.n ? LR[ri] : 0u;
         RecHdr h;
-        bool act = rec < B.n_records && !(B.rec_lane && B.rec_lane[rec] != lane);
+        bool act = ri < LR.n && lane_match(B, rec, lane);
         if (act) {
             const uint32_t off = B.offsets[rec];
             act = decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h);

@@ -33,7 +33,7 @@ __device__ __forceinline__ void stats_records(const EngineView& E, const BatchVi
         const uint64_t grec = B.first_record + rec;
         RecHdr h;
         h.p = recp;
-        bool live = present && !(B.rec_lane && B.rec_lane[rec] != lane);
+        bool live = present && lane_match(B, rec, lane);
         if (live) {
             if (!decode_hdr<M>(recp, avail, h)) { report_error(E, grec, 4); live = false; }
         }
@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(kStatsThreads, kStatsThreads > 256 ? 1 : (STAG
         }
     };
     uint32_t iters = 0;
-    for (uint32_t cta0 = blockIdx.x * blockDim.x; cta0 < B.n_records; cta0 += gridDim.x * blockDim.x) {
+    const LaneRecords LR = lane_records(B, lane);
+    for (uint32_t cta0 = blockIdx.x * blockDim.x; cta0 < LR.n; cta0 += gridDim.x * blockDim.x) {
         if (++iters == kStatsUnpackEvery) {   // (uniform over the CTA: cta0 is)
             __syncthreads();
             unpack();
@@ -374,12 +375,13 @@ __global__ void __launch_bounds__(kStatsThreads, kStatsThreads > 256 ? 1 : (STAG
             iters = 0;
         }
         const uint32_t r0 = cta0 + threadIdx.x - lane_id;
-        if (r0 >= B.n_records) continue;
-        const uint32_t n_here = min(32u, B.n_records - r0);
+        if (r0 >= LR.n) continue;
+        const uint32_t n_here = min(32u, LR.n - r0);
         uint32_t off = 0, end = 0;
-        if (lane_id < n_here) { off = B.offsets[r0 + lane_id]; end = B.offsets[r0 + lane_id + 1]; }
+        const uint32_t myrec = lane_id < n_here ? LR[r0 + lane_id] : 0u;   // (staged launches never use an index list: myrec = r0 + lane_id)
+        if (lane_id < n_here) { off = B.offsets[myrec]; end = B.offsets[myrec + 1]; }
         if (!STAGE) {
-            stats_records<GMem>(E, B, lane, sm, S, r0 + lane_id, lane_id < n_here, B.bytes + off, end - off);
+            stats_records<GMem>(E, B, lane, sm, S, myrec, lane_id < n_here, B.bytes + off, end - off);
             continue;
         }
         uint8_t* stage = (uint8_t*)(sm + S.stage) + (threadIdx.x >> 5) * kStatsStage;

@@ -32,6 +32,9 @@ struct BatchView {
     const uint8_t* bytes;      // inflated BAM records, padded with >= 64 readable bytes
     const uint32_t* offsets;   // n_records + 1 byte offsets
     const uint8_t* rec_lane;   // per record lane (multi-lane runs) or NULL
+    const uint32_t* index;     // multi-lane runs: the record indices grouped by lane (file order inside a lane), or NULL:
+    const uint32_t* index_range;  // ... lane l owns index[index_range[l] .. index_range[l + 1]), so that a lane's pass only
+                               // touches its own records instead of filtering the whole batch
     uint32_t n_records;
     uint32_t cycb;             // per-cycle smem capacity for this batch (>= max l_seq, multiple of 8)
     uint64_t first_record;     // global index of record 0 (error reporting)
@@ -111,6 +114,21 @@ __device__ __forceinline__ uint64_t ldu64(const uint8_t* p) {  // unaligned litt
 }
 // nibble i (0..15) of a 64-bit SEQ chunk: byte i/2, high nibble first
 __device__ __forceinline__ uint32_t nib_of(uint64_t w, uint32_t i) { return (uint32_t)(w >> (4 * (i ^ 1))) & 15u; }
+
+// the records a kernel launched for `lane` iterates over: all of the batch (filtered by rec_lane, if any), or the lane's
+// own index list
+struct LaneRecords {
+    uint32_t n;
+    const uint32_t* idx;
+    __device__ __forceinline__ uint32_t operator[](uint32_t i) const { return idx ? idx[i] : i; }
+};
+__device__ __forceinline__ LaneRecords lane_records(const BatchView& B, uint32_t lane) {
+    LaneRecords R;
+    if (B.index) { const uint32_t a = B.index_range[lane]; R.n = B.index_range[lane + 1] - a; R.idx = B.index + a; }
+    else { R.n = B.n_records; R.idx = nullptr; }
+    return R;
+}
+__device__ __forceinline__ bool lane_match(const BatchView& B, uint32_t rec, uint32_t lane) { return B.index || !B.rec_lane || B.rec_lane[rec] == lane; }
 
 __device__ __forceinline__ void report_error(const EngineView& E, uint64_t rec, uint32_t code) {
     atomicMin(E.error, (unsigned long long)((rec << 8) | code));
@@ -306,8 +324,10 @@ __global__ void __launch_bounds__(kEightThreads, 1) k_eightmer(EngineView E, Bat
     // reverse-complement code from the other end, which is the little-endian packing of the complemented codes.
     // A window counts iff it holds no literal N (:146-166): a nibble-stride mask of "N among the last eight bases",
     // with the distance to the last N carried between chunks (starting at 0, which also rules out the first 7 ends).
-    for (uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x; rec < B.n_records; rec += gridDim.x * blockDim.x) {
-        if (B.rec_lane && B.rec_lane[rec] != lane) continue;
+    const LaneRecords LR = lane_records(B, lane);
+    for (uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x; ri < LR.n; ri += gridDim.x * blockDim.x) {
+        const uint32_t rec = LR[ri];
+        if (!lane_match(B, rec, lane)) continue;
         const uint32_t off = B.offsets[rec];
         RecHdr h;
         if (!decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h)) continue;
@@ -411,10 +431,12 @@ __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch(EngineView E, Batc
     // with independent thread scheduling the lanes otherwise drift apart after the first CAS loop and the
     // per-base loop runs one lane at a time (measured: 2 active threads per instruction).
     const uint32_t lane_id = threadIdx.x & 31u;
-    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < B.n_records; r0 += gridDim.x * blockDim.x) {
-        const uint32_t rec = r0 + lane_id;
+    const LaneRecords LR = lane_records(B, lane);
+    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < LR.n; r0 += gridDim.x * blockDim.x) {
+        const uint32_t ri = r0 + lane_id;
+        const uint32_t rec = ri < LR.n ? LR[ri] : 0u;
         RecHdr h;
-        bool act = rec < B.n_records && !(B.rec_lane && B.rec_lane[rec] != lane);
+        bool act = ri < LR.n && lane_match(B, rec, lane);
         if (act) {
             const uint32_t off = B.offsets[rec];
             act = decode_hdr(B.bytes + off, B.offsets[rec + 1] - off, h);
