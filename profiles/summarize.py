@@ -1,5 +1,6 @@
 """Turn the ncu reports brought back in gpurun_out/ into the text summaries committed under profiles/<round>/.
-Usage: python profiles/summarize.py r1   (reads gpurun_out/r1_*.ncu-rep and gpurun_out/r1_launches.csv)"""
+Usage: python profiles/summarize.py r2   (reads gpurun_out/r2_*.ncu-rep and gpurun_out/r2_launches.csv; writes
+profiles/r2/ncu_full_summary.txt, traffic.json (read by bench.py for roofline.traffic), launches.csv, launch_summary.txt)"""
 import collections
 import csv
 import re
@@ -38,9 +39,9 @@ def main():
     dst = os.path.join(ROOT, "profiles", tag)
     os.makedirs(dst, exist_ok=True)
     seen = set()
-    lines = ["ncu --set full --clock-control none --import-source on; bench.py --records 3300000 --bgzf-records 3300000 --steps 1 --warmup 1",
-             "(one 957 MB batch of 3.30 M records kernel-only; 256 MB slices on the streaming paths).  Per-launch values; times under ncu are",
-             "cold-cache and serialised (compare shares, not absolutes).  First captured launch of every kernel.", ""]
+    lines = ["ncu --set full --clock-control none --import-source on -k regex:... ; bench.py --steps 1 --warmup 1 --no-cpu-baseline --bgzf-records 0",
+             "(cfg 2: one 957 MB batch of 3.30 M records per launch).  Per-launch values; times under ncu are cold-cache and serialised",
+             "(compare shares, not absolutes).  First captured launch of every kernel.", ""]
     traffic = {}
     for name in ("tables2", "tables", "frame", "inflate"):
         rep = os.path.join(gout, f"{tag}_{name}.ncu-rep")
@@ -67,10 +68,12 @@ def main():
                 pass
     open(os.path.join(dst, "ncu_full_summary.txt"), "w").write("\n".join(lines))
     # bench.py reads the per-launch DRAM traffic of the dominant kernel family from here
-    fam = {"k_stats": traffic.get("k_stats"), "k_eightmer": traffic.get("k_eightmer"), "k_sketch": traffic.get("k_sketch32"),
-           "k_inflate": traffic.get("k_inflate"), "k_cov_flush": traffic.get("k_cov_flush"),
-           "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 3.30 M-record (957 MB) batch; k_inflate: one 256 MB slice"}
-    json.dump(fam, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    fam = {"k_stats": traffic.get("k_stats"), "k_eightmer": traffic.get("k_eightmer"), "k_sketch": traffic.get("k_sketch32v2", traffic.get("k_sketch32")),
+           "k_cov": sum(v for k, v in traffic.items() if k.startswith("k_cov_")) or None,
+           "per_kernel": traffic,
+           "_source": f"dram__bytes_read.sum + dram__bytes_write.sum per launch from gpurun_out/{tag}_tables.ncu-rep (ncu --set full --clock-control none, "
+                      f"this round's final build, one 957 MB batch of 3.30 M cfg 2 records per launch); summarised by profiles/summarize.py {tag}"}
+    json.dump(fam, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
     # launch list
     lcsv = os.path.join(gout, f"{tag}_launches.csv")
     if os.path.exists(lcsv):
@@ -90,14 +93,15 @@ def main():
                     v = float(d["Metric Value"].replace(",", ""))
                 except ValueError:
                     continue
+                v *= {"ns": 1.0, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6, "s": 1e9}.get(d.get("Metric Unit", "ns"), 1.0)   # -> ns
                 a = agg.setdefault(kernel_name(d["Kernel Name"]), [0, 0.0])
                 a[0] += 1
                 a[1] += v
         with open(os.path.join(dst, "launches.csv"), "w", newline="") as f:
             csv.writer(f).writerows(keep)
         tot = sum(a[1] for a in agg.values())
-        out = ["ncu --metrics gpu__time_duration.sum --clock-control none; bench.py --steps 2 --warmup 1 --no-cpu-baseline (cfg 2, 10 M records:",
-               "3 kernel-only passes over 3 resident batches, 3 streaming passes over 12 slices of 256 MB, 4 BGZF passes).  Serialised, cold-cache times.", "",
+        out = ["ncu --metrics gpu__time_duration.sum --clock-control none; bench.py --steps 2 --warmup 1 --no-cpu-baseline --bgzf-records 3300000 (cfg 2, 10 M records:",
+               "kernel-only passes over 3 resident batches of 3.3 M records, streaming passes over 12 slices of 256 MB, BGZF passes).  Serialised, cold-cache times.", "",
                "%-22s %6s %12s %10s %7s" % ("kernel", "n", "total_us", "avg_us", "share")]
         for k, (n, t) in agg.items():
             out.append("%-22s %6d %12.1f %10.1f %7.3f" % (k, n, t / 1e3, t / 1e3 / n, t / tot))
