@@ -222,6 +222,7 @@ struct bqc_engine {
                               // 6.2 / 7.3 / 4.85 / 4.55 / 7.25 ms -- the restructured kernel needs ~86 registers to keep its loads in flight
     int tune_lane_index = 1;  // BQC_LANE_INDEX=0: every lane's pass filters the whole batch (round 1 behaviour, A/B)
     int tune_cov_bps = 6;                                // BQC_COV_BPS: k_cov_tiles CTAs per SM
+    int tune_cov_overlap = 1;                            // BQC_COV_OVERLAP=0: coverage kernels on the compute stream (A/B of the two-stream overlap)
     uint64_t records_seen = 0, frames_repaired = 0;
     std::atomic<uint64_t> launches{0};   // kernels launched (commit thread, anchor thread, caller)
     bool finished = false;
@@ -462,6 +463,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     if (const char* v = getenv("BQC_TRACE")) e->trace = atoi(v) != 0;
     if (const char* v = getenv("BQC_FRAME_FORCE_REPAIR")) e->force_bad_frames = atoi(v) != 0;
     if (const char* v = getenv("BQC_SKETCH_V2")) e->tune_sketch_v2 = atoi(v);
+    if (const char* v = getenv("BQC_COV_OVERLAP")) e->tune_cov_overlap = atoi(v);
     if (const char* v = getenv("BQC_LANE_INDEX")) e->tune_lane_index = atoi(v);
     if (const char* v = getenv("BQC_SKETCH_THREADS")) e->tune_sketch_threads = std::max(32, std::min(1024, atoi(v) & ~31));
     e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -759,7 +761,7 @@ struct ProfScope {  // records an event pair around the launches of one kernel f
     }
 };
 extern "C" void bqc_profile_enable(bqc_engine* e, int on) { e->profiling = on != 0; e->prof_serial = on == 2; }
-static inline cudaStream_t cov_stream(bqc_engine* e) { return e->prof_serial ? e->compute : e->covs; }
+static inline cudaStream_t cov_stream(bqc_engine* e) { return (e->prof_serial || !e->tune_cov_overlap) ? e->compute : e->covs; }
 // Accumulated device time per kernel family since the last call: 0 k_stats, 1 k_eightmer, 2 k_sketch,
 // 3 coverage flush (3 kernels per launch group), 4 merge/export.  Synchronises the compute stream.
 extern "C" int bqc_profile_read(bqc_engine* e, double ms_out[12], uint64_t n_out[12]) {
