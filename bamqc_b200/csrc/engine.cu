@@ -134,6 +134,7 @@ struct Slot {  // one half of the staging double buffer
     FrameResult* d_frame = nullptr;
     uint32_t *d_ws = nullptr, *d_we = nullptr, *d_wc = nullptr, *d_ws2 = nullptr, *d_we2 = nullptr, *d_wc2 = nullptr, *d_bsum = nullptr, *d_bbase = nullptr;
     cudaEvent_t framed = nullptr;
+    cudaEvent_t inflated = nullptr;    // k_inflate of this slot finished (recorded on its inflate stream)
     // device inflate (kernel_inflate.cuh)
     uint8_t* d_cin = nullptr;          // compressed BGZF bytes of the submission
     InflateBlock* h_blocks = nullptr;  // pinned
@@ -182,6 +183,10 @@ struct bqc_engine {
     std::vector<uint64_t> ref_len;
     cudaStream_t compute = nullptr, copy = nullptr, covs = nullptr;  // covs: coverage scatter + flush (HBM bound) overlaps the table kernels
     cudaStream_t frames = nullptr; // framing kernels: the H2D copy of the next buffer (copy stream) overlaps them
+    // k_inflate: consecutive submissions alternate between two streams.  One warp inflates one BGZF block from start to
+    // end (~6 ms for 64 KiB), and a 256 MB submission holds about as many blocks as the GPU has warp slots, so a launch
+    // alone ends in a long tail of half-empty SMs; the next submission's launch fills it.
+    cudaStream_t inflates[2] = {nullptr, nullptr};
     cudaEvent_t cov_done = nullptr, cov_go = nullptr;
     static const int kSlots = 4;  // depth of the staging pipeline: framing / anchor pass / H2D / kernels each hold one
     Slot slots[kSlots];
@@ -221,8 +226,11 @@ struct bqc_engine {
                               // 1024/512/640/768 threads per CTA (64/88/86/80 registers).  Measured per 10 M cfg2 records (serialised):
                               // 6.2 / 7.3 / 4.85 / 4.55 / 7.25 ms -- the restructured kernel needs ~86 registers to keep its loads in flight
     int tune_lane_index = 1;  // BQC_LANE_INDEX=0: every lane's pass filters the whole batch (round 1 behaviour, A/B)
+    int tune_inflate_streams = 2;                        // BQC_INFLATE_STREAMS=1: every k_inflate on the framing stream (one launch at a time), A/B
+    int tune_inflate = 2;                                // BQC_INFLATE=1: round-1 symbol loop (k_inflate_r1), A/B
     int tune_cov_bps = 6;                                // BQC_COV_BPS: k_cov_tiles CTAs per SM
-    int tune_cov_overlap = 1;                            // BQC_COV_OVERLAP=0: coverage kernels on the compute stream (A/B of the two-stream overlap)
+    int tune_cov_overlap = 0;                            // BQC_COV_OVERLAP=1: coverage kernels on their own stream next to the table kernels.  Measured (cfg 2,
+                                                         // same box, 2 runs each): 14.03 / 14.78 ms per 10 M records overlapped, 12.59 / 12.59 ms on one stream
     uint64_t records_seen = 0, frames_repaired = 0;
     std::atomic<uint64_t> launches{0};   // kernels launched (commit thread, anchor thread, caller)
     bool finished = false;
@@ -339,6 +347,7 @@ extern "C" void bqc_destroy(bqc_engine* e) {
         free_device_batch(s.dev);
         if (s.done) cudaEventDestroy(s.done);
         if (s.framed) cudaEventDestroy(s.framed);
+        if (s.inflated) cudaEventDestroy(s.inflated);
     }
     for (auto p : e->ref_bufs) cudaFree(p);
     cudaFree(e->d_counters);
@@ -360,6 +369,7 @@ extern "C" void bqc_destroy(bqc_engine* e) {
     if (e->cov_go) cudaEventDestroy(e->cov_go);
     if (e->covs) cudaStreamDestroy(e->covs);
     if (e->frames) cudaStreamDestroy(e->frames);
+    for (auto& st : e->inflates) if (st) cudaStreamDestroy(st);
     if (e->compute) cudaStreamDestroy(e->compute);
     if (e->copy) cudaStreamDestroy(e->copy);
     delete e;
@@ -394,6 +404,7 @@ extern "C" int bqc_reset(bqc_engine* e) {
     CU(cudaStreamSynchronize(e->copy));
     CU(cudaStreamSynchronize(e->covs));
     CU(cudaStreamSynchronize(e->frames));
+    for (auto& st : e->inflates) CU(cudaStreamSynchronize(st));
     e->last_stream_slot = -1;
     e->stream_seek = false;
     e->stream_skipped = -1;
@@ -464,6 +475,8 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     if (const char* v = getenv("BQC_FRAME_FORCE_REPAIR")) e->force_bad_frames = atoi(v) != 0;
     if (const char* v = getenv("BQC_SKETCH_V2")) e->tune_sketch_v2 = atoi(v);
     if (const char* v = getenv("BQC_COV_OVERLAP")) e->tune_cov_overlap = atoi(v);
+    if (const char* v = getenv("BQC_INFLATE")) e->tune_inflate = atoi(v);
+    if (const char* v = getenv("BQC_INFLATE_STREAMS")) e->tune_inflate_streams = atoi(v);
     if (const char* v = getenv("BQC_LANE_INDEX")) e->tune_lane_index = atoi(v);
     if (const char* v = getenv("BQC_SKETCH_THREADS")) e->tune_sketch_threads = std::max(32, std::min(1024, atoi(v) & ~31));
     e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -478,6 +491,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         CU(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&e->covs, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&e->frames, cudaStreamNonBlocking));
+        for (auto& st : e->inflates) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&e->cov_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&e->cov_go, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&e->copied, cudaEventDisableTiming));
@@ -514,9 +528,11 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         for (auto& s : e->slots) {
             CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s.framed, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s.inflated, cudaEventDisableTiming));
         }
         // opt in to large dynamic shared memory
         CU(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kInflateStreams * sizeof(InflateTabs))));
+        CU(cudaFuncSetAttribute(k_inflate_r1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kInflateStreams * sizeof(InflateTabs))));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->inflate_bps, k_inflate, (int)kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs)));
         if (e->inflate_bps < 1) e->inflate_bps = 1;
         CU(cudaFuncSetAttribute(k_stats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1155,13 +1171,19 @@ static int stream_stage_a(bqc_engine* e, const bqc_engine::Task& t) {
         CU(cudaMemcpyAsync(s.d_cin, t.h2d_src, t.span, cudaMemcpyHostToDevice, e->copy));
         CU(cudaMemcpyAsync(s.d_blocks, s.h_blocks, (size_t)t.n_blocks * sizeof(InflateBlock), cudaMemcpyHostToDevice, e->copy));
         CU(cudaEventRecord(e->copied, e->copy));
-        CU(cudaStreamWaitEvent(e->frames, e->copied, 0));
-        CU(cudaMemsetAsync(s.d_ictl, 0, 8, e->frames));
+        cudaStream_t is = e->tune_inflate_streams > 1 ? e->inflates[t.slot & 1] : e->frames;
+        CU(cudaStreamWaitEvent(is, e->copied, 0));
+        CU(cudaMemsetAsync(s.d_ictl, 0, 8, is));
         if (t.n_blocks) {
             const int grid = (int)std::min<uint64_t>(((uint64_t)t.n_blocks + kInflateStreams - 1) / kInflateStreams, (uint64_t)e->n_sm * e->inflate_bps);
-            ProfScope prof(e, 8, e->frames);
-            k_inflate<<<grid, kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs), e->frames>>>(s.d_cin, s.d_blocks, t.n_blocks, d.bytes + kFrameHead, s.d_ictl);
+            ProfScope prof(e, 8, is);
+            if (e->tune_inflate == 1) k_inflate_r1<<<grid, kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs), is>>>(s.d_cin, s.d_blocks, t.n_blocks, d.bytes + kFrameHead, s.d_ictl);
+            else k_inflate<<<grid, kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs), is>>>(s.d_cin, s.d_blocks, t.n_blocks, d.bytes + kFrameHead, s.d_ictl);
             e->launches += 1;
+        }
+        if (is != e->frames) {
+            CU(cudaEventRecord(s.inflated, is));
+            CU(cudaStreamWaitEvent(e->frames, s.inflated, 0));
         }
     } else {
         CU(cudaMemcpyAsync(d.bytes + kFrameHead, t.h2d_src, t.span, cudaMemcpyHostToDevice, e->copy));

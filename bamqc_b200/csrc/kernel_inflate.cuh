@@ -30,13 +30,23 @@ struct InflateBlock {   // one BGZF block, filled by the host from the block hea
 static const uint32_t kGroup = 32;
 static const uint32_t kInflateWarps = 6;          // warps per CTA
 static const uint32_t kInflateStreams = kInflateWarps * 32 / kGroup;   // BGZF blocks in flight per CTA
-static const uint32_t kLitBits = 10, kDistBits = 8, kClBits = 7;
+#ifndef BQC_INFLATE_LITBITS
+#define BQC_INFLATE_LITBITS 9
+#endif
+#ifndef BQC_INFLATE_DISTBITS
+#define BQC_INFLATE_DISTBITS 7
+#endif
+#ifndef BQC_INFLATE_MINBLOCKS
+#define BQC_INFLATE_MINBLOCKS 6
+#endif
+static const uint32_t kLitBits = BQC_INFLATE_LITBITS, kDistBits = BQC_INFLATE_DISTBITS, kClBits = 7;
 
 // Table entries are packed so that one shared-memory load yields everything a symbol needs:
 //   bits 0-3 code length (0 = the code is longer than the primary index: canonical search), bits 4-7 number of
 //   extra bits, bits 8-9 kind (0 literal, 1 length / distance, 2 end of block, 3 invalid symbol), bits 16-31 value
-//   (literal byte, length base, distance base; the symbol itself for the code-length alphabet).
+//   (literal byte, length base, distance base; the symbol itself for the code-length alphabet), bit 10 literal.
 static const uint32_t kKindBase = 1u << 8, kKindEob = 2u << 8, kKindInvalid = 3u << 8;
+static const uint32_t kIsLiteral = 1u << 10;      // literal/length alphabet only: the entry is a literal byte (one test on the fast path)
 
 struct alignas(16) InflateTabs {                   // per group, shared memory
     uint32_t lit[1u << kLitBits];
@@ -58,7 +68,7 @@ __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 
 
 // packed entry of a symbol (without the code length)
 __device__ __forceinline__ uint32_t inflate_lit_entry(uint32_t s) {
-    if (s < 256u) return s << 16;
+    if (s < 256u) return (s << 16) | kIsLiteral;
     if (s == 256u) return kKindEob;
     if (s > 285u) return kKindInvalid;
     return kKindBase | ((uint32_t)c_len_extra[s - 257u] << 4) | ((uint32_t)c_len_base[s - 257u] << 16);
@@ -184,7 +194,7 @@ __device__ __noinline__ uint32_t inflate_decode_slow(const InflateTabs& T, uint6
 
 // ctl[0] = ticket, ctl[1] = 1 + index of the first BGZF block that failed to inflate (0 = none; atomicMin on the
 // bitwise complement so that a zeroed word means "none")
-__global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* __restrict__ cin, const InflateBlock* __restrict__ blocks, uint32_t n_blocks,
+__global__ void __launch_bounds__(kInflateWarps * 32) k_inflate_r1(const uint8_t* __restrict__ cin, const InflateBlock* __restrict__ blocks, uint32_t n_blocks,
                                                                  uint8_t* out, uint32_t* ctl) {
     extern __shared__ __align__(16) uint8_t inflate_smem[];
     InflateTabs* tabs = reinterpret_cast<InflateTabs*>(inflate_smem);
@@ -338,6 +348,267 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(const uint8_t* _
                         if (j < len) { pend_val = o[sp + j]; pend = pos + j; }
                     } else {
                         for (; j + kGroup < len + lane; j += kGroup) o[pos + j] = o[sp + j % dist];
+                        if (j < len) { pend_val = o[sp + j % dist]; pend = pos + j; }
+                    }
+                }
+                pos += len;
+            }
+            if (br.bytes_used() > blk.clen + 8u) ok = false;  // ran past the payload
+        }
+        if (pend != kNone) o[pend] = (uint8_t)pend_val;
+        if (ok && (pos != isize || br.bytes_used() > blk.clen)) ok = false;
+        if (!ok && lane == 0) atomicMax(ctl + 1, 0xFFFFFFFFu - b);  // largest complement = smallest index
+        __syncwarp(gmask);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Round 2 symbol loop.  k_inflate_r1 above spends ~95 warp instructions per trip of up to three literals and ~140
+// per match, most of them 64-bit buffer bookkeeping and re-derived addresses (profiles/r1, 69 % issue-bound).
+// BitWin keeps the stream as three consecutive aligned 32-bit words and a bit position: a 32-bit window is one
+// funnel shift, dropping bits is one add, and a whole trip (up to four literals, or a length with its extra bits,
+// or a distance with its extra bits) is decoded out of one window with 32-bit shifts.
+// ------------------------------------------------------------------------------------------------
+struct BitWin {   // identical in every lane
+    const uint32_t* base;   // aligned word that holds the first payload byte
+    uint32_t wi;            // index of the word in nx
+    uint32_t wlim;          // last word index that may be loaded (payload + one refill of slack)
+    uint32_t lo, hi, nx;
+    uint32_t bp;            // bits of `lo` consumed; < 32 after norm(), < 64 always (a trip takes at most 32 bits)
+    uint32_t bit0;          // misalignment of the payload in bits
+    __device__ __forceinline__ uint32_t load(uint32_t w) const { return __ldg(base + (w < wlim ? w : wlim)); }
+    __device__ __forceinline__ void seek(uint32_t byte) {
+        const uint32_t bits = bit0 + byte * 8u, w = bits >> 5;
+        bp = bits & 31u;
+        lo = load(w);
+        hi = load(w + 1u);
+        nx = load(w + 2u);
+        wi = w + 2u;
+    }
+    __device__ __forceinline__ void init(const uint8_t* p, uint32_t clen) {
+        const uintptr_t a = (uintptr_t)p;
+        base = (const uint32_t*)(a & ~(uintptr_t)3);
+        bit0 = (uint32_t)(a & 3) * 8u;
+        wlim = (bit0 + clen * 8u + 31u) / 32u + 2u;
+        seek(0);
+    }
+    __device__ __forceinline__ void norm() {
+        if (bp >= 32u) {
+            lo = hi;
+            hi = nx;
+            ++wi;
+            nx = load(wi);
+            bp -= 32u;
+        }
+    }
+    __device__ __forceinline__ uint32_t win() const { return __funnelshift_r(lo, hi, bp); }   // 32 valid bits after norm()
+    __device__ __forceinline__ uint32_t take(uint32_t n) {  // n <= 16 (header fields)
+        norm();
+        const uint32_t v = win() & ((1u << n) - 1u);
+        bp += n;
+        return v;
+    }
+    __device__ __forceinline__ uint32_t bits_used() const { return (wi - 2u) * 32u + bp - bit0; }
+    __device__ __forceinline__ uint32_t bytes_used() const { return (bits_used() + 7u) >> 3; }   // a partial byte counts
+};
+
+// floor(65536 / d) + 1: (x * c_rcp[d]) >> 16 == x / d for x <= 32, d in 1..31
+__constant__ uint16_t c_rcp[32] = {0, 0, 32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554, 5958, 5462, 5042, 4682, 4370,
+                                   4097, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
+
+__global__ void __launch_bounds__(kInflateWarps * 32, BQC_INFLATE_MINBLOCKS) k_inflate(const uint8_t* __restrict__ cin, const InflateBlock* __restrict__ blocks, uint32_t n_blocks,
+                                                                 uint8_t* out, uint32_t* ctl) {
+    extern __shared__ __align__(16) uint8_t inflate_smem[];
+    InflateTabs* tabs = reinterpret_cast<InflateTabs*>(inflate_smem);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gmask = 0xFFFFFFFFu;
+    const uint32_t lane8 = (lane & 3u) * 8u;
+    InflateTabs& T = tabs[threadIdx.x / 32u];
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(ctl, 1u);
+        b = __shfl_sync(gmask, b, 0);
+        if (b >= n_blocks) break;
+        const InflateBlock blk = blocks[b];
+        uint8_t* o = out + blk.obeg;
+        uint8_t* ol = o + lane;    // this lane's column of the output
+        const uint32_t isize = blk.isize;
+        uint32_t pos = 0;
+        BitWin br;
+        br.init(cin + blk.cbeg, blk.clen);
+        bool ok = true;
+        uint32_t last = 0;
+        uint32_t pend = kNone;     // deferred store of the last step of the previous match (per lane): offset in o
+        uint32_t pend_val = 0;
+        while (ok && !last) {
+            const uint32_t hdr = br.take(3);
+            last = hdr & 1u;
+            const uint32_t type = hdr >> 1;
+            if (type == 0u) {  // stored (RFC 1951 3.2.4)
+                br.bp = (br.bp + 7u) & ~7u;   // bit0 and the word size are multiples of 8
+                const uint32_t len = br.take(16);
+                const uint32_t nlen = br.take(16);
+                const uint32_t p = br.bytes_used();
+                if (len != (~nlen & 0xFFFFu) || pos + len > isize || p + len > blk.clen) { ok = false; break; }
+                const uint8_t* src = cin + blk.cbeg + p;
+                for (uint32_t j = lane; j < len; j += 32u) o[pos + j] = ldg8(src + j);
+                pos += len;
+                br.seek(p + len);
+                continue;
+            }
+            if (type == 3u) { ok = false; break; }
+            uint32_t nlit = 288, ndist = 30;
+            if (type == 1u) {  // fixed codes (3.2.6)
+                for (uint32_t s = lane; s < 288; s += 32u) T.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
+                for (uint32_t s = lane; s < 30; s += 32u) T.lens[288 + s] = 5;
+            } else {           // dynamic codes (3.2.7)
+                const uint32_t h = br.take(14);
+                nlit = (h & 31u) + 257u;
+                ndist = ((h >> 5) & 31u) + 1u;
+                const uint32_t ncl = (h >> 10) + 4u;
+                if (nlit > 286 || ndist > 30) { ok = false; break; }
+                if (lane < 19u) T.cl_lens[lane] = 0;
+                __syncwarp(gmask);
+                for (uint32_t i = 0; i < ncl; ++i) {
+                    const uint32_t v = br.take(3);
+                    if (lane == 0) T.cl_lens[c_cl_order[i]] = (uint8_t)v;
+                }
+                if (!inflate_build<kClBits, 2>(T, T.cl_lens, 19, T.cl_count, T.cl_sorted, T.cl, lane, gmask)) { ok = false; break; }
+                const uint32_t total = nlit + ndist;
+                uint32_t i = 0;
+                while (i < total) {
+                    br.norm();
+                    const uint32_t w = br.win();
+                    const uint32_t ce = T.cl[w & ((1u << kClBits) - 1u)];
+                    if (!ce) { ok = false; break; }  // code-length codes are at most 7 bits: every valid code is in the table
+                    const uint32_t cl = ce & 15u;
+                    const uint32_t sym = ce >> 16;
+                    if (sym < 16u) {
+                        br.bp += cl;
+                        if (lane == 0) T.lens[i] = (uint8_t)sym;
+                        ++i;
+                        __syncwarp(gmask);
+                        continue;
+                    }
+                    const uint32_t xb = sym == 16u ? 2u : sym == 17u ? 3u : 7u;
+                    const uint32_t x = (w >> cl) & ((1u << xb) - 1u);
+                    br.bp += cl + xb;
+                    uint32_t val = 0;
+                    const uint32_t rep = (sym == 18u ? 11u : 3u) + x;
+                    if (sym == 16u) {
+                        if (i == 0) { ok = false; break; }
+                        val = T.lens[i - 1];
+                    }
+                    if (i + rep > total) { ok = false; break; }
+                    for (uint32_t j = lane; j < rep; j += 32u) T.lens[i + j] = (uint8_t)val;
+                    i += rep;
+                    __syncwarp(gmask);
+                }
+                if (!ok) break;
+                if (T.lens[256] == 0) { ok = false; break; }  // no end-of-block code
+            }
+            if (!inflate_build<kLitBits, 0>(T, T.lens, nlit, T.lit_count, T.lit_sorted, T.lit, lane, gmask)) { ok = false; break; }
+            if (!inflate_build<kDistBits, 1>(T, T.lens + nlit, ndist, T.dist_count, T.dist_sorted, T.dist, lane, gmask)) { ok = false; break; }
+            // ---- symbols of this block ------------------------------------------------------------------
+            const uint32_t* lit = T.lit;
+            for (;;) {
+                br.norm();
+                uint32_t w = br.win();
+                uint32_t e = lit[w & ((1u << kLitBits) - 1u)];
+                if (e & kIsLiteral) {
+                    // Literals come in runs: the window holds 32 bits, enough for three codes of the primary table
+                    // and usually a fourth.
+                    uint32_t l = e & 15u, used = l, b0 = e >> 16, nl = 1;
+                    w >>= l;
+                    e = lit[w & ((1u << kLitBits) - 1u)];
+                    if (e & kIsLiteral) {
+                        l = e & 15u;
+                        used += l;
+                        w >>= l;
+                        b0 |= (e >> 8) & 0xFF00u;
+                        nl = 2;
+                        e = lit[w & ((1u << kLitBits) - 1u)];
+                        if (e & kIsLiteral) {
+                            l = e & 15u;
+                            used += l;
+                            w >>= l;
+                            b0 |= e & 0xFF0000u;
+                            nl = 3;
+                            e = lit[w & ((1u << kLitBits) - 1u)];   // zeros above the window: valid only if the code fits
+                            if ((e & kIsLiteral) && used + (e & 15u) <= 32u) {
+                                used += e & 15u;
+                                b0 |= (e << 8) & 0xFF000000u;
+                                nl = 4;
+                            }
+                        }
+                    }
+                    br.bp += used;
+                    if (pos + nl > isize) { ok = false; break; }
+                    if (lane < nl) ol[pos] = (uint8_t)(b0 >> lane8);
+                    pos += nl;
+                    continue;
+                }
+                uint32_t l = e & 15u;
+                if (!l) {
+                    e = inflate_decode_slow<kLitBits, 0>(T, (uint64_t)w, T.lit_count, T.lit_sorted);
+                    if (!e) { ok = false; break; }
+                    l = e & 15u;
+                    if (e & kIsLiteral) {   // a literal with a long code
+                        br.bp += l;
+                        if (pos >= isize) { ok = false; break; }
+                        if (lane == 0) o[pos] = (uint8_t)(e >> 16);
+                        pos += 1;
+                        continue;
+                    }
+                }
+                if (e & 0x200u) {     // end of block, or a symbol that must not occur
+                    br.bp += l;
+                    if (e & 0x100u) ok = false;
+                    break;
+                }
+                w >>= l;
+                const uint32_t eb = (e >> 4) & 15u;
+                const uint32_t len = (e >> 16) + (w & ~(0xFFFFFFFFu << eb));
+                br.bp += l + eb;          // <= 15 + 5 bits
+                br.norm();
+                w = br.win();
+                uint32_t d = T.dist[w & ((1u << kDistBits) - 1u)];
+                if (!(d & 15u)) {
+                    d = inflate_decode_slow<kDistBits, 1>(T, (uint64_t)w, T.dist_count, T.dist_sorted);
+                    if (!d) { ok = false; break; }
+                }
+                const uint32_t dl = d & 15u, deb = (d >> 4) & 15u;
+                w >>= dl;
+                const uint32_t dist = (d >> 16) + (w & ~(0xFFFFFFFFu << deb));
+                br.bp += dl + deb;        // <= 15 + 13 bits
+                if ((d & 0x200u) || dist > pos || pos + len > isize) { ok = false; break; }
+                // The copy is software-pipelined: the last step of a match is loaded now and stored when the
+                // next match arrives (or at the end of the BGZF block), so the L2 round trip of the load overlaps
+                // the decoding of the following symbols instead of stalling the warp at the store.
+                if (pend != kNone) { o[pend] = (uint8_t)pend_val; pend = kNone; }
+                __syncwarp(gmask);  // the bytes the match refers to were stored by other lanes
+                const uint32_t sp = pos - dist;
+                // an overlapping match repeats with period dist: lane j reads byte j mod dist
+                const uint32_t rc = dist < 32u ? (uint32_t)c_rcp[dist] : 0u;
+                uint32_t m = dist == 1u ? 0u : lane - dist * ((lane * rc) >> 16);   // lane % dist (lane itself when dist >= 32)
+                if (len <= 32u) {   // the common case: one step, no loop
+                    if (lane < len) { pend_val = o[sp + m]; pend = pos + lane; }
+                } else {
+                    uint32_t j = lane;
+                    if (dist >= len) {
+                        for (; j + 32u < len + lane; j += 32u) ol[pos + j - lane] = o[sp + j];   // all but the last step (uniform trip count)
+                        if (j < len) { pend_val = o[sp + j]; pend = pos + j; }
+                    } else if (dist < 32u) {
+                        const uint32_t step = dist == 1u ? 0u : 32u - dist * ((32u * rc) >> 16);   // 32 % dist
+                        for (; j + 32u < len + lane; j += 32u) {
+                            ol[pos + j - lane] = o[sp + m];
+                            m += step;
+                            if (m >= dist) m -= dist;
+                        }
+                        if (j < len) { pend_val = o[sp + m]; pend = pos + j; }
+                    } else {
+                        for (; j + 32u < len + lane; j += 32u) ol[pos + j - lane] = o[sp + j % dist];
                         if (j < len) { pend_val = o[sp + j % dist]; pend = pos + j; }
                     }
                 }

@@ -183,12 +183,14 @@ def test_stream_truncated_record_is_an_error(tmp_path):
 
 
 # ---- device-side BGZF inflate (kernel_inflate.cuh) --------------------------------------------------------------
-def _bgzf_roundtrip(tmp_path, lib_, level, pieces=1, with_header=False, engine_kwargs=None, monkey_env=None):
+def _bgzf_roundtrip(tmp_path, lib_, level, pieces=1, with_header=False, engine_kwargs=None, monkey_env=None, mutate=None):
     """Records -> BGZF (zlib at `level`) -> bqc_submit_bgzf -> .bamqc identical to the oracle's."""
     from bamqc_b200 import Engine, synth
     genome = util.small_genome()
     records, offsets = synth.generate(genome, lib_)
     n_bytes = int(offsets[-1])
+    if mutate:
+        mutate(records, offsets)
     fasta, bam = tmp_path / "ref.fa", tmp_path / "in.ubam"
     genome.write_fasta(fasta)
     synth.write_bam(bam, genome, lib_, records, n_bytes)
@@ -241,6 +243,37 @@ def test_device_inflate_tiny_input_fixed_huffman(tmp_path):
     from bamqc_b200 import synth
     _bgzf_roundtrip(tmp_path, synth.Library(seed=43, n_pairs=3), 6)
     _bgzf_roundtrip(tmp_path, synth.Library(seed=44, n_pairs=40), 9)
+
+
+def _repetitive_fields(records, offsets):
+    """Overwrite SEQ / QUAL of most records with periodic patterns: zlib then emits long matches (up to 258) at short
+    distances -- period 1 (runs), 2..31 (a step of 32 lanes wraps several times), 32..63 (overlapping but longer than a
+    warp step) -- next to the ordinary literal-heavy records."""
+    periods = [1, 2, 3, 5, 7, 16, 31, 32, 33, 40, 63]
+    for i in range(len(offsets) - 1):
+        mode = i % 13
+        if mode >= len(periods):
+            continue
+        o = int(offsets[i]) + 4   # past block_size
+        l_name = int(records[o + 8])
+        n_cig = int(records[o + 12]) | int(records[o + 13]) << 8
+        l_seq = int(records[o + 16]) | int(records[o + 17]) << 8 | int(records[o + 18]) << 16
+        seq = o + 32 + l_name + 4 * n_cig
+        qual = seq + (l_seq + 1) // 2
+        per = periods[mode]
+        pat_q = (np.arange(per, dtype=np.uint8) * 3 + 5 + mode) % 41
+        records[qual:qual + l_seq] = np.resize(pat_q, l_seq)
+        if i % 2:   # one-hot nibbles only (A, C, G, T), so the sequence stays a plain read
+            pat_s = np.array([0x11, 0x12, 0x48, 0x84, 0x21, 0x88, 0x14], dtype=np.uint8)[(np.arange(per) * 5 + mode) % 7]
+            n = l_seq // 2
+            records[seq:seq + n] = np.resize(pat_s, n)
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_device_inflate_long_overlapping_matches(tmp_path, level):
+    from bamqc_b200 import synth
+    _bgzf_roundtrip(tmp_path, synth.Library(seed=47 + level, n_pairs=2500, read_len=400, ins_mean=600.0, ins_min=400, ins_max=1000), level,
+                    mutate=_repetitive_fields)
 
 
 def test_device_inflate_corrupt_block_is_an_error(tmp_path):
