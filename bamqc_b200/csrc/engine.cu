@@ -227,7 +227,6 @@ struct bqc_engine {
                               // 6.2 / 7.3 / 4.85 / 4.55 / 7.25 ms -- the restructured kernel needs ~86 registers to keep its loads in flight
     int tune_lane_index = 1;  // BQC_LANE_INDEX=0: every lane's pass filters the whole batch (round 1 behaviour, A/B)
     int tune_inflate_streams = 2;                        // BQC_INFLATE_STREAMS=1: every k_inflate on the framing stream (one launch at a time), A/B
-    int tune_inflate = 2;                                // BQC_INFLATE=1: round-1 symbol loop (k_inflate_r1), A/B
     int tune_cov_bps = 6;                                // BQC_COV_BPS: k_cov_tiles CTAs per SM
     int tune_cov_overlap = 0;                            // BQC_COV_OVERLAP=1: coverage kernels on their own stream next to the table kernels.  Measured (cfg 2,
                                                          // same box, 2 runs each): 14.03 / 14.78 ms per 10 M records overlapped, 12.59 / 12.59 ms on one stream
@@ -475,7 +474,6 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     if (const char* v = getenv("BQC_FRAME_FORCE_REPAIR")) e->force_bad_frames = atoi(v) != 0;
     if (const char* v = getenv("BQC_SKETCH_V2")) e->tune_sketch_v2 = atoi(v);
     if (const char* v = getenv("BQC_COV_OVERLAP")) e->tune_cov_overlap = atoi(v);
-    if (const char* v = getenv("BQC_INFLATE")) e->tune_inflate = atoi(v);
     if (const char* v = getenv("BQC_INFLATE_STREAMS")) e->tune_inflate_streams = atoi(v);
     if (const char* v = getenv("BQC_LANE_INDEX")) e->tune_lane_index = atoi(v);
     if (const char* v = getenv("BQC_SKETCH_THREADS")) e->tune_sketch_threads = std::max(32, std::min(1024, atoi(v) & ~31));
@@ -532,7 +530,6 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
         }
         // opt in to large dynamic shared memory
         CU(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kInflateStreams * sizeof(InflateTabs))));
-        CU(cudaFuncSetAttribute(k_inflate_r1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kInflateStreams * sizeof(InflateTabs))));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->inflate_bps, k_inflate, (int)kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs)));
         if (e->inflate_bps < 1) e->inflate_bps = 1;
         CU(cudaFuncSetAttribute(k_stats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1177,8 +1174,7 @@ static int stream_stage_a(bqc_engine* e, const bqc_engine::Task& t) {
         if (t.n_blocks) {
             const int grid = (int)std::min<uint64_t>(((uint64_t)t.n_blocks + kInflateStreams - 1) / kInflateStreams, (uint64_t)e->n_sm * e->inflate_bps);
             ProfScope prof(e, 8, is);
-            if (e->tune_inflate == 1) k_inflate_r1<<<grid, kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs), is>>>(s.d_cin, s.d_blocks, t.n_blocks, d.bytes + kFrameHead, s.d_ictl);
-            else k_inflate<<<grid, kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs), is>>>(s.d_cin, s.d_blocks, t.n_blocks, d.bytes + kFrameHead, s.d_ictl);
+            k_inflate<<<grid, kInflateWarps * 32, kInflateStreams * sizeof(InflateTabs), is>>>(s.d_cin, s.d_blocks, t.n_blocks, d.bytes + kFrameHead, s.d_ictl);
             e->launches += 1;
         }
         if (is != e->frames) {

@@ -2,16 +2,25 @@
 // cost at src/bamqualcheck.cpp:306).  A BGZF file is a sequence of independent raw DEFLATE
 // streams of at most 64 KiB of output each (SAM/BAM specification section 4.1; RFC 1951), so one WARP inflates one
 // BGZF block and thousands of blocks are in flight:
-//   * every lane holds the same bit buffer and decodes the same symbol (warp-uniform control flow, no
-//     divergence); the Huffman tables of the current DEFLATE block live in shared memory (10-bit primary table
-//     for literal/length codes, 8-bit for distances, canonical bit-by-bit search for the rare longer codes);
-//   * a literal is stored by one lane; a match is copied by all 32 lanes (overlapping matches index the source
-//     modulo the distance, which reproduces the byte-by-byte semantics of LZ77);
+//   * every lane holds the same bit window and decodes the same symbol (warp-uniform control flow, no
+//     divergence); the Huffman tables of the current DEFLATE block live in shared memory (9-bit primary table
+//     for literal/length codes, 7-bit for distances, canonical bit-by-bit search for the rare longer codes);
+//   * literals are stored up to four at a time by the first lanes; a match is copied by all 32 lanes (overlapping
+//     matches index the source modulo the distance, which reproduces the byte-by-byte semantics of LZ77);
 //   * table construction from the code lengths is spread over the lanes (counts with shared-memory atomics,
 //     canonical codes from the sorted symbol list, bit-reversed fan-out into the primary table).
 // Blocks are handed out through an atomic ticket (compressed sizes vary).  Errors (bad block type, distance
 // before the start of the block, output size different from ISIZE, input overrun) set a flag per BGZF block; the
 // engine reports them as the reference's "Could not read record" failure.
+//
+// What bounds it (profiles/r2): a warp needs ~6 ms for a 64 KiB block whatever else runs, the symbol stream of BAM
+// data is match-dominated, and every instruction of the symbol loop is one issue slot for one symbol, so throughput =
+// resident warps x issue share / instructions per symbol.  Round 2 therefore (a) halved the tables (4.3 KB per warp
+// -> 36 warps per SM instead of 30, CTAs of two warps so that finished blocks free their slots early), (b) lets the
+// launches of consecutive submissions overlap (engine.cu, two inflate streams) because one 256 MB submission has
+// fewer blocks than the GPU has warp slots, and (c) cut the instructions of a match: 32-bit window out of three
+// resident input words (no refill between the length and the distance code), field extraction with bfe, table
+// entries laid out in bytes, the modulo only for overlapping matches.
 #pragma once
 
 namespace bqc {
@@ -23,32 +32,32 @@ struct InflateBlock {   // one BGZF block, filled by the host from the block hea
     uint32_t isize;     // inflated size (BGZF trailer)
 };
 
-// Lanes that inflate one BGZF block together.  Sub-warp groups (8 lanes per block, four blocks per warp, the
-// instructions of a step shared by the groups whose symbols take the same path) were measured: 32 GB/s against
-// 38 GB/s for a whole warp per block -- the tables of four blocks per warp leave 12 warps per SM, too few to hide
-// the latency of the dependent decode chain -- so a block gets a full warp.
-static const uint32_t kGroup = 32;
-static const uint32_t kInflateWarps = 6;          // warps per CTA
-static const uint32_t kInflateStreams = kInflateWarps * 32 / kGroup;   // BGZF blocks in flight per CTA
 #ifndef BQC_INFLATE_LITBITS
 #define BQC_INFLATE_LITBITS 9
 #endif
 #ifndef BQC_INFLATE_DISTBITS
 #define BQC_INFLATE_DISTBITS 7
 #endif
-#ifndef BQC_INFLATE_MINBLOCKS
-#define BQC_INFLATE_MINBLOCKS 6
+#ifndef BQC_INFLATE_WARPS
+#define BQC_INFLATE_WARPS 2
 #endif
+#ifndef BQC_INFLATE_MINBLOCKS
+#define BQC_INFLATE_MINBLOCKS 18
+#endif
+static const uint32_t kInflateWarps = BQC_INFLATE_WARPS;          // warps per CTA = BGZF blocks in flight per CTA
+static const uint32_t kInflateStreams = kInflateWarps;
 static const uint32_t kLitBits = BQC_INFLATE_LITBITS, kDistBits = BQC_INFLATE_DISTBITS, kClBits = 7;
 
-// Table entries are packed so that one shared-memory load yields everything a symbol needs:
-//   bits 0-3 code length (0 = the code is longer than the primary index: canonical search), bits 4-7 number of
-//   extra bits, bits 8-9 kind (0 literal, 1 length / distance, 2 end of block, 3 invalid symbol), bits 16-31 value
-//   (literal byte, length base, distance base; the symbol itself for the code-length alphabet), bit 10 literal.
-static const uint32_t kKindBase = 1u << 8, kKindEob = 2u << 8, kKindInvalid = 3u << 8;
-static const uint32_t kIsLiteral = 1u << 10;      // literal/length alphabet only: the entry is a literal byte (one test on the fast path)
+// Table entries are packed so that one shared-memory load yields everything a symbol needs, each field in its own
+// byte (one PRMT / LOP to extract):
+//   byte 0: bits 0-3 code length (0 = the code is longer than the primary index: canonical search), bit 4 the value
+//           is a base with extra bits (length / distance), bit 5 end of block (bits 4+5: a symbol that must not
+//           occur), bit 6 literal;
+//   byte 1: number of extra bits;   bytes 2-3: value (literal byte, length base, distance base; the symbol itself
+//           for the code-length alphabet).
+static const uint32_t kIsBase = 1u << 4, kIsEob = 1u << 5, kIsInvalid = kIsBase | kIsEob, kIsLiteral = 1u << 6;
 
-struct alignas(16) InflateTabs {                   // per group, shared memory
+struct alignas(16) InflateTabs {                   // per warp, shared memory
     uint32_t lit[1u << kLitBits];
     uint32_t dist[1u << kDistBits];
     uint32_t cl[1u << kClBits];
@@ -65,70 +74,106 @@ __constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2
 __constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
 __constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+// floor(65536 / d) + 1: (x * c_rcp[d]) >> 16 == x / d for x <= 32, d in 2..31
+__constant__ uint16_t c_rcp[32] = {0, 0, 32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554, 5958, 5462, 5042, 4682, 4370,
+                                   4097, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
 
 // packed entry of a symbol (without the code length)
 __device__ __forceinline__ uint32_t inflate_lit_entry(uint32_t s) {
     if (s < 256u) return (s << 16) | kIsLiteral;
-    if (s == 256u) return kKindEob;
-    if (s > 285u) return kKindInvalid;
-    return kKindBase | ((uint32_t)c_len_extra[s - 257u] << 4) | ((uint32_t)c_len_base[s - 257u] << 16);
+    if (s == 256u) return kIsEob;
+    if (s > 285u) return kIsInvalid;
+    return kIsBase | ((uint32_t)c_len_extra[s - 257u] << 8) | ((uint32_t)c_len_base[s - 257u] << 16);
 }
 __device__ __forceinline__ uint32_t inflate_dist_entry(uint32_t s) {
-    if (s > 29u) return kKindInvalid;
-    return kKindBase | ((uint32_t)c_dist_extra[s] << 4) | ((uint32_t)c_dist_base[s] << 16);
+    if (s > 29u) return kIsInvalid;
+    return kIsBase | ((uint32_t)c_dist_extra[s] << 8) | ((uint32_t)c_dist_base[s] << 16);
 }
 __device__ __forceinline__ uint32_t inflate_cl_entry(uint32_t s) { return s << 16; }
 
-struct BitReader {  // LSB-first bit stream (RFC 1951 section 3.1.1); identical in every lane
-    const uint8_t* in;
-    uint32_t pos;         // bytes folded into buf so far
-    uint64_t buf;
-    uint32_t cnt;         // valid bits in buf
-    // input words are fetched one refill ahead through aligned 32-bit loads: w0 = aligned word under pos, wn = the
-    // one after it (already in flight), sh = byte misalignment of the payload
-    const uint32_t* wp;
-    uint32_t w0, wn, sh;
-    __device__ __forceinline__ void seek(uint32_t p) {
-        pos = p;
-        buf = 0;
-        cnt = 0;
-        const uintptr_t a = (uintptr_t)(in + p);
-        wp = (const uint32_t*)(a & ~(uintptr_t)3);
-        sh = (uint32_t)(a & 3) * 8;
-        w0 = __ldg(wp);
-        wn = __ldg(++wp);
+__device__ __forceinline__ uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len) {   // len bits of x from bit pos (pos, len < 32)
+    uint32_t m;
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(0u), "r"(len));   // (bfe.u32 costs three more PRMTs: it truncates pos and len to 8 bits)
+    return (x >> pos) & m;
+}
+// table[w & mask] of a table at shared address table_saddr.  The tables are rewritten (plain stores) only between
+// __syncwarp()s outside the symbol loop, so the loads need no memory clobber.
+__device__ __forceinline__ uint32_t inflate_lds(uint32_t table_saddr, uint32_t w, uint32_t mask) {
+    uint32_t a, e;
+    asm("and.b32 %0, %1, %2;\n\tmad.lo.u32 %0, %0, 4, %3;" : "=&r"(a) : "r"(w), "r"(mask), "r"(table_saddr));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(a));
+    return e;
+}
+
+// The input as three consecutive aligned 32-bit words and a bit position: a 32-bit window is one funnel shift,
+// dropping bits is one add, and a whole trip (up to four literals, or a length and a distance with their extra
+// bits) is decoded between two refills.  Identical in every lane.
+struct BitWin {
+    const uint32_t* base;   // aligned word that holds the first payload byte
+    uint32_t wi;            // index of the word in nx
+    uint32_t wlim;          // last word index that may be loaded (payload + one refill of slack)
+    uint32_t lo, hi, nx;
+    uint32_t bp;            // bits of `lo` consumed; < 32 after norm(), < 96 always
+    uint32_t bit0;          // misalignment of the payload in bits
+    __device__ __forceinline__ uint32_t load(uint32_t w) const { return __ldg(base + (w < wlim ? w : wlim)); }
+    __device__ __forceinline__ void seek(uint32_t byte) {
+        const uint32_t bits = bit0 + byte * 8u, w = bits >> 5;
+        bp = bits & 31u;
+        lo = load(w);
+        hi = load(w + 1u);
+        nx = load(w + 2u);
+        wi = w + 2u;
     }
-    __device__ __forceinline__ void init(const uint8_t* p) { in = p; seek(0); }
-    __device__ __forceinline__ void refill() {  // afterwards cnt >= 32
-        if (cnt < 32u) {
-            const uint32_t v = sh ? __funnelshift_r(w0, wn, sh) : w0;
-            buf |= (uint64_t)v << cnt;
-            pos += 4;
-            cnt += 32;
-            w0 = wn;
-            wn = __ldg(++wp);
+    __device__ __forceinline__ void init(const uint8_t* p, uint32_t clen) {
+        const uintptr_t a = (uintptr_t)p;
+        base = (const uint32_t*)(a & ~(uintptr_t)3);
+        bit0 = (uint32_t)(a & 3) * 8u;
+        wlim = (bit0 + clen * 8u + 31u) / 32u + 2u;
+        seek(0);
+    }
+    __device__ __forceinline__ void shift() {
+        lo = hi;
+        hi = nx;
+        ++wi;
+        nx = load(wi);
+        bp -= 32u;
+    }
+    __device__ __forceinline__ void norm() {
+        if (bp >= 32u) {
+            shift();
+            if (bp >= 32u) shift();   // a match with long codes and many extra bits (up to 48 bits in one trip)
         }
     }
-    __device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t)buf & ((1u << n) - 1u); }
-    __device__ __forceinline__ void drop(uint32_t n) { buf >>= n; cnt -= n; }
-    __device__ __forceinline__ uint32_t take(uint32_t n) { uint32_t v = peek(n); drop(n); return v; }
-    __device__ __forceinline__ uint32_t bytes_used() const { return pos - (cnt >> 3); }  // bytes consumed (partial byte counts)
+    __device__ __forceinline__ uint32_t win() const { return __funnelshift_r(lo, hi, bp); }   // 32 valid bits after norm()
+    // 32 bits from bp for 32 <= bp < 64 as well (the distance code right after a length, without a refill)
+    __device__ __forceinline__ uint32_t win2() const {
+        const bool up = bp >= 32u;
+        return __funnelshift_r(up ? hi : lo, up ? nx : hi, bp);   // the shift amount wraps at 32
+    }
+    __device__ __forceinline__ uint32_t take(uint32_t n) {  // n <= 16 (header fields)
+        norm();
+        const uint32_t v = win() & ((1u << n) - 1u);
+        bp += n;
+        return v;
+    }
+    __device__ __forceinline__ uint32_t bits_used() const { return (wi - 2u) * 32u + bp - bit0; }
+    __device__ __forceinline__ uint32_t bytes_used() const { return (bits_used() + 7u) >> 3; }   // a partial byte counts
 };
 
 // Build the decoding tables of one alphabet from lens[0..n): count[], sorted[], the primary table (PB index bits)
 // and the entry state of the canonical search for longer codes.  WHICH: 0 literal/length, 1 distance, 2 code
 // lengths.  Returns false for an over-subscribed code.  Called by all lanes.
 template <uint32_t PB, uint32_t WHICH>
-__device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* lens, uint32_t n, uint16_t* count, uint16_t* sorted, uint32_t* tab, uint32_t lane, uint32_t gmask) {
-    __syncwarp(gmask);
-    for (uint32_t i = lane; i < 8; i += kGroup) reinterpret_cast<uint32_t*>(count)[i] = 0;
-    for (uint32_t i = lane; i < (1u << PB); i += kGroup) tab[i] = 0;
-    __syncwarp(gmask);
-    for (uint32_t s = lane; s < n; s += kGroup) {  // 16-bit counters updated through their 32-bit word
+__device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* lens, uint32_t n, uint16_t* count, uint16_t* sorted, uint32_t* tab, uint32_t lane) {
+    __syncwarp();
+    if (lane < 8u) reinterpret_cast<uint32_t*>(count)[lane] = 0;
+    for (uint32_t i = lane; i < (1u << PB); i += 32u) tab[i] = 0;
+    __syncwarp();
+    for (uint32_t s = lane; s < n; s += 32u) {  // 16-bit counters updated through their 32-bit word
         const uint32_t l = lens[s];
         atomicAdd(reinterpret_cast<uint32_t*>(count) + (l >> 1), 1u << (16 * (l & 1)));
     }
-    __syncwarp(gmask);
+    __syncwarp();
     if (lane == 0) {
         uint32_t code = 0, off = 0, left = 1, bad = 0;
         for (uint32_t l = 1; l < 16; ++l) {
@@ -151,10 +196,10 @@ __device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* len
                 if (l) sorted[T.offs[l]++] = (uint16_t)s;
             }
     }
-    __syncwarp(gmask);
+    __syncwarp();
     if (T.offs[0]) return false;
     const uint32_t total = T.off0[0];
-    for (uint32_t i = lane; i < total; i += kGroup) {
+    for (uint32_t i = lane; i < total; i += 32u) {
         const uint32_t s = sorted[i];
         const uint32_t l = lens[s];
         if (l <= PB) {
@@ -164,17 +209,17 @@ __device__ __forceinline__ bool inflate_build(InflateTabs& T, const uint8_t* len
             for (uint32_t k = r; k < (1u << PB); k += (1u << l)) tab[k] = entry;
         }
     }
-    __syncwarp(gmask);
+    __syncwarp();
     return true;
 }
 
-// Codes longer than the primary index: canonical search one bit at a time, entered with the state it has after
-// PB bits (no shorter code matched, or the primary entry would exist).  Needs >= 15 bits in the buffer.  Returns
-// the packed entry with the full code length, or 0 if no code matches.
+// Codes longer than the primary index: canonical search one bit at a time over the 32-bit window `w`, entered with
+// the state it has after PB bits (no shorter code matched, or the primary entry would exist).  Returns the packed
+// entry with the full code length, or 0 if no code matches.
 template <uint32_t PB, uint32_t WHICH>
-__device__ __noinline__ uint32_t inflate_decode_slow(const InflateTabs& T, uint64_t buf, const uint16_t* count, const uint16_t* sorted) {
-    uint32_t bits = (uint32_t)(buf >> PB);
-    int code = (int)((__brev((uint32_t)buf) >> (32u - PB)) << 1);
+__device__ __noinline__ uint32_t inflate_decode_slow(const InflateTabs& T, uint32_t w, const uint16_t* count, const uint16_t* sorted) {
+    uint32_t bits = w >> PB;
+    int code = (int)((__brev(w) >> (32u - PB)) << 1);
     int first = T.slow_first[WHICH], index = T.slow_index[WHICH];
     for (uint32_t len = PB + 1; len < 16; ++len) {
         code |= (int)(bits & 1u);
@@ -192,254 +237,32 @@ __device__ __noinline__ uint32_t inflate_decode_slow(const InflateTabs& T, uint6
     return 0;
 }
 
-// ctl[0] = ticket, ctl[1] = 1 + index of the first BGZF block that failed to inflate (0 = none; atomicMin on the
+// ctl[0] = ticket, ctl[1] = 1 + index of the first BGZF block that failed to inflate (0 = none; atomicMax on the
 // bitwise complement so that a zeroed word means "none")
-__global__ void __launch_bounds__(kInflateWarps * 32) k_inflate_r1(const uint8_t* __restrict__ cin, const InflateBlock* __restrict__ blocks, uint32_t n_blocks,
-                                                                 uint8_t* out, uint32_t* ctl) {
-    extern __shared__ __align__(16) uint8_t inflate_smem[];
-    InflateTabs* tabs = reinterpret_cast<InflateTabs*>(inflate_smem);
-    // kGroup lanes work on one BGZF block; the groups of a warp run the same code on different blocks, so the
-    // instructions of a step are issued once for all groups whose symbols take the same path (literal / match)
-    const uint32_t lane = threadIdx.x & (kGroup - 1u);                       // lane within the group
-    const uint32_t gbase = (threadIdx.x & 31u) & ~(kGroup - 1u);              // first lane of the group in its warp
-    const uint32_t gmask = (kGroup == 32u ? 0xFFFFFFFFu : ((1u << kGroup) - 1u) << gbase);
-    InflateTabs& T = tabs[threadIdx.x / kGroup];
-    for (;;) {
-        uint32_t b = 0;
-        if (lane == 0) b = atomicAdd(ctl, 1u);
-        b = __shfl_sync(gmask, b, gbase);
-        if (b >= n_blocks) break;
-        const InflateBlock blk = blocks[b];
-        uint8_t* o = out + blk.obeg;
-        const uint32_t isize = blk.isize;
-        uint32_t pos = 0;
-        BitReader br;
-        br.init(cin + blk.cbeg);
-        bool ok = true;
-        uint32_t last = 0;
-        uint32_t pend = kNone;     // deferred store of the last step of the previous match (per lane): offset in o
-        uint32_t pend_val = 0;
-        while (ok && !last) {
-            br.refill();
-            last = br.take(1);
-            const uint32_t type = br.take(2);
-            if (type == 0u) {  // stored (RFC 1951 3.2.4)
-                br.drop(br.cnt & 7u);
-                br.refill();
-                const uint32_t len = br.take(16);
-                br.refill();
-                const uint32_t nlen = br.take(16);
-                const uint32_t p = br.bytes_used();
-                if (len != (~nlen & 0xFFFFu) || pos + len > isize || p + len > blk.clen) { ok = false; break; }
-                for (uint32_t j = lane; j < len; j += kGroup) o[pos + j] = ldg8(br.in + p + j);
-                pos += len;
-                br.seek(p + len);
-                continue;
-            }
-            if (type == 3u) { ok = false; break; }
-            uint32_t nlit = 288, ndist = 30;
-            if (type == 1u) {  // fixed codes (3.2.6)
-                for (uint32_t s = lane; s < 288; s += kGroup) T.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
-                for (uint32_t s = lane; s < 30; s += kGroup) T.lens[288 + s] = 5;
-            } else {           // dynamic codes (3.2.7)
-                br.refill();
-                nlit = br.take(5) + 257;
-                ndist = br.take(5) + 1;
-                const uint32_t ncl = br.take(4) + 4;
-                if (nlit > 286 || ndist > 30) { ok = false; break; }
-                for (uint32_t s = lane; s < 19; s += kGroup) T.cl_lens[s] = 0;
-                __syncwarp(gmask);
-                for (uint32_t i = 0; i < ncl; ++i) {
-                    br.refill();
-                    const uint32_t v = br.take(3);
-                    if (lane == 0) T.cl_lens[c_cl_order[i]] = (uint8_t)v;
-                }
-                if (!inflate_build<kClBits, 2>(T, T.cl_lens, 19, T.cl_count, T.cl_sorted, T.cl, lane, gmask)) { ok = false; break; }
-                const uint32_t total = nlit + ndist;
-                uint32_t i = 0;
-                while (i < total) {
-                    br.refill();
-                    uint32_t ce = T.cl[br.peek(kClBits)];
-                    if (!ce) { ok = false; break; }  // code-length codes are at most 7 bits: every valid code is in the table
-                    br.drop(ce & 15u);
-                    const int sym = (int)(ce >> 16);
-                    if (sym < 16) {
-                        if (lane == 0) T.lens[i] = (uint8_t)sym;
-                        ++i;
-                        __syncwarp(gmask);
-                        continue;
-                    }
-                    uint32_t val = 0, rep;
-                    if (sym == 16) {
-                        if (i == 0) { ok = false; break; }
-                        val = T.lens[i - 1];
-                        rep = 3 + br.take(2);
-                    } else if (sym == 17) rep = 3 + br.take(3);
-                    else rep = 11 + br.take(7);
-                    if (i + rep > total) { ok = false; break; }
-                    for (uint32_t j = lane; j < rep; j += kGroup) T.lens[i + j] = (uint8_t)val;
-                    i += rep;
-                    __syncwarp(gmask);
-                }
-                if (!ok) break;
-                if (T.lens[256] == 0) { ok = false; break; }  // no end-of-block code
-            }
-            if (!inflate_build<kLitBits, 0>(T, T.lens, nlit, T.lit_count, T.lit_sorted, T.lit, lane, gmask)) { ok = false; break; }
-            if (!inflate_build<kDistBits, 1>(T, T.lens + nlit, ndist, T.dist_count, T.dist_sorted, T.dist, lane, gmask)) { ok = false; break; }
-            // ---- symbols of this block ------------------------------------------------------------------
-            for (;;) {
-                br.refill();
-                uint32_t e = T.lit[br.peek(kLitBits)];
-                if (!(e & 15u)) {
-                    e = inflate_decode_slow<kLitBits, 0>(T, br.buf, T.lit_count, T.lit_sorted);
-                    if (!e) { ok = false; break; }
-                }
-                br.drop(e & 15u);
-                if (!(e & 0x300u)) {  // literal
-                    // Literals come in runs: after a refill the buffer holds >= 32 bits, enough for two more codes of
-                    // the primary table, so up to three literals are taken per refill / loop trip.
-                    uint32_t b0 = e >> 16, nl = 1;
-                    uint32_t e2 = T.lit[br.peek(kLitBits)];
-                    if ((e2 & 15u) && !(e2 & 0x300u)) {
-                        br.drop(e2 & 15u);
-                        b0 |= (e2 >> 16) << 8;
-                        nl = 2;
-                        e2 = T.lit[br.peek(kLitBits)];
-                        if ((e2 & 15u) && (e2 & 15u) <= br.cnt && !(e2 & 0x300u)) {  // (the first code may have been a long one)
-                            br.drop(e2 & 15u);
-                            b0 |= (e2 >> 16) << 16;
-                            nl = 3;
-                        }
-                    }
-                    if (pos + nl > isize) { ok = false; break; }
-                    if (lane < nl) o[pos + lane] = (uint8_t)(b0 >> (8 * lane));
-                    pos += nl;
-                    continue;
-                }
-                if (e & 0x200u) {     // end of block, or a symbol that must not occur
-                    if (e & 0x100u) ok = false;
-                    break;
-                }
-                const uint32_t len = (e >> 16) + br.take((e >> 4) & 15u);
-                br.refill();
-                uint32_t d = T.dist[br.peek(kDistBits)];
-                if (!(d & 15u)) {
-                    d = inflate_decode_slow<kDistBits, 1>(T, br.buf, T.dist_count, T.dist_sorted);
-                    if (!d) { ok = false; break; }
-                }
-                br.drop(d & 15u);
-                const uint32_t dist = (d >> 16) + br.take((d >> 4) & 15u);
-                if ((d & 0x200u) || dist > pos || pos + len > isize) { ok = false; break; }
-                // The copy is software-pipelined: the last step of a match is loaded now and stored when the
-                // next match arrives (or at the end of the BGZF block), so the L2 round trip of the load overlaps
-                // the decoding of the following symbols instead of stalling the warp at the store.
-                if (pend != kNone) { o[pend] = (uint8_t)pend_val; pend = kNone; }
-                __syncwarp(gmask);  // the bytes the match refers to were stored by other lanes
-                const uint32_t sp = pos - dist;
-                if (len <= kGroup) {   // the common case: one step, no loop
-                    // an overlapping match repeats with period dist: lane j reads byte j mod dist (j < 32)
-                    uint32_t m = lane;
-                    if (dist < len) m = dist == 1u ? 0u : lane % dist;
-                    if (lane < len) { pend_val = o[sp + m]; pend = pos + lane; }
-                } else {
-                    uint32_t j = lane;
-                    if (dist >= len) {
-                        for (; j + kGroup < len + lane; j += kGroup) o[pos + j] = o[sp + j];   // all but the last step (uniform trip count)
-                        if (j < len) { pend_val = o[sp + j]; pend = pos + j; }
-                    } else {
-                        for (; j + kGroup < len + lane; j += kGroup) o[pos + j] = o[sp + j % dist];
-                        if (j < len) { pend_val = o[sp + j % dist]; pend = pos + j; }
-                    }
-                }
-                pos += len;
-            }
-            if (br.bytes_used() > blk.clen + 8u) ok = false;  // ran past the payload
-        }
-        if (pend != kNone) o[pend] = (uint8_t)pend_val;
-        if (ok && (pos != isize || br.bytes_used() > blk.clen)) ok = false;
-        if (!ok && lane == 0) atomicMax(ctl + 1, 0xFFFFFFFFu - b);  // largest complement = smallest index
-        __syncwarp(gmask);
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// Round 2 symbol loop.  k_inflate_r1 above spends ~95 warp instructions per trip of up to three literals and ~140
-// per match, most of them 64-bit buffer bookkeeping and re-derived addresses (profiles/r1, 69 % issue-bound).
-// BitWin keeps the stream as three consecutive aligned 32-bit words and a bit position: a 32-bit window is one
-// funnel shift, dropping bits is one add, and a whole trip (up to four literals, or a length with its extra bits,
-// or a distance with its extra bits) is decoded out of one window with 32-bit shifts.
-// ------------------------------------------------------------------------------------------------
-struct BitWin {   // identical in every lane
-    const uint32_t* base;   // aligned word that holds the first payload byte
-    uint32_t wi;            // index of the word in nx
-    uint32_t wlim;          // last word index that may be loaded (payload + one refill of slack)
-    uint32_t lo, hi, nx;
-    uint32_t bp;            // bits of `lo` consumed; < 32 after norm(), < 64 always (a trip takes at most 32 bits)
-    uint32_t bit0;          // misalignment of the payload in bits
-    __device__ __forceinline__ uint32_t load(uint32_t w) const { return __ldg(base + (w < wlim ? w : wlim)); }
-    __device__ __forceinline__ void seek(uint32_t byte) {
-        const uint32_t bits = bit0 + byte * 8u, w = bits >> 5;
-        bp = bits & 31u;
-        lo = load(w);
-        hi = load(w + 1u);
-        nx = load(w + 2u);
-        wi = w + 2u;
-    }
-    __device__ __forceinline__ void init(const uint8_t* p, uint32_t clen) {
-        const uintptr_t a = (uintptr_t)p;
-        base = (const uint32_t*)(a & ~(uintptr_t)3);
-        bit0 = (uint32_t)(a & 3) * 8u;
-        wlim = (bit0 + clen * 8u + 31u) / 32u + 2u;
-        seek(0);
-    }
-    __device__ __forceinline__ void norm() {
-        if (bp >= 32u) {
-            lo = hi;
-            hi = nx;
-            ++wi;
-            nx = load(wi);
-            bp -= 32u;
-        }
-    }
-    __device__ __forceinline__ uint32_t win() const { return __funnelshift_r(lo, hi, bp); }   // 32 valid bits after norm()
-    __device__ __forceinline__ uint32_t take(uint32_t n) {  // n <= 16 (header fields)
-        norm();
-        const uint32_t v = win() & ((1u << n) - 1u);
-        bp += n;
-        return v;
-    }
-    __device__ __forceinline__ uint32_t bits_used() const { return (wi - 2u) * 32u + bp - bit0; }
-    __device__ __forceinline__ uint32_t bytes_used() const { return (bits_used() + 7u) >> 3; }   // a partial byte counts
-};
-
-// floor(65536 / d) + 1: (x * c_rcp[d]) >> 16 == x / d for x <= 32, d in 1..31
-__constant__ uint16_t c_rcp[32] = {0, 0, 32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554, 5958, 5462, 5042, 4682, 4370,
-                                   4097, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
-
 __global__ void __launch_bounds__(kInflateWarps * 32, BQC_INFLATE_MINBLOCKS) k_inflate(const uint8_t* __restrict__ cin, const InflateBlock* __restrict__ blocks, uint32_t n_blocks,
-                                                                 uint8_t* out, uint32_t* ctl) {
+                                                                                        uint8_t* out, uint32_t* ctl) {
     extern __shared__ __align__(16) uint8_t inflate_smem[];
     InflateTabs* tabs = reinterpret_cast<InflateTabs*>(inflate_smem);
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t gmask = 0xFFFFFFFFu;
     const uint32_t lane8 = (lane & 3u) * 8u;
     InflateTabs& T = tabs[threadIdx.x / 32u];
+    const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(T.lit), dist_sa = (uint32_t)__cvta_generic_to_shared(T.dist);
+    const uint32_t kLitMask = (1u << kLitBits) - 1u, kDistMask = (1u << kDistBits) - 1u;
     for (;;) {
         uint32_t b = 0;
         if (lane == 0) b = atomicAdd(ctl, 1u);
-        b = __shfl_sync(gmask, b, 0);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
         if (b >= n_blocks) break;
         const InflateBlock blk = blocks[b];
         uint8_t* o = out + blk.obeg;
-        uint8_t* ol = o + lane;    // this lane's column of the output
+        uint8_t* ol = o + lane;    // this lane's column of the output: lane j of a step at offset p writes ol[p]
         const uint32_t isize = blk.isize;
         uint32_t pos = 0;
         BitWin br;
         br.init(cin + blk.cbeg, blk.clen);
         bool ok = true;
         uint32_t last = 0;
-        uint32_t pend = kNone;     // deferred store of the last step of the previous match (per lane): offset in o
+        uint32_t pend = kNone;     // deferred store of the last step of the previous match (per lane): offset in ol
         uint32_t pend_val = 0;
         while (ok && !last) {
             const uint32_t hdr = br.take(3);
@@ -461,7 +284,7 @@ __global__ void __launch_bounds__(kInflateWarps * 32, BQC_INFLATE_MINBLOCKS) k_i
             uint32_t nlit = 288, ndist = 30;
             if (type == 1u) {  // fixed codes (3.2.6)
                 for (uint32_t s = lane; s < 288; s += 32u) T.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
-                for (uint32_t s = lane; s < 30; s += 32u) T.lens[288 + s] = 5;
+                if (lane < 30u) T.lens[288 + lane] = 5;
             } else {           // dynamic codes (3.2.7)
                 const uint32_t h = br.take(14);
                 nlit = (h & 31u) + 257u;
@@ -469,12 +292,12 @@ __global__ void __launch_bounds__(kInflateWarps * 32, BQC_INFLATE_MINBLOCKS) k_i
                 const uint32_t ncl = (h >> 10) + 4u;
                 if (nlit > 286 || ndist > 30) { ok = false; break; }
                 if (lane < 19u) T.cl_lens[lane] = 0;
-                __syncwarp(gmask);
+                __syncwarp();
                 for (uint32_t i = 0; i < ncl; ++i) {
                     const uint32_t v = br.take(3);
                     if (lane == 0) T.cl_lens[c_cl_order[i]] = (uint8_t)v;
                 }
-                if (!inflate_build<kClBits, 2>(T, T.cl_lens, 19, T.cl_count, T.cl_sorted, T.cl, lane, gmask)) { ok = false; break; }
+                if (!inflate_build<kClBits, 2>(T, T.cl_lens, 19, T.cl_count, T.cl_sorted, T.cl, lane)) { ok = false; break; }
                 const uint32_t total = nlit + ndist;
                 uint32_t i = 0;
                 while (i < total) {
@@ -488,7 +311,7 @@ __global__ void __launch_bounds__(kInflateWarps * 32, BQC_INFLATE_MINBLOCKS) k_i
                         br.bp += cl;
                         if (lane == 0) T.lens[i] = (uint8_t)sym;
                         ++i;
-                        __syncwarp(gmask);
+                        __syncwarp();
                         continue;
                     }
                     const uint32_t xb = sym == 16u ? 2u : sym == 17u ? 3u : 7u;
@@ -503,39 +326,38 @@ __global__ void __launch_bounds__(kInflateWarps * 32, BQC_INFLATE_MINBLOCKS) k_i
                     if (i + rep > total) { ok = false; break; }
                     for (uint32_t j = lane; j < rep; j += 32u) T.lens[i + j] = (uint8_t)val;
                     i += rep;
-                    __syncwarp(gmask);
+                    __syncwarp();
                 }
                 if (!ok) break;
                 if (T.lens[256] == 0) { ok = false; break; }  // no end-of-block code
             }
-            if (!inflate_build<kLitBits, 0>(T, T.lens, nlit, T.lit_count, T.lit_sorted, T.lit, lane, gmask)) { ok = false; break; }
-            if (!inflate_build<kDistBits, 1>(T, T.lens + nlit, ndist, T.dist_count, T.dist_sorted, T.dist, lane, gmask)) { ok = false; break; }
+            if (!inflate_build<kLitBits, 0>(T, T.lens, nlit, T.lit_count, T.lit_sorted, T.lit, lane)) { ok = false; break; }
+            if (!inflate_build<kDistBits, 1>(T, T.lens + nlit, ndist, T.dist_count, T.dist_sorted, T.dist, lane)) { ok = false; break; }
             // ---- symbols of this block ------------------------------------------------------------------
-            const uint32_t* lit = T.lit;
             for (;;) {
                 br.norm();
                 uint32_t w = br.win();
-                uint32_t e = lit[w & ((1u << kLitBits) - 1u)];
+                uint32_t e = inflate_lds(lit_sa, w, kLitMask);
                 if (e & kIsLiteral) {
                     // Literals come in runs: the window holds 32 bits, enough for three codes of the primary table
                     // and usually a fourth.
                     uint32_t l = e & 15u, used = l, b0 = e >> 16, nl = 1;
                     w >>= l;
-                    e = lit[w & ((1u << kLitBits) - 1u)];
+                    e = inflate_lds(lit_sa, w, kLitMask);
                     if (e & kIsLiteral) {
                         l = e & 15u;
                         used += l;
                         w >>= l;
                         b0 |= (e >> 8) & 0xFF00u;
                         nl = 2;
-                        e = lit[w & ((1u << kLitBits) - 1u)];
+                        e = inflate_lds(lit_sa, w, kLitMask);
                         if (e & kIsLiteral) {
                             l = e & 15u;
                             used += l;
                             w >>= l;
                             b0 |= e & 0xFF0000u;
                             nl = 3;
-                            e = lit[w & ((1u << kLitBits) - 1u)];   // zeros above the window: valid only if the code fits
+                            e = inflate_lds(lit_sa, w, kLitMask);   // zeros above the window: valid only if the code fits
                             if ((e & kIsLiteral) && used + (e & 15u) <= 32u) {
                                 used += e & 15u;
                                 b0 |= (e << 8) & 0xFF000000u;
@@ -551,7 +373,7 @@ __global__ void __launch_bounds__(kInflateWarps * 32, BQC_INFLATE_MINBLOCKS) k_i
                 }
                 uint32_t l = e & 15u;
                 if (!l) {
-                    e = inflate_decode_slow<kLitBits, 0>(T, (uint64_t)w, T.lit_count, T.lit_sorted);
+                    e = inflate_decode_slow<kLitBits, 0>(T, w, T.lit_count, T.lit_sorted);
                     if (!e) { ok = false; break; }
                     l = e & 15u;
                     if (e & kIsLiteral) {   // a literal with a long code
@@ -562,64 +384,67 @@ __global__ void __launch_bounds__(kInflateWarps * 32, BQC_INFLATE_MINBLOCKS) k_i
                         continue;
                     }
                 }
-                if (e & 0x200u) {     // end of block, or a symbol that must not occur
+                if (e & kIsEob) {     // end of block, or a symbol that must not occur
                     br.bp += l;
-                    if (e & 0x100u) ok = false;
+                    if (e & kIsBase) ok = false;
                     break;
                 }
-                w >>= l;
-                const uint32_t eb = (e >> 4) & 15u;
-                const uint32_t len = (e >> 16) + (w & ~(0xFFFFFFFFu << eb));
-                br.bp += l + eb;          // <= 15 + 5 bits
-                br.norm();
-                w = br.win();
-                uint32_t d = T.dist[w & ((1u << kDistBits) - 1u)];
-                if (!(d & 15u)) {
-                    d = inflate_decode_slow<kDistBits, 1>(T, (uint64_t)w, T.dist_count, T.dist_sorted);
-                    if (!d) { ok = false; break; }
+                const uint32_t eb = __byte_perm(e, 0, 0x4441);
+                const uint32_t len = (e >> 16) + bfe32(w, l, eb);
+                br.bp += l + eb;          // <= 15 + 5 bits: bp < 52, the distance code is still inside lo:hi:nx
+                w = br.win2();
+                uint32_t d = inflate_lds(dist_sa, w, kDistMask);
+                uint32_t dl = d & 15u;
+                if (!dl) {
+                    d = inflate_decode_slow<kDistBits, 1>(T, w, T.dist_count, T.dist_sorted);
+                    if (!d || (d & kIsEob)) { ok = false; break; }   // (symbols 30/31 never reach the primary table: ndist <= 30)
+                    dl = d & 15u;
                 }
-                const uint32_t dl = d & 15u, deb = (d >> 4) & 15u;
-                w >>= dl;
-                const uint32_t dist = (d >> 16) + (w & ~(0xFFFFFFFFu << deb));
-                br.bp += dl + deb;        // <= 15 + 13 bits
-                if ((d & 0x200u) || dist > pos || pos + len > isize) { ok = false; break; }
+                const uint32_t deb = __byte_perm(d, 0, 0x4441);
+                const uint32_t dist = (d >> 16) + bfe32(w, dl, deb);
+                br.bp += dl + deb;        // <= 15 + 13 bits: bp < 80
+                if (dist > pos || pos + len > isize) { ok = false; break; }
                 // The copy is software-pipelined: the last step of a match is loaded now and stored when the
                 // next match arrives (or at the end of the BGZF block), so the L2 round trip of the load overlaps
                 // the decoding of the following symbols instead of stalling the warp at the store.
-                if (pend != kNone) { o[pend] = (uint8_t)pend_val; pend = kNone; }
-                __syncwarp(gmask);  // the bytes the match refers to were stored by other lanes
+                if (pend != kNone) { ol[pend] = (uint8_t)pend_val; pend = kNone; }
+                __syncwarp();  // the bytes the match refers to were stored by other lanes
                 const uint32_t sp = pos - dist;
-                // an overlapping match repeats with period dist: lane j reads byte j mod dist
-                const uint32_t rc = dist < 32u ? (uint32_t)c_rcp[dist] : 0u;
-                uint32_t m = dist == 1u ? 0u : lane - dist * ((lane * rc) >> 16);   // lane % dist (lane itself when dist >= 32)
-                if (len <= 32u) {   // the common case: one step, no loop
-                    if (lane < len) { pend_val = o[sp + m]; pend = pos + lane; }
+                if (len <= 32u && dist >= len) {   // the common case: one step, source and destination apart
+                    if (lane < len) { pend_val = ol[sp]; pend = pos; }
                 } else {
-                    uint32_t j = lane;
-                    if (dist >= len) {
-                        for (; j + 32u < len + lane; j += 32u) ol[pos + j - lane] = o[sp + j];   // all but the last step (uniform trip count)
-                        if (j < len) { pend_val = o[sp + j]; pend = pos + j; }
-                    } else if (dist < 32u) {
-                        const uint32_t step = dist == 1u ? 0u : 32u - dist * ((32u * rc) >> 16);   // 32 % dist
-                        for (; j + 32u < len + lane; j += 32u) {
-                            ol[pos + j - lane] = o[sp + m];
-                            m += step;
-                            if (m >= dist) m -= dist;
-                        }
-                        if (j < len) { pend_val = o[sp + m]; pend = pos + j; }
+                    // an overlapping match repeats with period dist: lane j reads byte j mod dist
+                    const uint32_t rc = dist < 32u ? (uint32_t)c_rcp[dist] : 0u;
+                    uint32_t m = dist == 1u ? 0u : lane - dist * ((lane * rc) >> 16);   // lane % dist (lane itself when dist >= 32)
+                    if (len <= 32u) {
+                        if (lane < len) { pend_val = o[sp + m]; pend = pos; }
                     } else {
-                        for (; j + 32u < len + lane; j += 32u) ol[pos + j - lane] = o[sp + j % dist];
-                        if (j < len) { pend_val = o[sp + j % dist]; pend = pos + j; }
+                        uint32_t j = lane;
+                        if (dist >= len) {
+                            for (; j + 32u < len + lane; j += 32u) o[pos + j] = o[sp + j];   // all but the last step (uniform trip count)
+                            if (j < len) { pend_val = o[sp + j]; pend = pos + j - lane; }
+                        } else if (dist < 32u) {
+                            const uint32_t step = dist == 1u ? 0u : 32u - dist * ((32u * rc) >> 16);   // 32 % dist
+                            for (; j + 32u < len + lane; j += 32u) {
+                                o[pos + j] = o[sp + m];
+                                m += step;
+                                if (m >= dist) m -= dist;
+                            }
+                            if (j < len) { pend_val = o[sp + m]; pend = pos + j - lane; }
+                        } else {
+                            for (; j + 32u < len + lane; j += 32u) o[pos + j] = o[sp + j % dist];
+                            if (j < len) { pend_val = o[sp + j % dist]; pend = pos + j - lane; }
+                        }
                     }
                 }
                 pos += len;
             }
             if (br.bytes_used() > blk.clen + 8u) ok = false;  // ran past the payload
         }
-        if (pend != kNone) o[pend] = (uint8_t)pend_val;
+        if (pend != kNone) ol[pend] = (uint8_t)pend_val;
         if (ok && (pos != isize || br.bytes_used() > blk.clen)) ok = false;
         if (!ok && lane == 0) atomicMax(ctl + 1, 0xFFFFFFFFu - b);  // largest complement = smallest index
-        __syncwarp(gmask);
+        __syncwarp();
     }
 }
 
