@@ -224,7 +224,9 @@ struct bqc_engine {
     int tune_stats_bps = 0, tune_sketch_threads = 1024, tune_stats_stage = 1;  // BQC_STATS_STAGE=0: k_stats reads records straight from global memory (A/B tests)
     int tune_sketch_v2 = 3;   // BQC_SKETCH_V2: 0 = k_sketch32 of round 1 (per-base ballot, pair table), 1/2/3/4 = k_sketch32v2 with
                               // 1024/512/640/768 threads per CTA (64/88/86/80 registers).  Measured per 10 M cfg2 records (serialised):
-                              // 6.2 / 7.3 / 4.85 / 4.55 / 7.25 ms -- the restructured kernel needs ~86 registers to keep its loads in flight
+                              // 6.2 / 7.3 / 4.85 / 4.55 / 7.25 ms -- the restructured kernel needs ~86 registers to keep its loads in flight.
+                              // With SEQ/QUAL streamed as aligned 8-byte words (each sector fetched 4x instead of 8-16x): 3.96 ms at 640
+                              // threads (94 registers), 4.06 at 512, 7.6 at 768 (80 registers: spills the stream)
     int tune_lane_index = 1;  // BQC_LANE_INDEX=0: every lane's pass filters the whole batch (round 1 behaviour, A/B)
     int tune_inflate_streams = 2;                        // BQC_INFLATE_STREAMS=1: every k_inflate on the framing stream (one launch at a time), A/B
     int tune_cov_bps = 6;                                // BQC_COV_BPS: k_cov_tiles CTAs per SM

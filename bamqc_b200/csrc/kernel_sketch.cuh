@@ -52,6 +52,42 @@ struct SketchProbe {  // one in-flight probe per lane: the word was loaded, the 
     }
 };
 
+// k_sketch32v2: the increment is pipelined one stage further.  A probe goes through three drains of the warp's queue:
+// the sketch word is loaded (issue), the CAS of the incremented word is sent (cas), and only then is its outcome looked
+// at (check) -- the L2 round trips of the load and of the CAS both overlap the hashing of the next 8 bases of every
+// lane instead of stalling the warp (the blocking CAS loop of SketchProbe held 38 % of the stall samples of the
+// kernel, profiles/r2).  A CAS that lost a race (rare: another warp hit the same 32-bit word in between) is
+// repeated in place.
+struct SketchProbe2 {
+    uint32_t word, sh, old;              // stage 1: word index (kNone: empty), nibble shift, loaded value
+    uint32_t cword, csh, cexp, cold;     // stage 2: CAS sent with expected value cexp, cold = what it returned
+    __device__ __forceinline__ void check(uint32_t* sk) {    // stage 2 -> done
+        if (cword != kNone) {
+            while (cold != cexp && ((cold >> csh) & 15u) != 15u) {
+                cexp = cold;
+                cold = atomicCAS(sk + cword, cexp, cexp + (1u << csh));
+            }
+            cword = kNone;
+        }
+    }
+    __device__ __forceinline__ void advance(uint32_t* sk) {  // check the CAS in flight, send the CAS of the loaded word
+        check(sk);
+        if (word != kNone) {
+            if (((old >> sh) & 15u) != 15u) {  // 4-bit saturating increment
+                cword = word;
+                csh = sh;
+                cexp = old;
+                cold = atomicCAS(sk + word, old, old + (1u << sh));
+            }
+            word = kNone;
+        }
+    }
+    __device__ __forceinline__ void finish(uint32_t* sk) {
+        advance(sk);
+        check(sk);
+    }
+};
+
 __global__ void __launch_bounds__(kSketchThreads, 1) k_sketch32(EngineView E, BatchView B, uint32_t lane, SketchParams SP, const HashTables* __restrict__ HT) {
     extern __shared__ uint32_t sm[];                 // F2 table (f2size u32), the pair table, the per-warp hash queues
     const Layout& L = E.L;
@@ -254,10 +290,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_sketch32v2(EngineView E, BatchVi
     const uint32_t lt_mask = (1u << lane_id) - 1u;
     const uint32_t queue_s = (uint32_t)__cvta_generic_to_shared(queue);
     uint32_t qn = 0;                                 // queued hashes of this warp (uniform, < 32 between sub-chunks)
-    SketchProbe probe = {kNone, 0u, 0u};
+    SketchProbe2 probe = {kNone, 0u, 0u, kNone, 0u, 0u, 0u};
 
     auto probe_issue = [&](uint64_t hv) {            // StreamCounter::operator() (src/kmerstream/StreamCounter.hpp:67-93)
-        probe.finish(sk);
+        probe.advance(sk);
         atomicAdd(sm + ((uint32_t)hv & f2mask), 1u);
         uint32_t w = hv ? (uint32_t)(__ffsll((long long)hv) - 1) : 63u;  // bitScanForward, 63 for 0
         if (w > 31u) w = 31u;
@@ -288,14 +324,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_sketch32v2(EngineView E, BatchVi
         const uint32_t out_lo = sm_out + s * 2048u + (lane_id & 7u) * 16u;
         uint64_t hlo = 0, tlo = 0;
         uint32_t hhi = 0, thi = 0;                    // top 32 bits of h.hi, low 32 bits of ht.hi
-        uint32_t seq_cur = ldu32(seqp), seq_next = ldu32(seqp + 4);   // 8 bases each; loads run two sub-chunks ahead
-        uint64_t q_cur = ldu64(qualp), q_next = ldu64(qualp + 8);
+        // SEQ and QUAL are read as streams of ALIGNED 8-byte words, each loaded once and realigned in registers (one
+        // SEQ word = 16 bases = two sub-chunks, one QUAL word per sub-chunk), two sub-chunks ahead of their use.  A lane
+        // reads its own record, so every load touches 32 sectors per warp whatever its width: with the unaligned 4- and
+        // 8-byte loads of the first version (two aligned loads each) a sector was fetched 16 times for SEQ and 8 times for
+        // QUAL and the L1 data pipe was the busiest unit of the kernel (78 %, profiles/r2); now it is 4 times each.
+        const uint64_t* sA = reinterpret_cast<const uint64_t*>((uintptr_t)seqp & ~(uintptr_t)7);
+        const uint64_t* qA = reinterpret_cast<const uint64_t*>((uintptr_t)qualp & ~(uintptr_t)7);
+        const uint32_t ssh = ((uint32_t)(uintptr_t)seqp & 7u) * 8u, qsh = ((uint32_t)(uintptr_t)qualp & 7u) * 8u;
+        auto align64 = [](uint64_t a, uint64_t b, uint32_t sh) { return (a >> sh) | ((b << 1) << (63u - sh)); };
+        uint64_t A0 = __ldg(sA), A1 = __ldg(sA + 1);
+        uint64_t Q0 = __ldg(qA), Q1 = __ldg(qA + 1), Q2 = __ldg(qA + 2);
         uint32_t lag0 = 0, lag1 = 0, lag2 = 0, lag3 = 0;  // SEQ words of the last 4 sub-chunks, oldest first (the base leaving a 32-window sits 4 words back)
         uint32_t vh = 0;                              // validity of the last 32 bases, newest in bit 0
         const uint32_t nsub = (maxL + kSketchSub - 1u) / kSketchSub;
-        for (uint32_t c = 0; c < nsub; ++c) {
-            const uint32_t seq_next2 = ldu32(seqp + 4u * (c + 2u));         // reads past a short record stay inside the padded batch
-            const uint64_t q_next2 = ldu64(qualp + 8u * (c + 2u));
+        auto sub_chunk = [&](const uint32_t c, const uint32_t seq_cur, uint64_t q_cur) {
             // ---- pass 1: which of the 8 bases end a window of 32 valid bases
             const uint32_t left = Ls > 8u * c ? Ls - 8u * c : 0u;           // bases of the read from here on
             if (left < 8u) q_cur |= ~0ULL << (8u * left);                   // past the end: quality 255 = not valid
@@ -338,8 +381,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_sketch32v2(EngineView E, BatchVi
                 }
             }
             lag0 = lag1; lag1 = lag2; lag2 = lag3; lag3 = seq_cur;
-            seq_cur = seq_next; seq_next = seq_next2;
-            q_cur = q_next; q_next = q_next2;
             if (total) {  // warp-uniform
                 __syncwarp();
                 warp_count += total;
@@ -355,6 +396,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_sketch32v2(EngineView E, BatchVi
                 qn = rest;
                 __syncwarp();
             }
+        };
+        for (uint32_t c = 0; c < nsub; c += 2u) {
+            const uint64_t A2 = __ldg(sA + (c >> 1) + 2u);                  // reads past a short record stay inside the padded batch
+            const uint64_t Q3 = __ldg(qA + c + 3u), Q4 = __ldg(qA + c + 4u);
+            const uint64_t sv = align64(A0, A1, ssh);
+            sub_chunk(c, (uint32_t)sv, align64(Q0, Q1, qsh));
+            if (c + 1u < nsub) sub_chunk(c + 1u, (uint32_t)(sv >> 32), align64(Q1, Q2, qsh));
+            A0 = A1; A1 = A2;
+            Q0 = Q2; Q1 = Q3; Q2 = Q4;
         }
     }
     __syncwarp();
