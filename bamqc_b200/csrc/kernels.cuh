@@ -339,8 +339,16 @@ __global__ void __launch_bounds__(kEightThreads, 1) k_eightmer(EngineView E, Bat
         uint32_t prev = 0;        // packed codes of the previous chunk
         uint32_t since_n = 0;     // bases since the last N (or the start of the read) at the start of the chunk, saturating
         const uint32_t nch = (Ls + 15u) >> 4;
+        // SEQ as a stream of aligned 8-byte words, each loaded once, one chunk ahead of its use, realigned in registers
+        // (an unaligned ldu64 per chunk is two loads that both wait right before their first use)
+        const uint64_t* sA = reinterpret_cast<const uint64_t*>((uintptr_t)seqp & ~(uintptr_t)7);
+        const uint32_t ssh = ((uint32_t)(uintptr_t)seqp & 7u) * 8u;
+        uint64_t A0 = __ldg(sA), A1 = __ldg(sA + 1);
         for (uint32_t c = 0; c < nch; ++c) {
-            const uint64_t R = swar_swap_nibbles(ldu64(seqp + 8u * c));   // base j of the chunk in nibble j
+            const uint64_t A2 = __ldg(sA + c + 2u);                       // (past a short record: still inside the padded batch)
+            const uint64_t R = swar_swap_nibbles((A0 >> ssh) | ((A1 << 1) << (63u - ssh)));   // base j of the chunk in nibble j
+            A0 = A1;
+            A1 = A2;
             const uint32_t rem = Ls - 16u * c;                             // bases of the read in this chunk (>= 1)
             const uint64_t inr = rem >= 16u ? ~0ULL : (1ULL << (4u * rem)) - 1ULL;
             const uint64_t s2 = (R & 0x5555555555555555ULL) + ((R >> 1) & 0x5555555555555555ULL);
