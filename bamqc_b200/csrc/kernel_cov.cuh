@@ -170,7 +170,7 @@ __device__ __forceinline__ void cov_walk_cigar(const uint8_t* p, F emit) {
 // not duplicate, rID in the -c set) and their (rid, begin, interval), compacted in file order.
 // ------------------------------------------------------------------------------------------------
 // append != 0 (shard mode): the records are added behind the carry->nq already collected instead of replacing them.
-__global__ void __launch_bounds__(kCovPrepThreads) k_cov_prep(EngineView E, BatchView B, uint32_t lane, CovScratch S, CovCarry* carry, uint32_t append) {
+__global__ void __launch_bounds__(kCovPrepThreads, 2) k_cov_prep(EngineView E, BatchView B, uint32_t lane, CovScratch S, CovCarry* carry, uint32_t append) {
     __shared__ uint32_t ws[33];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;

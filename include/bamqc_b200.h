@@ -132,7 +132,7 @@ int bqc_get_error(bqc_engine* e, bqc_error_info* out); /* sticky device/host err
 
 /* Optional device timing of each kernel family with CUDA events on the compute stream.
  * bqc_profile_read: milliseconds and launch-group counts accumulated since the previous read, per family:
- * 0 k_stats, 1 k_eightmer, 2 k_sketch, 3 coverage kernels (own stream), 4 merge/export, 5-6 host framing / header
+ * 0 k_stats, 1 k_eightmer, 2 k_sketch, 3 coverage kernels, 4 merge/export, 5-6 host framing / header
  * pre-pass of host-framed submissions (wall clock), 7 unused, 8 k_inflate, 9 framing kernels. */
 void bqc_profile_enable(bqc_engine* e, int on);
 int bqc_profile_read(bqc_engine* e, double ms_out[12], uint64_t n_out[12]);
