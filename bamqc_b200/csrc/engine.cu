@@ -230,8 +230,11 @@ struct bqc_engine {
     int tune_lane_index = 1;  // BQC_LANE_INDEX=0: every lane's pass filters the whole batch (round 1 behaviour, A/B)
     int tune_inflate_streams = 2;                        // BQC_INFLATE_STREAMS=1: every k_inflate on the framing stream (one launch at a time), A/B
     int tune_cov_bps = 6;                                // BQC_COV_BPS: k_cov_tiles CTAs per SM
-    int tune_cov_overlap = 0;                            // BQC_COV_OVERLAP=1: coverage kernels on their own stream next to the table kernels.  Measured (cfg 2,
-                                                         // same box, 2 runs each): 14.03 / 14.78 ms per 10 M records overlapped, 12.59 / 12.59 ms on one stream
+    int tune_cov_overlap = 2;                            // BQC_COV_OVERLAP: 1 = coverage kernels on their own stream next to the table kernels, 0 = on the
+                                                         // compute stream, 2 = by batch size.  Measured on one box, kernel-only M records/s, one resident batch
+                                                         // of 64 / 128 / 256 / 512 / 1024 / 2048 MB: own stream 469 / 587 / 678 / 732 / 785 / 806, compute stream
+                                                         // 416 / 540 / 643 / 728 / 794 / 823; three 1 GB batches (cfg 2): 12.0 ms on one stream, 12.5 on two
+    bool cov_overlap_now = false;                        // decision for the batch in flight (run_device_batch)
     uint64_t records_seen = 0, frames_repaired = 0;
     std::atomic<uint64_t> launches{0};   // kernels launched (commit thread, anchor thread, caller)
     bool finished = false;
@@ -776,7 +779,10 @@ struct ProfScope {  // records an event pair around the launches of one kernel f
     }
 };
 extern "C" void bqc_profile_enable(bqc_engine* e, int on) { e->profiling = on != 0; e->prof_serial = on == 2; }
-static inline cudaStream_t cov_stream(bqc_engine* e) { return (e->prof_serial || !e->tune_cov_overlap) ? e->compute : e->covs; }
+static inline cudaStream_t cov_stream(bqc_engine* e) {
+    if (e->prof_serial || e->tune_cov_overlap == 0) return e->compute;
+    return (e->tune_cov_overlap == 1 || e->cov_overlap_now) ? e->covs : e->compute;
+}
 // Accumulated device time per kernel family since the last call: 0 k_stats, 1 k_eightmer, 2 k_sketch,
 // 3 coverage flush (3 kernels per launch group), 4 merge/export.  Synchronises the compute stream.
 extern "C" int bqc_profile_read(bqc_engine* e, double ms_out[12], uint64_t n_out[12]) {
@@ -1076,6 +1082,9 @@ static int run_device_batch(bqc_engine* e, const DeviceBatch& d) {
     BatchLaunch BL;
     int rc = batch_launch_setup(e, d, BL);
     if (rc) return rc;
+    // small batches: the coverage kernels (many short launches) hide behind k_stats; large ones: they only delay the CTAs of
+    // the persistent table kernels.  Either way the two streams hand over through cov_go / cov_done.
+    e->cov_overlap_now = d.n_bytes < (384ull << 20);
     CU(cudaEventRecord(e->cov_go, e->compute));
     CU(cudaStreamWaitEvent(e->covs, e->cov_go, 0));
     rc = launch_cov(e, d, BL);
