@@ -234,6 +234,8 @@ struct bqc_engine {
                                                          // compute stream, 2 = by batch size.  Measured on one box, kernel-only M records/s, one resident batch
                                                          // of 64 / 128 / 256 / 512 / 1024 / 2048 MB: own stream 469 / 587 / 678 / 732 / 785 / 806, compute stream
                                                          // 416 / 540 / 643 / 728 / 794 / 823; three 1 GB batches (cfg 2): 12.0 ms on one stream, 12.5 on two
+    int tune_tickets = 1;                                // BQC_TICKETS=0: static grid-stride split of the records in the persistent table kernels (A/B)
+    uint32_t* d_tab_tickets = nullptr;                   // [256] work counters of the table kernels (kernels.cuh BatchView::tickets)
     bool cov_overlap_now = false;                        // decision for the batch in flight (run_device_batch)
     uint64_t records_seen = 0, frames_repaired = 0;
     std::atomic<uint64_t> launches{0};   // kernels launched (commit thread, anchor thread, caller)
@@ -361,6 +363,7 @@ extern "C" void bqc_destroy(bqc_engine* e) {
     cudaFree(e->d_cov_scratch);
     cudaFree(e->d_cov_q);
     cudaFree(e->d_cov_fn);
+    cudaFree(e->d_tab_tickets);
     cudaFree(e->d_error);
     cudaFree((void*)e->d_ref);
     cudaFree(e->d_ref_len);
@@ -479,6 +482,7 @@ extern "C" int bqc_create(const bqc_config* cfg, bqc_engine** out) {
     if (const char* v = getenv("BQC_FRAME_FORCE_REPAIR")) e->force_bad_frames = atoi(v) != 0;
     if (const char* v = getenv("BQC_SKETCH_V2")) e->tune_sketch_v2 = atoi(v);
     if (const char* v = getenv("BQC_COV_OVERLAP")) e->tune_cov_overlap = atoi(v);
+    if (const char* v = getenv("BQC_TICKETS")) e->tune_tickets = atoi(v);
     if (const char* v = getenv("BQC_INFLATE_STREAMS")) e->tune_inflate_streams = atoi(v);
     if (const char* v = getenv("BQC_LANE_INDEX")) e->tune_lane_index = atoi(v);
     if (const char* v = getenv("BQC_SKETCH_THREADS")) e->tune_sketch_threads = std::max(32, std::min(1024, atoi(v) & ~31));
@@ -1037,6 +1041,11 @@ static int launch_tables(bqc_engine* e, const DeviceBatch& d, const BatchLaunch&
         B.n_records = (uint32_t)n;
         B.cycb = BL.cycb;
         B.first_record = d.first_record;
+        if (e->tune_tickets && 2u + e->qlist.size() * e->klist.size() <= 256u) {
+            if (!e->d_tab_tickets) CU(cudaMalloc(&e->d_tab_tickets, 256 * 4));
+            CU(cudaMemsetAsync(e->d_tab_tickets, 0, 256 * 4, e->compute));
+            B.tickets = e->d_tab_tickets;
+        }
         int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * BL.bps);
         {
             ProfScope prof(e, 0);

@@ -304,8 +304,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_sketch32v2(EngineView E, BatchVi
     };
 
     const LaneRecords LR = lane_records(B, lane);
-    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id; r0 < LR.n; r0 += gridDim.x * blockDim.x) {
+    uint32_t* const ticket = B.tickets ? B.tickets + 2u + SP.qk : nullptr;
+    uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id;
+    for (;;) {
+        if (ticket) r0 = warp_take32(ticket, lane_id);
+        if (r0 >= LR.n) break;
         const uint32_t ri = r0 + lane_id;
+        if (!ticket) r0 += gridDim.x * blockDim.x;
         const uint32_t rec = ri < LR.n ? LR[ri] : 0u;
         RecHdr h;
         bool act = ri < LR.n && lane_match(B, rec, lane);

@@ -365,17 +365,17 @@ __global__ void __launch_bounds__(kStatsThreads, kStatsThreads > 256 ? 1 : (STAG
             }
         }
     };
-    uint32_t iters = 0;
     const LaneRecords LR = lane_records(B, lane);
-    for (uint32_t cta0 = blockIdx.x * blockDim.x; cta0 < LR.n; cta0 += gridDim.x * blockDim.x) {
-        if (++iters == kStatsUnpackEvery) {   // (uniform over the CTA: cta0 is)
-            __syncthreads();
-            unpack();
-            __syncthreads();
-            iters = 0;
-        }
-        const uint32_t r0 = cta0 + threadIdx.x - lane_id;
-        if (r0 >= LR.n) continue;
+    // Epochs of at most kStatsUnpackEvery - 1 warp iterations (32 records each) per warp, then the CTA empties its packed
+    // cells.  A warp gets its records from a ticket (B.tickets) or, without one, from the static grid-stride split.
+    uint32_t cta0 = blockIdx.x * blockDim.x;
+    for (;;) {
+    bool more = true;
+    for (uint32_t it = 0; it + 1u < kStatsUnpackEvery; ++it) {
+        uint32_t r0;
+        if (B.tickets) r0 = warp_take32(B.tickets, lane_id);
+        else { r0 = cta0 + threadIdx.x - lane_id; cta0 += gridDim.x * blockDim.x; }
+        if (r0 >= LR.n) { more = false; break; }
         const uint32_t n_here = min(32u, LR.n - r0);
         uint32_t off = 0, end = 0;
         const uint32_t myrec = lane_id < n_here ? LR[r0 + lane_id] : 0u;   // (staged launches never use an index list: myrec = r0 + lane_id)
@@ -416,9 +416,11 @@ __global__ void __launch_bounds__(kStatsThreads, kStatsThreads > 256 ? 1 : (STAG
             sub += m;
         }
     }
-    __syncthreads();
+    const int any = __syncthreads_or(more ? 1 : 0);
     unpack();
     __syncthreads();
+    if (!any) break;
+    }
     // ---- flush the CTA-private tables (skip zeros) ---------------------------------------------------
     auto flush = [&](uint32_t smo, uint32_t n, uint64_t* g) {
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {

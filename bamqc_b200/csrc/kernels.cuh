@@ -38,7 +38,18 @@ struct BatchView {
     uint32_t n_records;
     uint32_t cycb;             // per-cycle smem capacity for this batch (>= max l_seq, multiple of 8)
     uint64_t first_record;     // global index of record 0 (error reporting)
+    uint32_t* tickets = nullptr;  // zeroed before every lane pass: [0] k_stats, [1] k_eightmer, [2 + qk] sketch kernels -- the
+                               // persistent table kernels take warps of 32 records from these counters instead of a
+                               // static round-robin split (a CTA that becomes resident late, e.g. behind a coverage CTA,
+                               // then simply takes fewer records); NULL = static split
 };
+
+// next 32 records of a warp: a ticket (all lanes get the same value), or the static grid-stride position
+__device__ __forceinline__ uint32_t warp_take32(uint32_t* ticket, uint32_t lane_id) {
+    uint32_t r0 = 0;
+    if (lane_id == 0) r0 = atomicAdd(ticket, 32u);
+    return __shfl_sync(0xFFFFFFFFu, r0, 0);
+}
 
 struct EngineView {
     Layout L;
@@ -325,7 +336,14 @@ __global__ void __launch_bounds__(kEightThreads, 1) k_eightmer(EngineView E, Bat
     // A window counts iff it holds no literal N (:146-166): a nibble-stride mask of "N among the last eight bases",
     // with the distance to the last N carried between chunks (starting at 0, which also rules out the first 7 ends).
     const LaneRecords LR = lane_records(B, lane);
-    for (uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x; ri < LR.n; ri += gridDim.x * blockDim.x) {
+    const uint32_t lane_id = threadIdx.x & 31u;
+    uint32_t w0 = blockIdx.x * blockDim.x + threadIdx.x - lane_id;   // first record of this warp's 32
+    for (;;) {
+        if (B.tickets) w0 = warp_take32(B.tickets + 1, lane_id);
+        if (w0 >= LR.n) break;
+        const uint32_t ri = w0 + lane_id;
+        if (!B.tickets) w0 += gridDim.x * blockDim.x;
+        if (ri >= LR.n) continue;
         const uint32_t rec = LR[ri];
         if (!lane_match(B, rec, lane)) continue;
         const uint32_t off = B.offsets[rec];
