@@ -1049,10 +1049,12 @@ static int launch_tables(bqc_engine* e, const DeviceBatch& d, const BatchLaunch&
         int grid = (int)std::min<uint64_t>((n + kStatsThreads - 1) / kStatsThreads, (uint64_t)e->n_sm * BL.bps);
         {
             ProfScope prof(e, 0);
-            if (B.index) k_stats<0><<<grid, kStatsThreads, BL.stats_smem0, e->compute>>>(E, B, lane);   // a lane's records are not contiguous: no span to stage
-            else if (BL.staged && e->tune_stats_stage == 2) k_stats<2><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
-            else if (BL.staged) k_stats<1><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
-            else k_stats<0><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, B, lane);
+            BatchView Bs = B;
+            if (e->tune_tickets == 2) Bs.tickets = nullptr;   // (A/B: tickets for the 8-mer and sketch kernels only)
+            if (B.index) k_stats<0><<<grid, kStatsThreads, BL.stats_smem0, e->compute>>>(E, Bs, lane);   // a lane's records are not contiguous: no span to stage
+            else if (BL.staged && e->tune_stats_stage == 2) k_stats<2><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, Bs, lane);
+            else if (BL.staged) k_stats<1><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, Bs, lane);
+            else k_stats<0><<<grid, kStatsThreads, BL.stats_smem, e->compute>>>(E, Bs, lane);
         }
         int g8 = (int)std::min<uint64_t>((n + kEightThreads - 1) / kEightThreads, (uint64_t)e->n_sm);
         if (g8 < 1) g8 = 1;
