@@ -205,6 +205,39 @@ def test_sam_on_stdin_gives_the_same_bamqc_as_the_bam_file(tmp_path):
     assert not util.diff_bamqc(tmp_path / "h_oracle.bamqc", tmp_path / "h_sam.bamqc")
 
 
+def test_large_deletions(tmp_path):
+    """Summed deletion lengths up to 4095 bp in one read: the reference resizes `deletions` to the largest value seen
+    (src/QualityCheck.hpp:261-265) and the engine's histogram has 4096 bins.  (Reads like these run past the reference's
+    two coverage windows, where src/OverallNumbers.hpp:126-129 writes outside `v2`; the oracle and the engine drop those
+    writes, the reference's own code aborts in free() -- so the oracle is the checker here.)  From 4096 bp on the engine
+    reports BQC_ERR_UNSUPPORTED."""
+    genome = util.golden_genome()
+    fasta = tmp_path / "ref.fa"
+    genome.write_fasta(fasta)
+
+    def records(dels):
+        recs = []
+        for i, dl in enumerate(dels):
+            recs.append(util.bam_record(name=f"d{i}", flag=0x63 if i % 2 == 0 else 0x93, pos=1000 + 40 * i, npos=1400, tlen=500,
+                                        cigar=((50, "M"), (dl, "D"), (100, "M")),
+                                        tags=(("RG", "Z", "L1"), ("NM", "i", dl + (i % 3)), ("AS", "C", 140))))
+        return recs
+
+    recs = records((3, 2000, 4095, 7))
+    recs.append(util.bam_record(name="dd", flag=0x63, pos=1300, npos=1500, tlen=400, cigar=((30, "M"), (2000, "D"), (60, "M"), (2000, "D"), (60, "M")),
+                                tags=(("RG", "Z", "L1"), ("NM", "i", 4000), ("AS", "C", 140))))   # two deletions in one read add up
+    open(tmp_path / "d.ubam", "wb").write(util.bam_stream(recs))
+    o = util.run_oracle(tmp_path / "d.ubam", fasta, tmp_path / "oracle.bamqc", chroms="chr1")
+    assert o.returncode == 0, o.stderr
+    g = util.run_cli(["-r", fasta, "-c", "chr1", "-o", tmp_path / "gpu.bamqc", tmp_path / "d.ubam"])
+    assert g.returncode == 0, g.stderr
+    diffs = util.diff_bamqc(tmp_path / "oracle.bamqc", tmp_path / "gpu.bamqc")
+    assert not diffs, "\n".join(diffs)
+    open(tmp_path / "e.ubam", "wb").write(util.bam_stream(records((3, 4096))))
+    g = util.run_cli(["-r", fasta, "-c", "chr1", "-o", tmp_path / "e.bamqc", tmp_path / "e.ubam"])
+    assert g.returncode != 0 and "capacit" in g.stderr
+
+
 def test_records_larger_than_a_framing_window(tmp_path):
     """Records of 6-20 KB (long aux arrays) between ordinary ones: speculation windows of 4 KiB without any record
     start, chains that jump over several windows, through the raw-stream and the BGZF paths of the CLI."""
