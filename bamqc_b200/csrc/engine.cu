@@ -234,7 +234,9 @@ struct bqc_engine {
                                                          // compute stream, 2 = by batch size.  Measured on one box, kernel-only M records/s, one resident batch
                                                          // of 64 / 128 / 256 / 512 / 1024 / 2048 MB: own stream 469 / 587 / 678 / 732 / 785 / 806, compute stream
                                                          // 416 / 540 / 643 / 728 / 794 / 823; three 1 GB batches (cfg 2): 12.0 ms on one stream, 12.5 on two
-    int tune_tickets = 1;                                // BQC_TICKETS=0: static grid-stride split of the records in the persistent table kernels (A/B)
+    int tune_tickets = 1;                                // BQC_TICKETS: 1 = the persistent table kernels take warps of 32 records from ticket counters, 0 = static
+                                                         // grid-stride split, 2 = tickets for k_eightmer / k_sketch32v2 only.  cfg 2, same box: 11.50 ms (1) vs 12.16
+                                                         // (0) per 10 M records; cfg 3 at 30x on 2-8 GPUs: k_stats 9 % slower with tickets
     uint32_t* d_tab_tickets = nullptr;                   // [256] work counters of the table kernels (kernels.cuh BatchView::tickets)
     bool cov_overlap_now = false;                        // decision for the batch in flight (run_device_batch)
     uint64_t records_seen = 0, frames_repaired = 0;
