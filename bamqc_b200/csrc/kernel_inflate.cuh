@@ -22,6 +22,7 @@
 // resident input words (no refill between the length and the distance code), field extraction with bfe, table
 // entries laid out in bytes, the modulo only for overlapping matches.
 #pragma once
+#include "inflate_bits.h"
 
 namespace bqc {
 
@@ -105,60 +106,8 @@ __device__ __forceinline__ uint32_t inflate_lds(uint32_t table_saddr, uint32_t w
     return e;
 }
 
-// The input as three consecutive aligned 32-bit words and a bit position: a 32-bit window is one funnel shift,
-// dropping bits is one add, and a whole trip (up to four literals, or a length and a distance with their extra
-// bits) is decoded between two refills.  Identical in every lane.
-struct BitWin {
-    const uint32_t* base;   // aligned word that holds the first payload byte
-    uint32_t wi;            // index of the word in nx
-    uint32_t wlim;          // last word index that may be loaded (payload + one refill of slack)
-    uint32_t lo, hi, nx;
-    uint32_t bp;            // bits of `lo` consumed; < 32 after norm(), < 96 always
-    uint32_t bit0;          // misalignment of the payload in bits
-    __device__ __forceinline__ uint32_t load(uint32_t w) const { return __ldg(base + (w < wlim ? w : wlim)); }
-    __device__ __forceinline__ void seek(uint32_t byte) {
-        const uint32_t bits = bit0 + byte * 8u, w = bits >> 5;
-        bp = bits & 31u;
-        lo = load(w);
-        hi = load(w + 1u);
-        nx = load(w + 2u);
-        wi = w + 2u;
-    }
-    __device__ __forceinline__ void init(const uint8_t* p, uint32_t clen) {
-        const uintptr_t a = (uintptr_t)p;
-        base = (const uint32_t*)(a & ~(uintptr_t)3);
-        bit0 = (uint32_t)(a & 3) * 8u;
-        wlim = (bit0 + clen * 8u + 31u) / 32u + 2u;
-        seek(0);
-    }
-    __device__ __forceinline__ void shift() {
-        lo = hi;
-        hi = nx;
-        ++wi;
-        nx = load(wi);
-        bp -= 32u;
-    }
-    __device__ __forceinline__ void norm() {
-        if (bp >= 32u) {
-            shift();
-            if (bp >= 32u) shift();   // a match with long codes and many extra bits (up to 48 bits in one trip)
-        }
-    }
-    __device__ __forceinline__ uint32_t win() const { return __funnelshift_r(lo, hi, bp); }   // 32 valid bits after norm()
-    // 32 bits from bp for 32 <= bp < 64 as well (the distance code right after a length, without a refill)
-    __device__ __forceinline__ uint32_t win2() const {
-        const bool up = bp >= 32u;
-        return __funnelshift_r(up ? hi : lo, up ? nx : hi, bp);   // the shift amount wraps at 32
-    }
-    __device__ __forceinline__ uint32_t take(uint32_t n) {  // n <= 16 (header fields)
-        norm();
-        const uint32_t v = win() & ((1u << n) - 1u);
-        bp += n;
-        return v;
-    }
-    __device__ __forceinline__ uint32_t bits_used() const { return (wi - 2u) * 32u + bp - bit0; }
-    __device__ __forceinline__ uint32_t bytes_used() const { return (bits_used() + 7u) >> 3; }   // a partial byte counts
-};
+// BitWin, the bit reader (three resident input words and a bit position), lives in inflate_bits.h: host/device code,
+// checked on the CPU by tests/inflate_selftest.cpp.
 
 // Build the decoding tables of one alphabet from lens[0..n): count[], sorted[], the primary table (PB index bits)
 // and the entry state of the canonical search for longer codes.  WHICH: 0 literal/length, 1 distance, 2 code
